@@ -1,0 +1,128 @@
+"""Restatement of the HandRecoveryFlow geometry glue -- TEST INFRASTRUCTURE ONLY.
+
+Torch-CPU fp32 restatement of stages R0 and R4-R7 of SURVEY.md section 8a
+(paths relative to /root/reference/HOIG_HOv3):
+
+* R0  ``utils/nmr.py:109-140`` orthographic_proj_withz_idrot, ``:506`` y flip,
+      ``thirdparty/neural_renderer/neural_renderer/look_at.py:6-62``,
+      ``.../vertices_to_faces.py:4-22``
+* R4  ``utils/nmr.py:567-595`` encode_fim / encode_sem (fim=-1 hits the last row)
+* R5  ``models/trainer.py:71-72,109-136`` one-hot seg, hand/bg masks, cond split
+* R6  ``utils/util.py:142-158`` morph (erode)
+* R7  ``utils/nmr.py:874-968`` cal_bc_transform (T only; O is discarded by the
+      caller, trainer.py:80) and ``trainer.py:81`` T_hand
+
+Pinned by the reference's look_at KAT (tests/test_look_at.py:10-19) in
+tests/test_oracle_geometry.py; the remaining functions have no reference
+tests ("parity unpinned" by the reference) and are restated
+op-for-op from the cited lines.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+EYE_Z = -(1.0 / math.tan(math.radians(30.0)) + 1.0)  # utils/nmr.py:357
+
+
+def project(verts: torch.Tensor, cam: torch.Tensor, offset_z: float = 0.0) -> torch.Tensor:
+    """utils/nmr.py:109-140.  verts (B,V,3) OpenGL coords, cam (B,15)."""
+    bs = cam.shape[0]
+    cam_mat = cam[:, 0:9].reshape(bs, 3, 3)
+    trans = cam[:, 9:].reshape(bs, 2, 3)
+    cc = torch.tensor([[1.0, 0, 0], [0, -1.0, 0], [0, 0, -1.0]], dtype=torch.float32)[None].repeat(bs, 1, 1)
+    p = torch.einsum("ijk,imk->ijm", [verts, cc])
+    pp = torch.einsum("ijk,imk->ijm", [p, cam_mat])
+    z = pp[:, :, 2]
+    xy = torch.stack([pp[:, :, 0] / z, pp[:, :, 1] / z], 2)
+    xy1 = torch.cat([xy, torch.ones_like(xy)[:, :, 1:2]], 2)
+    xyt = torch.einsum("ijk,imk->ijm", [trans, xy1]).permute(0, 2, 1)
+    xyt = xyt / 255.0 * 2 - 1
+    return torch.cat((xyt, p[:, :, 2:3] + offset_z), 2)
+
+
+def look_at(vertices: torch.Tensor, eye, at=(0, 0, 0), up=(0, 1, 0)) -> torch.Tensor:
+    """thirdparty/neural_renderer/neural_renderer/look_at.py:6-62."""
+    eye = torch.as_tensor(np.asarray(eye, np.float32))
+    at = torch.as_tensor(np.asarray(at, np.float32))
+    up = torch.as_tensor(np.asarray(up, np.float32))
+    B = vertices.shape[0]
+    eye, at, up = (t[None].repeat(B, 1) if t.ndim == 1 else t for t in (eye, at, up))
+    z = F.normalize(at - eye, eps=1e-5)
+    x = F.normalize(torch.cross(up, z, dim=1), eps=1e-5)
+    y = F.normalize(torch.cross(z, x, dim=1), eps=1e-5)
+    r = torch.stack([x, y, z], 1)
+    return torch.matmul(vertices - eye[:, None, :], r.transpose(1, 2))
+
+
+def vertices_to_faces(vertices: torch.Tensor, faces: torch.Tensor) -> torch.Tensor:
+    """thirdparty/neural_renderer/neural_renderer/vertices_to_faces.py:4-22."""
+    B, nv = vertices.shape[:2]
+    idx = faces.long() + (torch.arange(B) * nv)[:, None, None]
+    return vertices.reshape(B * nv, 3)[idx]
+
+
+def render_faces(cam: torch.Tensor, verts: torch.Tensor, faces_idx: torch.Tensor) -> torch.Tensor:
+    """utils/nmr.py:496-511 up to the rasterizer call: (B,F,3,3) camera-space faces."""
+    pv = project(verts, cam)
+    pv = pv.clone()
+    pv[:, :, 1] *= -1
+    v = look_at(pv, [0.0, 0.0, EYE_Z])
+    if faces_idx.ndim == 2:
+        faces_idx = faces_idx[None].repeat(cam.shape[0], 1, 1)
+    return vertices_to_faces(v, faces_idx)
+
+
+def encode(fim: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    """utils/nmr.py:567-595: ``table[fim.long()]`` then NCHW; -1 wraps to the last (bg) row."""
+    return table[fim.long()].permute(0, 3, 1, 2)
+
+
+def erode(mask: torch.Tensor, ks: int) -> torch.Tensor:
+    """utils/util.py:142-153 (mode='erode')."""
+    pad = ks // 2
+    m = F.pad(mask, [pad] * 4, value=1.0)
+    out = F.conv2d(m, torch.ones(1, 1, ks, ks))
+    return (out == ks * ks).float()
+
+
+def bc_transform(src_f2pts: torch.Tensor, dst_fim: torch.Tensor, dst_wim: torch.Tensor) -> torch.Tensor:
+    """utils/nmr.py:874-925: T = sum_k src_f2pts[fim][k] * wim[k] where fim != -1, else -2."""
+    B, H, W = dst_fim.shape
+    T = -2 * torch.ones(B, H * W, 2)
+    for i in range(B):
+        f = dst_fim[i].long().reshape(-1)
+        w = dst_wim[i].reshape(-1, 3)
+        m = f != -1
+        T[i, m] = (src_f2pts[i][f[m]] * w[m][:, :, None]).sum(dim=1)
+    return T.view(B, H, W, 2)
+
+
+def condition_maps(faces_src, fim_src, fim_ref, wim_ref, map_fn, sem_full, n_hand_faces: int = 1538):
+    """models/trainer.py:66-81,109-124 for a batch (the reference loops per sample).
+
+    Returns a dict with cond/seg/masks for src and ref plus T_hand.
+    """
+    f2v = faces_src[:, :, :, 0:2].clone()
+    f2v[:, :, :, 1] *= -1
+    out = {}
+    for tag, fim in (("src", fim_src), ("ref", fim_ref)):
+        cond = encode(fim, map_fn)
+        sem = encode(fim, sem_full)
+        out[f"{tag}_cond"] = cond
+        out[f"{tag}_seg"] = torch.cat([(sem == i).float() for i in range(1, 16)], 1)
+        out[f"{tag}_mask_hand"] = erode(1 - ((fim != -1) & (fim < n_hand_faces))[:, None].float(), 3)
+        out[f"{tag}_mask_bg"] = erode(cond[:, -1:], 3)
+        out[f"{tag}_bg_mask15"] = erode(cond[:, -1:], 15)
+        hm = (cond[:, :1] < 1.5).float()
+        out[f"{tag}_cond_hand"] = torch.cat([hm * cond[:, :2], cond[:, 2:] + 1 - hm], 1)
+        om = (cond[:, :1] > 1.5).float()
+        out[f"{tag}_cond_obj"] = torch.cat([om * cond[:, :2], cond[:, 2:] + 1 - om], 1)
+    T = bc_transform(f2v, fim_ref, wim_ref)
+    mh = out["ref_mask_hand"][:, 0][:, :, :, None]
+    out["T"] = T
+    out["T_hand"] = T * (mh == 0) + (-2) * torch.ones_like(T) * (mh == 1)
+    return out
