@@ -1,0 +1,111 @@
+"""ctypes binding of libhoig_b200.so (the C ABI in include/hoig_b200.h).
+
+The library is built in-tree by ``hoig_b200/build.py`` (nvcc, sm_100a).  There
+is no fallback: if it is missing or the device is not a B200-class GPU the
+first op raises ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_C", "libhoig_b200.so")
+
+HOIG_F32, HOIG_BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
+CONV, CONV_TRANSPOSED, CONV_LOCAL_ATTN = 0, 1, 2
+
+
+class ConvDesc(Structure):
+    """Mirror of ``hoigConvDesc``."""
+    _fields_ = [
+        ("dtype", c_int), ("mode", c_int),
+        ("N", c_int), ("H", c_int), ("W", c_int),
+        ("C0", c_int), ("C1", c_int),
+        ("OH", c_int), ("OW", c_int), ("Cout", c_int),
+        ("KH", c_int), ("KW", c_int), ("stride", c_int), ("pad", c_int),
+        ("src0", c_void_p), ("ld0", c_int64),
+        ("src1", c_void_p), ("ld1", c_int64),
+        ("weight", c_void_p),
+        ("bias", c_void_p),
+        ("act", c_int),
+        ("residual", c_void_p), ("ldr", c_int64),
+        ("dst", c_void_p), ("ldd", c_int64),
+        ("stats", c_void_p),
+        ("flow", c_void_p),
+    ]
+
+
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "hoig_version": (c_char_p, []),
+    "hoig_last_error": (c_char_p, []),
+    "hoig_check_device": (c_int, []),
+    "hoig_rasterize_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "hoig_rasterize_fim_wim": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_size_t, c_void_p]),
+    "hoig_face_inv": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "hoig_project_faces": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "hoig_condition_maps": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_void_p]),
+    "hoig_bc_transform": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "hoig_erode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "hoig_block_extract_f32": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
+    "hoig_local_attn_reshape_f32": (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
+    "hoig_conv_packed_dims": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
+    "hoig_conv2d": (c_int, [POINTER(ConvDesc), c_void_p]),
+    "hoig_conv2d_simt": (c_int, [POINTER(ConvDesc), c_void_p]),
+    "hoig_nchw_to_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "hoig_nhwc_to_nchw": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "hoig_seg_resize_nearest": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_int,
+                                        c_int, c_void_p]),
+    "hoig_plane_stats": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "hoig_instnorm_apply": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                    c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "hoig_resize_flow": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "hoig_attn_finish": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                 c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "hoig_grid_sample": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int,
+                                 c_int, c_int, c_void_p]),
+    "hoig_composite": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+_device_checked = False
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the library and bind every entry point (no CUDA call is made)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -m hoig_b200.build` (nvcc, sm_100a). "
+                "hoig_b200 has no CPU or PyTorch fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError here == header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().hoig_last_error().decode(errors="replace")
+        raise RuntimeError(f"hoig_b200.{what} failed (status {status}): {msg}")
+
+
+def lib() -> ctypes.CDLL:
+    """Library handle for compute calls; verifies once that the device is sm_100."""
+    global _device_checked
+    L = load()
+    if not _device_checked:
+        check(L.hoig_check_device(), "check_device")
+        _device_checked = True
+    return L

@@ -1,0 +1,571 @@
+// conv_umma.cu -- bf16 implicit-GEMM convolution on 5th-gen tensor cores (sm_100a).
+//
+// D[128 pixels][BN channels] (fp32, TMEM) += A[128][64] (bf16, smem) * W[BN][64]^T (bf16, smem)
+// per k-block, tcgen05.mma.cta_group::1.kind::f16, UMMA 128 x BN x 16, BN <= 256.
+//
+// Persistent, warp-specialised CTA (one per SM, 320 threads):
+//   warps 0-3  epilogue: tcgen05.ld TMEM -> regs, +bias (+residual), activation, bf16 store,
+//              per-plane sum / sum-of-squares (instance-norm statistics) by warp-transpose
+//              reduction; overlaps the next tile's main loop (two TMEM accumulator stages)
+//   warps 4-7  A producers in "gather" mode: one output pixel (A row) per thread, 16-byte
+//              cp.async chunks written straight into the 128B-swizzled K-major layout the
+//              UMMA descriptor expects (zero-fill = padding); in local-attention mode the
+//              BlockExtractor bilinear taps are blended in registers and stored to smem.
+//   warp  8    TMA producer: weights (2D map, always) and, in "TMA-A" mode (stride-1 convs
+//              with Cin % 64 == 0), the activation tile itself as one 4D box per (tap, 64
+//              channels): out-of-bounds box rows are zero-filled by TMA == conv padding.
+//   warp  9    TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit -> mbarriers
+//
+// smem ring: STAGES x (A 16 KB + B BN*128 B), 1024-byte aligned for SWIZZLE_128B.
+#include <cuda.h>
+
+#include "conv_common.cuh"
+
+namespace hoig {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int EPI_WARPS = 4, PROD_WARPS = 4;
+constexpr int TMA_WARP = 8, MMA_WARP = 9;
+constexpr int THREADS = 320;
+constexpr int MAX_STAGES = 8;
+constexpr int LOOKAHEAD = 3;           // cp.async groups in flight per producer thread
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+struct UmmaParams {
+    ConvParams c;
+    int BN;          // UMMA N (multiple of 16, <= 256)
+    int n_tiles;     // ceil(Npad / BN)
+    int m_tiles;     // N * tiles_per_image
+    int k_blocks;    // Kpad / 64
+    int stages;
+    int tma_a;       // 1: activations by TMA boxes, 0: cp.async / register gather
+    int chunks_per_tap;  // Cin / 8
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug traps (-> launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        if ((spin & 0x3ff) == 0x3ff) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 6000000000ll) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src, uint32_t src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1):
+// start address >> 4 | LBO (unused for swizzled K-major, canonical 1) | SBO = 1024 B (8 rows x 128 B)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffff) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 16 values per lane x 32 lanes -> column totals: after the call lane L holds the total of
+// column  8*b4 + 4*b3 + 2*b2 + b1  (bits of L), duplicated on lanes L and L^1.
+__device__ __forceinline__ float transpose_reduce16(const float v[16], int lane)
+{
+    float a[8], b[4], c[2];
+    const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = h4 ? v[i] : v[i + 8];
+        const float keep = h4 ? v[i + 8] : v[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = h3 ? a[i] : a[i + 4];
+        const float keep = h3 ? a[i + 4] : a[i];
+        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = h2 ? b[i] : b[i + 2];
+        const float keep = h2 ? b[i + 2] : b[i];
+        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    const float send = h1 ? c[0] : c[1];
+    const float keep = h1 ? c[1] : c[0];
+    float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;
+}
+
+// ------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(THREADS, 1)
+conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
+                 const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1)
+{
+    extern __shared__ __align__(1024) uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ float s_stats[2][256];
+
+    const ConvParams &p = P.c;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int BN = P.BN;
+    const int stage_bytes = A_STAGE_BYTES + BN * BK * 2;
+    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    const uint32_t smem_base = smem_u32(smem);
+    const int total_tiles = P.m_tiles * P.n_tiles;
+    const int npix = p.OH * p.OW;
+
+    if (threadIdx.x == 0) {
+        const uint32_t full_count = P.tma_a ? 1u : (uint32_t)(PROD_WARPS * 32 + 1);
+        for (int s = 0; s < P.stages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), full_count);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(&tfull_bar[a]), 1);
+            mbar_init(smem_u32(&tempty_bar[a]), EPI_WARPS * 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 256) { s_stats[0][threadIdx.x] = 0.f; s_stats[1][threadIdx.x] = 0.f; }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_smem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp == TMA_WARP && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        if (P.tma_a) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a0) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a1) : "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
+        // =============================================== A producers (gather mode)
+        if (!P.tma_a) {
+            const int row = threadIdx.x - EPI_WARPS * 32;  // 0..127 : A row == pixel of the tile
+            const uint32_t row_off = (uint32_t)row * 128u;
+            const uint32_t sw = (uint32_t)(row & 7);
+            uint32_t it = 0;  // running k-block counter across tiles
+            int pending = 0;  // k-blocks issued but not yet signalled
+            uint32_t sig_it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / P.n_tiles;
+                const int n_img = mt / p.tiles_per_image;
+                const int pix = (mt % p.tiles_per_image) * BM + row;
+                const bool valid = pix < npix;
+                const int oy = valid ? pix / p.OW : 0, ox = valid ? pix % p.OW : 0;
+                for (int kb = 0; kb < P.k_blocks; ++kb, ++it) {
+                    const int s = it % P.stages;
+                    mbar_wait(smem_u32(&empty_bar[s]), ((it / P.stages) & 1) ^ 1);
+                    const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes + row_off;
+                    if (p.mode != HOIG_CONV_LOCAL_ATTN) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int k0 = kb * BK + j * 8;
+                            const void *src = p.src0;
+                            uint32_t bytes = 0;
+                            if (valid && k0 < p.K) {
+                                const int tap = k0 / p.Cin;
+                                int c = k0 - tap * p.Cin;
+                                const int r = tap / p.KW, sx = tap - r * p.KW;
+                                int iy, ix;
+                                bool ok;
+                                if (p.mode == HOIG_CONV) {
+                                    iy = oy * p.stride - p.pad + r; ix = ox * p.stride - p.pad + sx;
+                                    ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                                } else {
+                                    const int ty = oy + p.pad - r, tx = ox + p.pad - sx;
+                                    ok = ty >= 0 && tx >= 0 && (ty % p.stride) == 0 && (tx % p.stride) == 0;
+                                    iy = ty / p.stride; ix = tx / p.stride;
+                                    ok = ok && iy < p.H && ix < p.W;
+                                }
+                                if (ok) {
+                                    const int64_t pixoff = (int64_t)(n_img * p.H + iy) * p.W + ix;
+                                    if (c >= p.C0) src = static_cast<const __nv_bfloat16 *>(p.src1) + pixoff * p.ld1 + (c - p.C0);
+                                    else           src = static_cast<const __nv_bfloat16 *>(p.src0) + pixoff * p.ld0 + c;
+                                    bytes = 16;
+                                }
+                            }
+                            cp_async_16(a_dst + (((uint32_t)j ^ sw) << 4), src, bytes);
+                        }
+                    } else {
+                        // local attention: chunks of [target | source] channels per 5x5 tap
+                        // (extract_attn.py:24-26); target taps are plain copies (zero flow),
+                        // source taps are the BlockExtractor bilinear blend, done in registers.
+                        const int64_t plane = (int64_t)n_img * p.H * p.W;
+                        int cached_tap = -1;
+                        BETap t;
+#pragma unroll 2
+                        for (int j = 0; j < 8; ++j) {
+                            const int k0 = kb * BK + j * 8;
+                            const uint32_t dst_j = a_dst + (((uint32_t)j ^ sw) << 4);
+                            if (!valid || k0 >= p.K) { cp_async_16(dst_j, p.src0, 0); continue; }
+                            const int tap = k0 / p.Cin;
+                            int c = k0 - tap * p.Cin;
+                            const int r = tap / p.KW, sx = tap - r * p.KW;
+                            if (c < p.C0) {
+                                const int iy = max(min(oy + r - p.KH / 2, p.H - 1), 0), ix = max(min(ox + sx - p.KW / 2, p.W - 1), 0);
+                                cp_async_16(dst_j, static_cast<const __nv_bfloat16 *>(p.src0) + (plane + (int64_t)iy * p.W + ix) * p.ld0 + c, 16);
+                            } else {
+                                c -= p.C0;
+                                if (tap != cached_tap) {
+                                    const float *fl = p.flow + (plane + (int64_t)oy * p.W + ox) * 2;
+                                    t = be_tap(fl[0], fl[1], oy, ox, r, sx, p.KH, p.H, p.W);
+                                    cached_tap = tap;
+                                }
+                                const __nv_bfloat16 *sb = static_cast<const __nv_bfloat16 *>(p.src1) + plane * p.ld1 + c;
+                                float acc[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    float u[8];
+                                    load8(sb + (int64_t)t.idx[q] * p.ld1, u);
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) acc[e] = __fmaf_rn(t.w[q], u[e], acc[e]);
+                                }
+                                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst_j),
+                                             "r"(pack_bf16x2(acc[0], acc[1])), "r"(pack_bf16x2(acc[2], acc[3])),
+                                             "r"(pack_bf16x2(acc[4], acc[5])), "r"(pack_bf16x2(acc[6], acc[7])) : "memory");
+                            }
+                        }
+                    }
+                    cp_async_commit();
+                    ++pending;
+                    if (pending > LOOKAHEAD) {
+                        cp_async_wait<LOOKAHEAD>();
+                        fence_proxy_async();
+                        mbar_arrive(smem_u32(&full_bar[sig_it % P.stages]));
+                        ++sig_it; --pending;
+                    }
+                }
+            }
+            cp_async_wait<0>();
+            fence_proxy_async();
+            while (pending > 0) {
+                mbar_arrive(smem_u32(&full_bar[sig_it % P.stages]));
+                ++sig_it; --pending;
+            }
+        }
+    } else if (warp == TMA_WARP) {
+        // ======================================================== TMA producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            const uint32_t tx_bytes = (uint32_t)(BN * BK * 2) + (P.tma_a ? (uint32_t)A_STAGE_BYTES : 0u);
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / P.n_tiles, nt = tile % P.n_tiles;
+                const int n_img = mt / p.tiles_per_image;
+                const int pix0 = (mt % p.tiles_per_image) * BM;
+                const int oy0 = pix0 / p.OW, ox0 = pix0 % p.OW;
+                for (int kb = 0; kb < P.k_blocks; ++kb, ++it) {
+                    const int s = it % P.stages;
+                    mbar_wait(smem_u32(&empty_bar[s]), ((it / P.stages) & 1) ^ 1);
+                    const uint32_t bar = smem_u32(&full_bar[s]);
+                    const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
+                    mbar_arrive_expect_tx(bar, tx_bytes);
+                    if (P.tma_a) {
+                        const int k0 = kb * BK;
+                        const int tap = k0 / p.Cin;
+                        const int c = k0 - tap * p.Cin;
+                        const int r = tap / p.KW, sx = tap - r * p.KW;
+                        if (c >= p.C0) tma_load_4d(a_dst, &map_a1, bar, c - p.C0, ox0 + sx - p.pad, oy0 + r - p.pad, n_img);
+                        else           tma_load_4d(a_dst, &map_a0, bar, c, ox0 + sx - p.pad, oy0 + r - p.pad, n_img);
+                    }
+                    tma_load_2d(a_dst + A_STAGE_BYTES, &map_w, bar, kb * BK, nt * BN);
+                }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // ========================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+                const uint32_t acc = tcount & 1;
+                mbar_wait(smem_u32(&tempty_bar[acc]), ((tcount >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)BN;
+                for (int kb = 0; kb < P.k_blocks; ++kb, ++it) {
+                    const int s = it % P.stages;
+                    mbar_wait(smem_u32(&full_bar[s]), (it / P.stages) & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
+                    const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(smem_u32(&empty_bar[s]));   // frees the smem stage when these MMAs retire
+                }
+                umma_commit(smem_u32(&tfull_bar[acc]));     // accumulator complete
+            }
+        }
+    } else {
+        // ============================================================ epilogue
+        const int row = warp * 32 + lane;  // TMEM lane == tile row; warp w may touch lanes 32w..32w+31
+        const __nv_bfloat16 *res = static_cast<const __nv_bfloat16 *>(p.residual);
+        __nv_bfloat16 *dst = static_cast<__nv_bfloat16 *>(p.dst);
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            const int mt = tile / P.n_tiles, nt = tile % P.n_tiles;
+            const int n_img = mt / p.tiles_per_image;
+            const int pix = (mt % p.tiles_per_image) * BM + row;
+            const bool valid = pix < npix;
+            const int64_t m = (int64_t)n_img * npix + pix;
+            const uint32_t acc = tcount & 1;
+            mbar_wait(smem_u32(&tfull_bar[acc]), (tcount >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (uint32_t)BN;
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                const int n0 = nt * BN + c0;
+                uint32_t r[16];
+                tmem_ld16(t_row + (uint32_t)c0, r);
+                tmem_ld_wait();
+                if (n0 >= p.Cout) continue;   // warp-uniform
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                if (p.bias) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += (n0 + j < p.Cout) ? __ldg(p.bias + n0 + j) : 0.f;
+                }
+                const bool full = n0 + 16 <= p.Cout;
+                if (res && valid) {
+                    if (full) {
+                        float u[8];
+                        load8(res + m * p.ldr + n0, u);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] += u[j];
+                        load8(res + m * p.ldr + n0 + 8, u);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[8 + j] += u[j];
+                    } else {
+                        for (int j = 0; j < 16; ++j)
+                            if (n0 + j < p.Cout) v[j] += __bfloat162float(res[m * p.ldr + n0 + j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = round_to<__nv_bfloat16>(apply_act(v[j], p.act));
+                if (valid) {
+                    if (full && ((p.ldd & 7) == 0)) {
+                        store8(dst + m * p.ldd + n0, v);
+                        store8(dst + m * p.ldd + n0 + 8, v + 8);
+                    } else {
+                        for (int j = 0; j < 16; ++j)
+                            if (n0 + j < p.Cout) dst[m * p.ldd + n0 + j] = __float2bfloat16_rn(v[j]);
+                    }
+                }
+                if (p.stats) {
+                    float q[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { v[j] = valid ? v[j] : 0.f; q[j] = v[j] * v[j]; }
+                    const float cs = transpose_reduce16(v, lane);
+                    const float cq = transpose_reduce16(q, lane);
+                    if ((lane & 1) == 0) {
+                        const int col = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                        atomicAdd(&s_stats[0][col], cs);
+                        atomicAdd(&s_stats[1][col], cq);
+                    }
+                }
+            }
+            // accumulator drained: hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(smem_u32(&tempty_bar[acc]));
+            if (p.stats) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int i = threadIdx.x; i < 2 * BN; i += EPI_WARPS * 32) {
+                    const int which = i / BN, col = i % BN;
+                    const int n = nt * BN + col;
+                    if (n < p.Cout) atomicAdd(&p.stats[((int64_t)n_img * p.Cout + n) * 2 + which], (double)s_stats[which][col]);
+                    s_stats[which][col] = 0.f;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// --------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+int make_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
+             const cuuint32_t *box, const char *what)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return HOIG_ERR_CUDA; }
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), dims, strides_bytes, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r); return HOIG_ERR_CUDA; }
+    return HOIG_OK;
+}
+
+int g_force_gather = -1;
+
+}  // namespace
+
+int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
+{
+    UmmaParams P;
+    int st = fill_conv_params(d, BM, &P.c);
+    if (st != HOIG_OK) return st;
+    const ConvParams &p = P.c;
+    HOIG_REQUIRE(p.Npad <= 4096, "conv2d: Cout too large");
+    P.BN = p.Npad <= 256 ? p.Npad : 256;
+    P.n_tiles = ceil_div(p.Npad, P.BN);
+    P.m_tiles = p.N * p.tiles_per_image;
+    P.k_blocks = p.Kpad / BK;
+    P.chunks_per_tap = p.Cin / 8;
+    const int stage_bytes = A_STAGE_BYTES + P.BN * BK * 2;
+    P.stages = (SMEM_BUDGET - 1024) / stage_bytes;
+    if (P.stages > MAX_STAGES) P.stages = MAX_STAGES;
+    HOIG_REQUIRE(P.stages >= LOOKAHEAD + 1, "conv2d: not enough shared memory stages");
+
+    if (g_force_gather < 0) {
+        const char *e = getenv("HOIG_UMMA_GATHER_ONLY");
+        g_force_gather = (e && e[0] == '1') ? 1 : 0;
+    }
+    const int64_t npix = (int64_t)p.OH * p.OW;
+    const bool rect = (p.OW % BM == 0) || (BM % p.OW == 0);
+    P.tma_a = (!g_force_gather && p.mode == HOIG_CONV && p.stride == 1 && p.C0 % 64 == 0 && p.C1 % 64 == 0 && rect &&
+               p.OH == p.H && p.OW == p.W && npix % BM == 0)
+                  ? 1 : 0;
+
+    CUtensorMap map_w, map_a0, map_a1;
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)p.Kpad, (cuuint64_t)p.Npad};
+        const cuuint64_t strides[1] = {(cuuint64_t)p.Kpad * 2};
+        const cuuint32_t box[2] = {BK, (cuuint32_t)P.BN};
+        st = make_map(&map_w, p.weight, 2, dims, strides, box, "weights");
+        if (st != HOIG_OK) return st;
+    }
+    map_a0 = map_w; map_a1 = map_w;
+    if (P.tma_a) {
+        const int bw = p.OW < BM ? p.OW : BM;
+        const int bh = BM / bw;
+        const cuuint32_t box[4] = {BK, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+        {
+            const cuuint64_t dims[4] = {(cuuint64_t)p.C0, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+            const cuuint64_t strides[3] = {(cuuint64_t)p.ld0 * 2, (cuuint64_t)p.W * p.ld0 * 2, (cuuint64_t)p.H * p.W * p.ld0 * 2};
+            st = make_map(&map_a0, p.src0, 4, dims, strides, box, "activations0");
+            if (st != HOIG_OK) return st;
+        }
+        if (p.C1 > 0) {
+            const cuuint64_t dims[4] = {(cuuint64_t)p.C1, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+            const cuuint64_t strides[3] = {(cuuint64_t)p.ld1 * 2, (cuuint64_t)p.W * p.ld1 * 2, (cuuint64_t)p.H * p.W * p.ld1 * 2};
+            st = make_map(&map_a1, p.src1, 4, dims, strides, box, "activations1");
+            if (st != HOIG_OK) return st;
+        }
+    }
+
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET) != cudaSuccess)
+            return check_launch("conv_umma smem attribute");
+    }
+    const int total = P.m_tiles * P.n_tiles;
+    const int grid = total < num_sms ? total : num_sms;
+    const size_t smem = (size_t)P.stages * stage_bytes + 1024;
+    conv_umma_kernel<<<grid, THREADS, smem, stream>>>(P, map_w, map_a0, map_a1);
+    return check_launch("conv_umma_kernel");
+}
+
+}  // namespace hoig

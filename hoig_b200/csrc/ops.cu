@@ -1,0 +1,500 @@
+// ops.cu -- bandwidth-bound stages of the generator forward and the two
+// reference op boundaries (BlockExtractor / LocalAttnReshape forward).
+// All kernels move 8-channel (16/32-byte) chunks of NHWC rows so that warps
+// issue fully coalesced 128-bit accesses.
+#include "conv_common.cuh"
+
+namespace hoig {
+namespace {
+
+constexpr int TPB = 256;
+
+// ---------------------------------------------------------------- layout glue
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float *__restrict__ src, int B, int C, int HW, T *__restrict__ dst, int64_t ldd, int Cpad)
+{
+    const int chunks = Cpad / 8;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * HW * chunks) return;
+    const int ch = (int)(i % chunks);
+    const int64_t bp = i / chunks;
+    const int b = (int)(bp / HW), p = (int)(bp % HW);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = ch * 8 + j;
+        v[j] = c < C ? src[((int64_t)b * C + c) * HW + p] : 0.f;
+    }
+    store8(dst + bp * ldd + ch * 8, v);
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T *__restrict__ src, int64_t lds, int B, int C, int HW, float *__restrict__ dst)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * C * HW) return;
+    const int p = (int)(i % HW);
+    const int c = (int)((i / HW) % C);
+    const int b = (int)(i / ((int64_t)HW * C));
+    dst[i] = DT<T>::ld(src + ((int64_t)b * HW + p) * lds + c);
+}
+
+// spade.py:30, legacy 'nearest': src = min(floor(dst * in/out), in-1)
+template <typename T>
+__global__ void seg_resize_kernel(const float *__restrict__ seg, int B, int C, int Hi, int Wi, T *__restrict__ dst,
+                                  int64_t ldd, int Cpad, int Ho, int Wo)
+{
+    const int chunks = Cpad / 8;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * Ho * Wo * chunks) return;
+    const int ch = (int)(i % chunks);
+    const int64_t bp = i / chunks;
+    const int x = (int)(bp % Wo), y = (int)((bp / Wo) % Ho), b = (int)(bp / ((int64_t)Wo * Ho));
+    const float sy = (float)Hi / (float)Ho, sx = (float)Wi / (float)Wo;
+    const int iy = min((int)floorf(y * sy), Hi - 1), ix = min((int)floorf(x * sx), Wi - 1);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = ch * 8 + j;
+        v[j] = c < C ? seg[(((int64_t)b * C + c) * Hi + iy) * Wi + ix] : 0.f;
+    }
+    store8(dst + bp * ldd + ch * 8, v);
+}
+
+// ------------------------------------------------------------- instance norm
+// grid (slabs, N); thread = (pixel lane, channel chunk)
+template <typename T>
+__global__ void plane_stats_kernel(const T *__restrict__ x, int64_t ldx, int HW, int C, int pix_per_block, double *__restrict__ stats)
+{
+    extern __shared__ float sm[];  // [lanes][C][2]
+    const int chunks = C / 8;
+    const int lanes = blockDim.x / chunks;
+    const int cc = threadIdx.x % chunks, pl = threadIdx.x / chunks;
+    const int n = blockIdx.y;
+    const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    if (pl < lanes) {
+        for (int p = p0 + pl; p < p1; p += lanes) {
+            float v[8];
+            load8(x + ((int64_t)n * HW + p) * ldx + cc * 8, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sm[((size_t)pl * C + cc * 8 + j) * 2] = s[j];
+            sm[((size_t)pl * C + cc * 8 + j) * 2 + 1] = q[j];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
+        float a = 0.f;
+        for (int l = 0; l < lanes; ++l) a += sm[(size_t)l * C * 2 + i];
+        atomicAdd(&stats[(int64_t)n * C * 2 + i], (double)a);
+    }
+}
+
+// grid (slabs, N).  mean / rstd of the C planes of image n are rebuilt in smem per CTA.
+template <typename T>
+__global__ void instnorm_apply_kernel(const T *__restrict__ x, int64_t ldx, const double *__restrict__ stats,
+                                      const float *__restrict__ gamma, const float *__restrict__ beta,
+                                      const T *__restrict__ gb, int64_t ldgb, const T *__restrict__ res, int64_t ldr,
+                                      int relu, T *__restrict__ dst, int64_t ldd, int HW, int C, int pix_per_block, float eps)
+{
+    extern __shared__ float sm[];  // mean[C] | scale[C] | shift[C]
+    float *meanv = sm, *scale = sm + C, *shift = sm + 2 * C;
+    const int n = blockIdx.y;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const double s = stats[((int64_t)n * C + c) * 2], q = stats[((int64_t)n * C + c) * 2 + 1];
+        const double mean = s / HW;
+        double var = q / HW - mean * mean;
+        if (var < 0) var = 0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+        meanv[c] = (float)mean;
+        scale[c] = rstd * g;
+        shift[c] = b;
+    }
+    __syncthreads();
+    const int chunks = C / 8;
+    const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+    for (int i = threadIdx.x; i < (p1 - p0) * chunks; i += blockDim.x) {
+        const int cc = i % chunks, p = p0 + i / chunks;
+        const int64_t row = (int64_t)n * HW + p;
+        float v[8];
+        load8(x + row * ldx + cc * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j] - meanv[cc * 8 + j], scale[cc * 8 + j], shift[cc * 8 + j]);
+        if (gb) {  // spade.py:36  normalized * (1 + gamma) + beta
+            float g[8], b[8];
+            load8(gb + row * ldgb + cc * 8, g);
+            load8(gb + row * ldgb + C + cc * 8, b);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], 1.f + g[j], b[j]);
+        }
+        if (res) {
+            float r[8];
+            load8(res + row * ldr + cc * 8, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += r[j];
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        store8(dst + row * ldd + cc * 8, v);
+    }
+}
+
+// ------------------------------------------------------------------- warping
+// generator.py:466-473 (upsample_bilinear2d, align_corners=True) + generator.py:484-488.
+__global__ void resize_flow_kernel(const float *__restrict__ T, int B, int Hi, int Wi, int h, int sub_idt, float *__restrict__ flow)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * h * h) return;
+    const int x = (int)(i % h), y = (int)((i / h) % h), b = (int)(i / ((int64_t)h * h));
+    const float rh = h > 1 ? (float)(Hi - 1) / (float)(h - 1) : 0.f;
+    const float rw = h > 1 ? (float)(Wi - 1) / (float)(h - 1) : 0.f;
+    const float h1r = rh * y, w1r = rw * x;
+    const int h1 = (int)h1r, w1 = (int)w1r;
+    const int h1p = h1 < Hi - 1 ? 1 : 0, w1p = w1 < Wi - 1 ? 1 : 0;
+    const float h1l = h1r - h1, h0l = 1.f - h1l, w1l = w1r - w1, w0l = 1.f - w1l;
+    const float *t = T + (int64_t)b * Hi * Wi * 2;
+    // 'ij' identity grid: channel 0 follows the ROW index, channel 1 the COLUMN index (quirk Q2)
+    const float idt0 = (float)(-1.0 + y * (2.0 / h)), idt1 = (float)(-1.0 + x * (2.0 / h));
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const float v00 = t[((int64_t)h1 * Wi + w1) * 2 + c], v01 = t[((int64_t)h1 * Wi + w1 + w1p) * 2 + c];
+        const float v10 = t[((int64_t)(h1 + h1p) * Wi + w1) * 2 + c], v11 = t[((int64_t)(h1 + h1p) * Wi + w1 + w1p) * 2 + c];
+        const float val = h0l * (w0l * v00 + w1l * v01) + h1l * (w0l * v10 + w1l * v11);
+        flow[i * 2 + c] = sub_idt ? val - (c == 0 ? idt0 : idt1) : val;
+    }
+}
+
+// extract_attn.py:24-28 tail.  One warp per pixel: conv1x1 -> softmax -> weighted average of the
+// 25 bilinear taps of the source, plus the residual add of generator.py:407/427/446.
+template <typename T, int KK>
+__global__ void __launch_bounds__(128)
+attn_finish_kernel(const T *__restrict__ hidden, int64_t ldh, int Chid, const float *__restrict__ w2,
+                   const float *__restrict__ b2, const T *__restrict__ src, int64_t lds, const float *__restrict__ flow,
+                   const T *__restrict__ tgt, int64_t ldt, T *__restrict__ dst, int64_t ldd, int64_t npix_total, int h, int C)
+{
+    constexpr int K = (KK == 25) ? 5 : 3;
+    __shared__ float s_attn[4][KK];
+    __shared__ int s_idx[4][KK][4];
+    __shared__ float s_w[4][KK][4];
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int64_t pix = (int64_t)blockIdx.x * 4 + warp;
+    if (pix >= npix_total) return;  // whole warp exits together; no block-level sync below
+    const int x = (int)(pix % h), y = (int)((pix / h) % h);
+    const int64_t plane = (pix / ((int64_t)h * h)) * h * h;
+
+    // logits: lane-strided partial dot products, butterfly-reduced
+    float logit = -INFINITY;
+    {
+        float part[KK];
+#pragma unroll
+        for (int t = 0; t < KK; ++t) part[t] = 0.f;
+        for (int c = lane; c < Chid; c += 32) {
+            const float hv = DT<T>::ld(hidden + pix * ldh + c);
+#pragma unroll
+            for (int t = 0; t < KK; ++t) part[t] = fmaf(hv, __ldg(w2 + t * Chid + c), part[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < KK; ++t) {
+            const float tot = warp_sum(part[t]);
+            if (lane == t) logit = tot + b2[t];
+        }
+    }
+    float mx = logit;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e = lane < KK ? expf(logit - mx) : 0.f;
+    const float den = warp_sum(e);
+    if (lane < KK) {
+        s_attn[warp][lane] = e / den;
+        const BETap tp = be_tap(flow[pix * 2], flow[pix * 2 + 1], y, x, lane / K, lane % K, K, h, h);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { s_idx[warp][lane][q] = tp.idx[q]; s_w[warp][lane][q] = tp.w[q]; }
+    }
+    __syncwarp();
+    for (int cc = lane; cc < C / 8; cc += 32) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int t = 0; t < KK; ++t) {
+            float smp[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) smp[j] = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float u[8];
+                load8(src + (plane + s_idx[warp][t][q]) * lds + cc * 8, u);
+                const float wq = s_w[warp][t][q];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) smp[j] = __fmaf_rn(wq, u[j], smp[j]);
+            }
+            const float a = s_attn[warp][t];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(a, smp[j], acc[j]);
+        }
+        float tv[8];
+        load8(tgt + pix * ldt + cc * 8, tv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tv[j] += acc[j] * (1.0f / KK);
+        store8(dst + pix * ldd + cc * 8, tv);
+    }
+}
+
+// generator.py:475-478: F.grid_sample bilinear / zeros / align_corners=False
+template <typename T>
+__global__ void grid_sample_kernel(const T *__restrict__ x, int64_t ldx, const float *__restrict__ grid,
+                                   const T *__restrict__ tgt, int64_t ldt, T *__restrict__ dst, int64_t ldd,
+                                   int64_t npix_total, int h, int C)
+{
+    const int chunks = C / 8;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix_total * chunks) return;
+    const int cc = (int)(i % chunks);
+    const int64_t pix = i / chunks;
+    const int64_t plane = (pix / ((int64_t)h * h)) * h * h;
+    const float gx = grid[pix * 2], gy = grid[pix * 2 + 1];
+    const float ix = ((gx + 1.f) * h - 1.f) * 0.5f, iy = ((gy + 1.f) * h - 1.f) * 0.5f;
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int x0 = (int)fx, y0 = (int)fy;
+    const float wx1 = ix - fx, wy1 = iy - fy, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int xs[2] = {x0, x0 + 1}, ys[2] = {y0, y0 + 1};
+    const float wxs[2] = {wx0, wx1}, wys[2] = {wy0, wy1};
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            if (ys[a] < 0 || ys[a] >= h || xs[b] < 0 || xs[b] >= h) continue;
+            float u[8];
+            load8(x + (plane + (int64_t)ys[a] * h + xs[b]) * ldx + cc * 8, u);
+            const float w = wys[a] * wxs[b];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, u[j], acc[j]);
+        }
+    if (tgt) {
+        float tv[8];
+        load8(tgt + pix * ldt + cc * 8, tv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += tv[j];
+    }
+    store8(dst + pix * ldd + cc * 8, acc);
+}
+
+__global__ void composite_kernel(const float *__restrict__ bg, const float *__restrict__ obj, const float *__restrict__ hand,
+                                 const float *__restrict__ mbg, const float *__restrict__ mhand, float *__restrict__ out, int B, int HW)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * 3 * HW) return;
+    const int p = (int)(i % HW);
+    const int b = (int)(i / ((int64_t)3 * HW));
+    const float mb = mbg[(int64_t)b * HW + p], mh = mhand[(int64_t)b * HW + p];
+    out[i] = mb * bg[i] + (1.f - mb) * (obj[i] * mh + hand[i] * (1.f - mh));
+}
+
+// ------------------------------------------ reference op boundary (NCHW f32)
+// block_extractor_kernel.cu:21-85, one thread per output element.
+__global__ void block_extract_kernel(const float *__restrict__ src, const float *__restrict__ flow, float *__restrict__ out,
+                                     int64_t n, int C, int Hs, int Ws, int Hf, int Wf, int k)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int Wo = k * Wf, Ho = k * Hf;
+    const int x = (int)(i % Wo), y = (int)((i / Wo) % Ho);
+    const int c = (int)((i / ((int64_t)Wo * Ho)) % C), b = (int)(i / ((int64_t)Wo * Ho * C));
+    const int yf = y / k, xf = x / k;
+    const float fx = flow[(((int64_t)b * 2 + 0) * Hf + yf) * Wf + xf];
+    const float fy = flow[(((int64_t)b * 2 + 1) * Hf + yf) * Wf + xf];
+    const BETap t = be_tap(fx, fy, yf, xf, y % k, x % k, k, Hs, Ws);
+    const float *s = src + ((int64_t)b * C + c) * Hs * Ws;
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc = __fmaf_rn(t.w[q], s[t.idx[q]], acc);
+    out[i] = acc;
+}
+
+// local_attn_reshape_kernel.cu:21-61
+__global__ void local_attn_reshape_kernel(const float *__restrict__ in, float *__restrict__ out, int64_t n, int k, int H, int W)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int Wo = k * W, Ho = k * H;
+    const int x = (int)(i % Wo), y = (int)((i / Wo) % Ho), b = (int)(i / ((int64_t)Wo * Ho));
+    out[i] = in[(((int64_t)b * k * k + (y % k) * k + x % k) * H + y / k) * W + x / k];
+}
+
+template <typename F> int dispatch(int dtype, F f)
+{
+    if (dtype == HOIG_F32) return f((float *)nullptr);
+    if (dtype == HOIG_BF16) return f((__nv_bfloat16 *)nullptr);
+    set_error("bad dtype %d", dtype);
+    return HOIG_ERR_INVALID;
+}
+
+}  // namespace
+}  // namespace hoig
+
+using namespace hoig;
+
+extern "C" int hoig_nchw_to_nhwc(const float *src, int B, int C, int H, int W, void *dst, int64_t ldd, int Cpad, int dtype,
+                                 hoigStream_t stream)
+{
+    HOIG_REQUIRE(src && dst && Cpad % 8 == 0 && Cpad >= C && ldd >= Cpad && ldd % 8 == 0, "nchw_to_nhwc: bad argument");
+    const int64_t n = (int64_t)B * H * W * (Cpad / 8);
+    if (n == 0) return HOIG_OK;
+    return dispatch(dtype, [&](auto *tag) {
+        using T = std::remove_pointer_t<decltype(tag)>;
+        nchw_to_nhwc_kernel<T><<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>(src, B, C, H * W, (T *)dst, ldd, Cpad);
+        return check_launch("nchw_to_nhwc_kernel");
+    });
+}
+
+extern "C" int hoig_nhwc_to_nchw(const void *src, int64_t lds, int dtype, int B, int C, int H, int W, float *dst, hoigStream_t stream)
+{
+    HOIG_REQUIRE(src && dst && lds >= C, "nhwc_to_nchw: bad argument");
+    const int64_t n = (int64_t)B * C * H * W;
+    if (n == 0) return HOIG_OK;
+    return dispatch(dtype, [&](auto *tag) {
+        using T = std::remove_pointer_t<decltype(tag)>;
+        nhwc_to_nchw_kernel<T><<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>((const T *)src, lds, B, C, H * W, dst);
+        return check_launch("nhwc_to_nchw_kernel");
+    });
+}
+
+extern "C" int hoig_seg_resize_nearest(const float *seg, int B, int C, int Hi, int Wi, void *dst, int64_t ldd, int Cpad,
+                                       int Ho, int Wo, int dtype, hoigStream_t stream)
+{
+    HOIG_REQUIRE(seg && dst && Cpad % 8 == 0 && Cpad >= C && ldd >= Cpad && ldd % 8 == 0, "seg_resize: bad argument");
+    const int64_t n = (int64_t)B * Ho * Wo * (Cpad / 8);
+    if (n == 0) return HOIG_OK;
+    return dispatch(dtype, [&](auto *tag) {
+        using T = std::remove_pointer_t<decltype(tag)>;
+        seg_resize_kernel<T><<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>(seg, B, C, Hi, Wi, (T *)dst, ldd, Cpad, Ho, Wo);
+        return check_launch("seg_resize_kernel");
+    });
+}
+
+static int slab_pixels(int HW, int N)
+{
+    // aim for >= 4 CTAs per SM over the (slab, image) grid
+    int slabs = (148 * 4 + N - 1) / N;
+    if (slabs < 1) slabs = 1;
+    int pp = (HW + slabs - 1) / slabs;
+    if (pp < 64) pp = 64;
+    return pp;
+}
+
+extern "C" int hoig_plane_stats(const void *x, int64_t ldx, int dtype, int N, int HW, int C, double *stats, hoigStream_t stream)
+{
+    HOIG_REQUIRE(x && stats && C % 8 == 0 && C / 8 <= TPB && ldx >= C && ldx % 8 == 0, "plane_stats: bad argument (C=%d)", C);
+    if (N == 0 || HW == 0) return HOIG_OK;
+    const int pp = slab_pixels(HW, N);
+    const int lanes = TPB / (C / 8);
+    const size_t smem = (size_t)lanes * C * 2 * sizeof(float);
+    dim3 grid(ceil_div(HW, pp), N);
+    return dispatch(dtype, [&](auto *tag) {
+        using T = std::remove_pointer_t<decltype(tag)>;
+        plane_stats_kernel<T><<<grid, TPB, smem, as_stream(stream)>>>((const T *)x, ldx, HW, C, pp, stats);
+        return check_launch("plane_stats_kernel");
+    });
+}
+
+extern "C" int hoig_instnorm_apply(const void *x, int64_t ldx, const double *stats, const float *gamma, const float *beta,
+                                   const void *gb, int64_t ldgb, const void *residual, int64_t ldr, int relu, void *dst,
+                                   int64_t ldd, int dtype, int N, int HW, int C, float eps, hoigStream_t stream)
+{
+    HOIG_REQUIRE(x && stats && dst && C % 8 == 0 && ldx % 8 == 0 && ldd % 8 == 0, "instnorm_apply: bad argument");
+    HOIG_REQUIRE(!gb || (ldgb >= 2 * C && ldgb % 8 == 0), "instnorm_apply: gb needs 2C channels");
+    HOIG_REQUIRE(!residual || ldr % 8 == 0, "instnorm_apply: bad residual stride");
+    if (N == 0 || HW == 0) return HOIG_OK;
+    const int pp = slab_pixels(HW, N);
+    dim3 grid(ceil_div(HW, pp), N);
+    return dispatch(dtype, [&](auto *tag) {
+        using T = std::remove_pointer_t<decltype(tag)>;
+        instnorm_apply_kernel<T><<<grid, TPB, 3 * C * sizeof(float), as_stream(stream)>>>(
+            (const T *)x, ldx, stats, gamma, beta, (const T *)gb, ldgb, (const T *)residual, ldr, relu, (T *)dst, ldd, HW, C, pp, eps);
+        return check_launch("instnorm_apply_kernel");
+    });
+}
+
+extern "C" int hoig_resize_flow(const float *T, int B, int Hi, int Wi, int h, int subtract_identity, float *flow, hoigStream_t stream)
+{
+    HOIG_REQUIRE(T && flow && h >= 1, "resize_flow: bad argument");
+    const int64_t n = (int64_t)B * h * h;
+    if (n == 0) return HOIG_OK;
+    resize_flow_kernel<<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>(T, B, Hi, Wi, h, subtract_identity, flow);
+    return check_launch("resize_flow_kernel");
+}
+
+extern "C" int hoig_attn_finish(const void *hidden, int64_t ldh, int Chid, const float *w2, const float *b2, const void *src,
+                                int64_t lds, const float *flow, const void *tgt, int64_t ldt, void *dst, int64_t ldd, int dtype,
+                                int N, int h, int C, int k, hoigStream_t stream)
+{
+    HOIG_REQUIRE(hidden && w2 && b2 && src && flow && tgt && dst, "attn_finish: null pointer");
+    HOIG_REQUIRE(k == 5 || k == 3, "attn_finish: kernel size %d not supported (3 or 5)", k);
+    HOIG_REQUIRE(C % 8 == 0 && lds % 8 == 0 && ldt % 8 == 0 && ldd % 8 == 0, "attn_finish: channels / strides must be multiples of 8");
+    const int64_t npix = (int64_t)N * h * h;
+    if (npix == 0) return HOIG_OK;
+    return dispatch(dtype, [&](auto *tag) {
+        using T = std::remove_pointer_t<decltype(tag)>;
+        if (k == 5)
+            attn_finish_kernel<T, 25><<<ceil_div(npix, 4), 128, 0, as_stream(stream)>>>(
+                (const T *)hidden, ldh, Chid, w2, b2, (const T *)src, lds, flow, (const T *)tgt, ldt, (T *)dst, ldd, npix, h, C);
+        else
+            attn_finish_kernel<T, 9><<<ceil_div(npix, 4), 128, 0, as_stream(stream)>>>(
+                (const T *)hidden, ldh, Chid, w2, b2, (const T *)src, lds, flow, (const T *)tgt, ldt, (T *)dst, ldd, npix, h, C);
+        return check_launch("attn_finish_kernel");
+    });
+}
+
+extern "C" int hoig_grid_sample(const void *x, int64_t ldx, const float *grid, const void *tgt, int64_t ldt, void *dst,
+                                int64_t ldd, int dtype, int N, int h, int C, hoigStream_t stream)
+{
+    HOIG_REQUIRE(x && grid && dst && C % 8 == 0 && ldx % 8 == 0 && ldd % 8 == 0, "grid_sample: bad argument");
+    const int64_t npix = (int64_t)N * h * h;
+    if (npix == 0) return HOIG_OK;
+    return dispatch(dtype, [&](auto *tag) {
+        using T = std::remove_pointer_t<decltype(tag)>;
+        grid_sample_kernel<T><<<ceil_div(npix * (C / 8), TPB), TPB, 0, as_stream(stream)>>>(
+            (const T *)x, ldx, grid, (const T *)tgt, ldt, (T *)dst, ldd, npix, h, C);
+        return check_launch("grid_sample_kernel");
+    });
+}
+
+extern "C" int hoig_composite(const float *img_bg, const float *obj, const float *hand, const float *mask_bg,
+                              const float *mask_hand, float *out, int B, int HW, hoigStream_t stream)
+{
+    HOIG_REQUIRE(img_bg && obj && hand && mask_bg && mask_hand && out, "composite: null pointer");
+    const int64_t n = (int64_t)B * 3 * HW;
+    if (n == 0) return HOIG_OK;
+    composite_kernel<<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>(img_bg, obj, hand, mask_bg, mask_hand, out, B, HW);
+    return check_launch("composite_kernel");
+}
+
+extern "C" int hoig_block_extract_f32(const float *source, const float *flow, float *out, int B, int C, int Hs, int Ws, int Hf,
+                                      int Wf, int k, hoigStream_t stream)
+{
+    HOIG_REQUIRE(source && flow && out && k >= 1, "block_extract: bad argument");
+    const int64_t n = (int64_t)B * C * k * Hf * k * Wf;
+    if (n == 0) return HOIG_OK;
+    block_extract_kernel<<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>(source, flow, out, n, C, Hs, Ws, Hf, Wf, k);
+    return check_launch("block_extract_kernel");
+}
+
+extern "C" int hoig_local_attn_reshape_f32(const float *in, float *out, int B, int k, int H, int W, hoigStream_t stream)
+{
+    HOIG_REQUIRE(in && out && k >= 1, "local_attn_reshape: bad argument");
+    const int64_t n = (int64_t)B * k * H * k * W;
+    if (n == 0) return HOIG_OK;
+    local_attn_reshape_kernel<<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>(in, out, n, k, H, W);
+    return check_launch("local_attn_reshape_kernel");
+}

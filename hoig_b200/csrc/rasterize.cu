@@ -1,0 +1,414 @@
+// rasterize.cu -- stage R: bit-exact condition rasterizer + condition-map kernels.
+//
+// Replaces (paths relative to /root/reference/HOIG_HOv3):
+//   thirdparty/neural_renderer/neural_renderer/cuda/rasterize_cuda_kernel.cu:41-186
+//   (forward_face_index_map kernels _1/_2), rasterize.py:50-52 (output init),
+//   rasterize.py:335-338 (vertical flip).
+//
+// Design (B200-first, not the reference's per-pixel x all-faces loop):
+//   * face-parallel scatter.  One CTA owns (mesh, band of rows); its z-buffer
+//     lives in shared memory as 64-bit keys (ordered depth bits << 32 | face
+//     index) resolved with shared-memory atomicMin, so the winner is the
+//     minimum depth with the LOWEST face index on ties -- exactly the result
+//     of the reference's in-order strict '<' z-test.
+//   * Candidate pixels of a face are found EXACTLY, with no epsilon: each of
+//     the reference's three edge tests compares A(y) = (yp-ya)*dx against
+//     B(x) = (xp-xa)*dy; IEEE rounding is monotone, so A is monotone in the
+//     row index and B in the column index.  The set of rows that can pass and,
+//     per row, the column interval that passes are therefore found by binary
+//     search on the reference's own float predicate.  Every pixel inside the
+//     interval passes all three tests bit-identically to the reference.
+//   * Per-(pixel,face) arithmetic replays the reference's compiled op
+//     sequence with explicit __f*_rn intrinsics, which
+//     nvcc never contracts.
+//   * A second phase of the same kernel turns keys into fim / wim / depth and
+//     writes them coalesced (flip fused).
+#include "common.cuh"
+
+namespace hoig {
+namespace {
+
+constexpr int kRastThreads = 512;
+constexpr int kMaxBandPixels = 16384;  // 128 KB of 64-bit keys
+constexpr unsigned long long kEmptyKey = 0xffffffffffffffffull;
+constexpr float kWild = 1e15f;
+
+struct FaceInv { float v[9]; };
+
+// rasterize_cuda_kernel.cu:62-79 with the contraction pattern nvcc emits.
+__device__ __forceinline__ void face_inverse(const float f[9], float isf, float fi[9])
+{
+    float p[3][2];
+#pragma unroll
+    for (int n = 0; n < 3; ++n)
+#pragma unroll
+        for (int d = 0; d < 2; ++d)
+            p[n][d] = __fmul_rn(__fadd_rn(__fmaf_rn(f[3 * n + d], isf, isf), -1.0f), 0.5f);
+    fi[0] = __fsub_rn(p[1][1], p[2][1]);
+    fi[1] = __fsub_rn(p[2][0], p[1][0]);
+    fi[2] = __fmaf_rn(p[1][0], p[2][1], -__fmul_rn(p[2][0], p[1][1]));
+    fi[3] = __fsub_rn(p[2][1], p[0][1]);
+    fi[4] = __fsub_rn(p[0][0], p[2][0]);
+    fi[5] = __fmaf_rn(p[2][0], p[0][1], -__fmul_rn(p[0][0], p[2][1]));
+    fi[6] = __fsub_rn(p[0][1], p[1][1]);
+    fi[7] = __fsub_rn(p[1][0], p[0][0]);
+    fi[8] = __fmaf_rn(p[0][0], p[1][1], -__fmul_rn(p[1][0], p[0][1]));
+    const float den = __fmaf_rn(p[1][0], fi[3], __fmaf_rn(p[2][0], fi[6], __fmul_rn(p[0][0], fi[0])));
+#pragma unroll
+    for (int k = 0; k < 9; ++k) fi[k] = __fdiv_rn(fi[k], den);
+}
+
+// rasterize_cuda_kernel.cu:57 / :128
+__device__ __forceinline__ bool back_facing(const float f[9])
+{
+    return __fmul_rn(__fsub_rn(f[7], f[1]), __fsub_rn(f[3], f[0])) <
+           __fmul_rn(__fsub_rn(f[4], f[1]), __fsub_rn(f[6], f[0]));
+}
+
+// rasterize_cuda_kernel.cu:139-153.  Returns true and (w, zp) when the pixel survives
+// the near/far test; NaN zp never survives (it fails the later zp < depth_min).
+__device__ __forceinline__ bool shade(const float f[9], const float fi[9], float xf, float yf, float near_, float far_,
+                                      float w[3], float &zp)
+{
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        w[k] = __fadd_rn(__fmaf_rn(fi[3 * k], xf, __fmul_rn(fi[3 * k + 1], yf)), fi[3 * k + 2]);
+    float ws = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        w[k] = fminf(fmaxf(w[k], 0.f), 1.f);
+        ws = __fadd_rn(ws, w[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) w[k] = __fdiv_rn(w[k], ws);
+    zp = __frcp_rn(__fadd_rn(__fadd_rn(__fdiv_rn(w[0], f[2]), __fdiv_rn(w[1], f[5])), __fdiv_rn(w[2], f[8])));
+    return (zp > near_) && (zp < far_);
+}
+
+__device__ __forceinline__ uint32_t ordered_bits(float z)
+{
+    const uint32_t b = __float_as_uint(z);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits(uint32_t o)
+{
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// smallest i in [lo,hi] with pred(i) true (pred monotone false->true), hi+1 if none
+template <class P> __device__ __forceinline__ int first_true(int lo, int hi, P pred)
+{
+    int l = lo, h = hi + 1;
+    while (l < h) {
+        const int m = (l + h) >> 1;
+        if (pred(m)) h = m; else l = m + 1;
+    }
+    return l;
+}
+
+struct Edges {
+    float ya[3], dx[3], xa[3], dy[3];
+    __device__ __forceinline__ float A(int i, float yp) const { return __fmul_rn(__fsub_rn(yp, ya[i]), dx[i]); }
+    __device__ __forceinline__ float B(int i, float xp) const { return __fmul_rn(__fsub_rn(xp, xa[i]), dy[i]); }
+};
+
+// One CTA per (mesh, band).  Dynamic smem: keys[band_rows*is] (u64) | centre[is] (f32).
+__global__ void __launch_bounds__(kRastThreads, 1)
+rasterize_kernel(const float *__restrict__ faces, int F, int is, int band_rows, int n_bands, float near_, float far_,
+                 int flip_y, int32_t *__restrict__ fim, float *__restrict__ wim, float *__restrict__ depth)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
+    float *centre = reinterpret_cast<float *>(keys + (size_t)band_rows * is);
+
+    const int mesh = blockIdx.x / n_bands;
+    const int band = blockIdx.x % n_bands;
+    const int r0 = band * band_rows;
+    const int r1 = min(is, r0 + band_rows) - 1;  // inclusive
+    const int npix = (r1 - r0 + 1) * is;
+    const float isf = (float)is;
+
+    for (int i = threadIdx.x; i < npix; i += blockDim.x) keys[i] = kEmptyKey;
+    // rasterize_cuda_kernel.cu:113-114: pixel centre in f64, rounded once
+    for (int i = threadIdx.x; i < is; i += blockDim.x) centre[i] = (float)((2. * i + 1 - is) / is);
+    __syncthreads();
+
+    const float *mf = faces + (size_t)mesh * F * 9;
+    for (int fn = threadIdx.x; fn < F; fn += blockDim.x) {
+        float f[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) f[k] = __ldg(mf + (size_t)fn * 9 + k);
+        if (back_facing(f)) continue;
+
+        bool wild = false;
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            if (k % 3 != 2) wild |= !(fabsf(f[k]) <= kWild);  // catches NaN / inf / huge
+
+        float fi[9];
+        int row_lo = r0, row_hi = r1;
+        Edges e;
+        e.ya[0] = f[1]; e.dx[0] = __fsub_rn(f[3], f[0]); e.xa[0] = f[0]; e.dy[0] = __fsub_rn(f[4], f[1]);
+        e.ya[1] = f[4]; e.dx[1] = __fsub_rn(f[6], f[3]); e.xa[1] = f[3]; e.dy[1] = __fsub_rn(f[7], f[4]);
+        e.ya[2] = f[7]; e.dx[2] = __fsub_rn(f[0], f[6]); e.xa[2] = f[6]; e.dy[2] = __fsub_rn(f[1], f[7]);
+
+        if (!wild) {
+            // rows of this band that can pass edge i: A_i(y) >= min_x B_i(x); B monotone => min at an end.
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float bmin = fminf(e.B(i, centre[0]), e.B(i, centre[is - 1]));
+                if (!(fmaxf(e.A(i, centre[r0]), e.A(i, centre[r1])) >= bmin)) { row_lo = 1; row_hi = 0; }
+            }
+            if (row_lo > row_hi) continue;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float bmin = fminf(e.B(i, centre[0]), e.B(i, centre[is - 1]));
+                if (e.dx[i] >= 0.f) {  // A non-decreasing in y: passing rows are a suffix
+                    row_lo = max(row_lo, first_true(r0, r1, [&](int y) { return e.A(i, centre[y]) >= bmin; }));
+                } else {               // A non-increasing: passing rows are a prefix
+                    row_hi = min(row_hi, first_true(r0, r1, [&](int y) { return !(e.A(i, centre[y]) >= bmin); }) - 1);
+                }
+            }
+            if (row_lo > row_hi) continue;
+        }
+        face_inverse(f, isf, fi);
+
+        for (int y = row_lo; y <= row_hi; ++y) {
+            const float yp = centre[y];
+            int c_lo = 0, c_hi = is - 1;
+            if (!wild) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const float a = e.A(i, yp);
+                    if (e.dy[i] >= 0.f) {  // B non-decreasing in x: pass set {B <= a} is a prefix
+                        c_hi = min(c_hi, first_true(0, is - 1, [&](int x) { return a < e.B(i, centre[x]); }) - 1);
+                    } else {               // B non-increasing: pass set is a suffix
+                        c_lo = max(c_lo, first_true(0, is - 1, [&](int x) { return !(a < e.B(i, centre[x])); }));
+                    }
+                }
+            }
+            for (int x = c_lo; x <= c_hi; ++x) {
+                if (wild) {  // rasterize_cuda_kernel.cu:132-135 verbatim (NaN compares false => passes)
+                    const float xp = centre[x];
+                    if ((e.A(0, yp) < e.B(0, xp)) || (e.A(1, yp) < e.B(1, xp)) || (e.A(2, yp) < e.B(2, xp))) continue;
+                }
+                float w[3], zp;
+                if (!shade(f, fi, (float)x, (float)y, near_, far_, w, zp)) continue;
+                const unsigned long long key = ((unsigned long long)ordered_bits(zp) << 32) | (uint32_t)fn;
+                atomicMin(&keys[(size_t)(y - r0) * is + x], key);
+            }
+        }
+    }
+    __syncthreads();
+
+    // resolve: keys -> fim / wim / depth  (rasterize_cuda_kernel.cu:174-179, rasterize.py:50-52,335-338)
+    for (int i = threadIdx.x; i < npix; i += blockDim.x) {
+        const int y = r0 + i / is, x = i % is;
+        const unsigned long long key = keys[i];
+        const int yo = flip_y ? (is - 1 - y) : y;
+        const size_t o = ((size_t)mesh * is + yo) * is + x;
+        int face = -1;
+        float w[3] = {0.f, 0.f, 0.f};
+        float zp = far_;
+        if (key != kEmptyKey) {
+            face = (int)(uint32_t)key;
+            float f[9], fi[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) f[k] = __ldg(mf + (size_t)face * 9 + k);
+            face_inverse(f, isf, fi);
+            float z2;
+            shade(f, fi, (float)x, (float)y, near_, far_, w, z2);
+            zp = from_ordered_bits((uint32_t)(key >> 32));
+        }
+        fim[o] = face;
+        wim[3 * o] = w[0]; wim[3 * o + 1] = w[1]; wim[3 * o + 2] = w[2];
+        if (depth) depth[o] = zp;
+    }
+}
+
+__global__ void face_inv_kernel(const float *__restrict__ faces, int64_t BF, int is, float *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= BF) return;
+    float f[9], fi[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) f[k] = faces[i * 9 + k];
+    if (back_facing(f)) return;
+    face_inverse(f, (float)is, fi);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) out[i * 9 + k] = fi[k];
+}
+
+// R0: utils/nmr.py:109-140 + :506 + look_at (identity rotation for eye on -z) + vertices_to_faces.
+// One thread per (mesh, face, corner).
+__global__ void project_faces_kernel(const float *__restrict__ verts, const float *__restrict__ cam,
+                                     const int32_t *__restrict__ fidx, int B, int V, int F, float eye_z,
+                                     float *__restrict__ faces)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)B * F * 3) return;
+    const int b = (int)(t / ((int64_t)F * 3));
+    const int fc = (int)(t % ((int64_t)F * 3));
+    const int v = fidx[fc];
+    const float *p = verts + ((size_t)b * V + v) * 3;
+    const float *c = cam + (size_t)b * 15;
+    // OpenGL -> camera coords (x, -y, -z); einsum accumulations written as the
+    // left-to-right sums torch performs for K=3 dot products.
+    const float X = p[0], Y = -p[1], Z = -p[2];
+    const float px = c[0] * X + c[1] * Y + c[2] * Z;
+    const float py = c[3] * X + c[4] * Y + c[5] * Z;
+    const float pz = c[6] * X + c[7] * Y + c[8] * Z;
+    const float u = px / pz, w = py / pz;
+    float ox = c[9] * u + c[10] * w + c[11];
+    float oy = c[12] * u + c[13] * w + c[14];
+    ox = ox / 255.0f * 2.f - 1.f;
+    oy = oy / 255.0f * 2.f - 1.f;
+    float *o = faces + (size_t)t * 3;
+    o[0] = ox;
+    o[1] = -oy;          // utils/nmr.py:506
+    o[2] = Z - eye_z;    // look_at: vertices - eye, identity rotation
+}
+
+// R4/R5: table gathers by fim (utils/nmr.py:567-595) + one-hot seg + hand mask (trainer.py:71-72).
+__global__ void condition_maps_kernel(const int32_t *__restrict__ fim, int64_t npix_total, int hw, int F,
+                                      const float *__restrict__ map_fn, const float *__restrict__ sem_full,
+                                      int n_hand, float *__restrict__ cond, float *__restrict__ seg,
+                                      float *__restrict__ not_hand)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix_total) return;
+    const int b = (int)(i / hw), p = (int)(i % hw);
+    const int f = fim[i];
+    const int row = f < 0 ? F : f;  // python negative index -1 -> last (background) row
+    if (cond) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) cond[((size_t)b * 3 + c) * hw + p] = map_fn[(size_t)row * 3 + c];
+    }
+    if (seg) {
+        const float s = sem_full[row];
+#pragma unroll
+        for (int c = 0; c < 15; ++c) seg[((size_t)b * 15 + c) * hw + p] = (s == (float)(c + 1)) ? 1.f : 0.f;
+    }
+    if (not_hand) not_hand[i] = 1.f - ((f != -1 && f < n_hand) ? 1.f : 0.f);
+}
+
+// R7: utils/nmr.py:874-925 (T only) with the y re-negation of trainer.py:67-68.
+__global__ void bc_transform_kernel(const float *__restrict__ src_faces, const int32_t *__restrict__ fim,
+                                    const float *__restrict__ wim, int64_t npix_total, int hw, int F,
+                                    float *__restrict__ T)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix_total) return;
+    const int b = (int)(i / hw);
+    const int f = fim[i];
+    float tx = -2.f, ty = -2.f;
+    if (f != -1) {
+        const float *fv = src_faces + ((size_t)b * F + f) * 9;
+        const float w0 = wim[3 * i], w1 = wim[3 * i + 1], w2 = wim[3 * i + 2];
+        // (f2pts * w[:, :, None]).sum(dim=1): products rounded, summed in vertex order
+        tx = __fadd_rn(__fadd_rn(__fmul_rn(fv[0], w0), __fmul_rn(fv[3], w1)), __fmul_rn(fv[6], w2));
+        ty = __fadd_rn(__fadd_rn(__fmul_rn(-fv[1], w0), __fmul_rn(-fv[4], w1)), __fmul_rn(-fv[7], w2));
+    }
+    T[2 * i] = tx;
+    T[2 * i + 1] = ty;
+}
+
+// R6: utils/util.py:142-153.  Inputs are 0/1 masks; erode == all ks*ks neighbours (pad value 1) are 1.
+// The reference tests conv_sum == ks*ks on floats, reproduced as an exact float sum of the window.
+__global__ void erode_kernel(const float *__restrict__ in, float *__restrict__ out, int B, int H, int W, int ks)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * H * W) return;
+    const int b = (int)(i / ((int64_t)H * W));
+    const int y = (int)((i / W) % H), x = (int)(i % W);
+    const int r = ks / 2;
+    float s = 0.f;
+    for (int dy = -r; dy <= r; ++dy)
+        for (int dx = -r; dx <= r; ++dx) {
+            const int yy = y + dy, xx = x + dx;
+            s += (yy < 0 || yy >= H || xx < 0 || xx >= W) ? 1.f : in[((size_t)b * H + yy) * W + xx];
+        }
+    out[i] = (s == (float)(ks * ks)) ? 1.f : 0.f;
+}
+
+}  // namespace
+}  // namespace hoig
+
+using namespace hoig;
+
+extern "C" size_t hoig_rasterize_workspace_bytes(int, int, int) { return 0; }  // z-buffer lives in shared memory
+
+extern "C" int hoig_rasterize_fim_wim(const float *faces, int B, int F, int image_size, float near_, float far_,
+                                      int flip_y, int32_t *fim, float *wim, float *depth, void *, size_t,
+                                      hoigStream_t stream)
+{
+    HOIG_REQUIRE(faces && fim && wim, "rasterize: null pointer");
+    HOIG_REQUIRE(B >= 0 && F >= 0 && image_size >= 1 && image_size <= 2048, "rasterize: bad shape B=%d F=%d is=%d", B, F, image_size);
+    if (B == 0) return HOIG_OK;
+    const int is = image_size;
+    int band_rows = kMaxBandPixels / is;
+    if (band_rows > is) band_rows = is;
+    HOIG_REQUIRE(band_rows >= 1, "rasterize: image too wide");
+    const int n_bands = ceil_div(is, band_rows);
+    const size_t smem = (size_t)band_rows * is * sizeof(unsigned long long) + (size_t)is * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(rasterize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+            return check_launch("rasterize smem attribute");
+        attr_set = true;
+    }
+    rasterize_kernel<<<(unsigned)((int64_t)B * n_bands), kRastThreads, smem, as_stream(stream)>>>(
+        faces, F, is, band_rows, n_bands, near_, far_, flip_y, fim, wim, depth);
+    return check_launch("rasterize_kernel");
+}
+
+extern "C" int hoig_face_inv(const float *faces, int64_t BF, int image_size, float *faces_inv, hoigStream_t stream)
+{
+    HOIG_REQUIRE(faces && faces_inv && BF >= 0, "face_inv: bad argument");
+    if (BF == 0) return HOIG_OK;
+    face_inv_kernel<<<ceil_div(BF, 256), 256, 0, as_stream(stream)>>>(faces, BF, image_size, faces_inv);
+    return check_launch("face_inv_kernel");
+}
+
+extern "C" int hoig_project_faces(const float *verts, const float *cam, const int32_t *faces_idx, int B, int V, int F,
+                                  float eye_z, float *faces, hoigStream_t stream)
+{
+    HOIG_REQUIRE(verts && cam && faces_idx && faces, "project_faces: null pointer");
+    const int64_t n = (int64_t)B * F * 3;
+    if (n == 0) return HOIG_OK;
+    project_faces_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(verts, cam, faces_idx, B, V, F, eye_z, faces);
+    return check_launch("project_faces_kernel");
+}
+
+extern "C" int hoig_condition_maps(const int32_t *fim, int B, int F, int image_size, const float *map_fn,
+                                   const float *sem_full, int n_hand_faces, float *cond, float *seg, float *not_hand,
+                                   hoigStream_t stream)
+{
+    HOIG_REQUIRE(fim && map_fn && sem_full, "condition_maps: null pointer");
+    const int hw = image_size * image_size;
+    const int64_t n = (int64_t)B * hw;
+    if (n == 0) return HOIG_OK;
+    condition_maps_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(fim, n, hw, F, map_fn, sem_full, n_hand_faces,
+                                                                        cond, seg, not_hand);
+    return check_launch("condition_maps_kernel");
+}
+
+extern "C" int hoig_bc_transform(const float *src_faces, const int32_t *fim_ref, const float *wim_ref, int B, int F,
+                                 int image_size, float *T, hoigStream_t stream)
+{
+    HOIG_REQUIRE(src_faces && fim_ref && wim_ref && T, "bc_transform: null pointer");
+    const int hw = image_size * image_size;
+    const int64_t n = (int64_t)B * hw;
+    if (n == 0) return HOIG_OK;
+    bc_transform_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(src_faces, fim_ref, wim_ref, n, hw, F, T);
+    return check_launch("bc_transform_kernel");
+}
+
+extern "C" int hoig_erode(const float *in, float *out, int B, int H, int W, int ks, hoigStream_t stream)
+{
+    HOIG_REQUIRE(in && out && ks >= 1 && (ks & 1), "erode: bad argument");
+    const int64_t n = (int64_t)B * H * W;
+    if (n == 0) return HOIG_OK;
+    erode_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(in, out, B, H, W, ks);
+    return check_launch("erode_kernel");
+}

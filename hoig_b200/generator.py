@@ -1,0 +1,486 @@
+"""GeneratorB200 -- drop-in replacement for the reference HOGAN ``Generator``.
+
+Boundary B1 of SURVEY.md section 8b: same constructor arguments, same
+``forward`` signature and 10-tuple result, same ``state_dict`` key layout
+(425 entries for the shipped HOv3 config) as
+``/root/reference/HOIG_HOv3/models/networks/generator.py:318-376``, so
+``NetworksFactory`` / ``Trainer`` / ``eval.py`` can swap it in.  Parameters stay
+OIHW fp32 ``nn.Parameter``s (checkpoint compatible); the kernels consume packed
+copies that are rebuilt whenever a parameter changes.
+
+The forward pass itself is a schedule of hand-written sm_100a kernels called
+through the C ABI (``hoig_b200.ops``): there is no PyTorch-op fallback, and a
+missing library or non-B200 device raises.
+
+Schedule (reference line numbers in comments):
+  * activations are NHWC, ``dtype`` bf16 (tcgen05 path) or fp32 (SIMT parity path);
+  * every conv is one implicit-GEMM launch whose epilogue also accumulates the
+    per-plane statistics InstanceNorm needs, so a norm costs one light
+    normalise/modulate pass (``instnorm_apply``) and no reduction pass;
+  * SPADE gamma/beta convs run as one GEMM with N = 2C;
+  * U-Net skip concatenations are channel slices of one wider buffer;
+  * the local-attention warp never materialises the 25x BlockExtractor tensors:
+    the k5s5 conv gathers them on the fly and ``attn_finish`` fuses conv1x1 +
+    softmax + weighted re-gather + mean + residual add.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .packing import ceil_to, pack_conv_weight, pack_spade_gamma_beta
+
+NHIDDEN = 128  # spade.py:16
+ATTN_HIDDEN = 128  # extract_attn.py:11
+ATTN_K = 5  # generator.py:344
+
+
+class _Params(nn.Module):
+    """Parameter-only container; children are named like the reference's modules."""
+
+    def child(self, name: str) -> "_Params":
+        if name not in self._modules:
+            self.add_module(name, _Params())
+        return self._modules[name]
+
+    def add(self, dotted: str, shape: Tuple[int, ...]) -> None:
+        *path, leaf = dotted.split(".")
+        m = self
+        for p in path:
+            m = m.child(p)
+        m.register_parameter(leaf, nn.Parameter(torch.zeros(shape)))
+
+
+def _conv(out: List, p: str, co: int, ci: int, k: int, bias: bool):
+    out.append((p + "weight", (co, ci, k, k), "conv"))
+    if bias:
+        out.append((p + "bias", (co,), "conv_bias"))
+
+
+def _inorm(out: List, p: str, c: int):
+    out.append((p + "weight", (c,), "norm_weight"))
+    out.append((p + "bias", (c,), "norm_bias"))
+
+
+def _spade(out: List, p: str, c: int, s: int):
+    _conv(out, p + "mlp_shared.0.", NHIDDEN, s, 3, True)
+    _conv(out, p + "mlp_gamma.", c, NHIDDEN, 3, True)
+    _conv(out, p + "mlp_beta.", c, NHIDDEN, 3, True)
+
+
+def parameter_layout(bg_dim, img_dim, obj_dim, img_cond_dim, obj_cond_dim, conv_dim, repeat_num, n_down,
+                     spade_layers, attn_layers) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """Ordered (name, shape, kind) list reproducing the reference registration order
+    (generator.py:93-135 ResNetGenerator, :138-242 ResUnetGenerator, :318-345 Generator)."""
+    out: List = []
+    # bg_model: nn.Sequential indices are part of the key names
+    p, i, c = "bg_model.model.", 0, conv_dim
+    _conv(out, f"{p}{i}.", c, bg_dim, 7, False); _inorm(out, f"{p}{i + 1}.", c); i += 3
+    for _ in range(n_down):
+        _conv(out, f"{p}{i}.", 2 * c, c, 3, False); _inorm(out, f"{p}{i + 1}.", 2 * c); i += 3; c *= 2
+    for _ in range(repeat_num):
+        _conv(out, f"{p}{i}.main.0.", c, c, 3, False); _inorm(out, f"{p}{i}.main.1.", c)
+        _conv(out, f"{p}{i}.main.3.", c, c, 3, False); _inorm(out, f"{p}{i}.main.4.", c); i += 1
+    for _ in range(n_down):
+        out.append((f"{p}{i}.weight", (c, c // 2, 3, 3), "conv")); _inorm(out, f"{p}{i + 1}.", c // 2); i += 3; c //= 2
+    _conv(out, f"{p}{i}.", 3, c, 7, False)
+
+    def unet(p, c_dim, s_dim, on_obj):
+        c = conv_dim
+        _conv(out, p + "encoders.0.0.", c, c_dim, 7, False); _inorm(out, p + "encoders.0.1.", c)
+        for i in range(1, n_down + 1):
+            if spade_layers[0]:
+                _conv(out, f"{p}encoders.{i}.conv.", 2 * c, c, 3, False); _spade(out, f"{p}encoders.{i}.norm.", 2 * c, s_dim)
+            else:
+                _conv(out, f"{p}encoders.{i}.0.", 2 * c, c, 3, False); _inorm(out, f"{p}encoders.{i}.1.", 2 * c)
+            c *= 2
+        for i in range(repeat_num):
+            q = f"{p}resnets.{i}."
+            if spade_layers[1] if i < repeat_num // 2 else spade_layers[2]:
+                _conv(out, q + "conv_0.", c, c, 3, True); _conv(out, q + "conv_1.", c, c, 3, True)
+                _spade(out, q + "norm_0.", c, s_dim); _spade(out, q + "norm_1.", c, s_dim)
+            else:
+                _conv(out, q + "main.0.", c, c, 3, False); _inorm(out, q + "main.1.", c)
+                _conv(out, q + "main.3.", c, c, 3, False); _inorm(out, q + "main.4.", c)
+        dec, skip = [], []
+        for i in range(n_down):
+            if spade_layers[3]:
+                dec.append((f"{p}decoders.{i}.conv.weight", (c, c // 2, 3, 3), "conv")); _spade(dec, f"{p}decoders.{i}.norm.", c // 2, s_dim)
+            else:
+                dec.append((f"{p}decoders.{i}.0.weight", (c, c // 2, 3, 3), "conv")); _inorm(dec, f"{p}decoders.{i}.1.", c // 2)
+            _conv(skip, f"{p}skippers.{i}.0.", c // 2, c, 3, False); _inorm(skip, f"{p}skippers.{i}.1.", c // 2)
+            c //= 2
+        out.extend(dec); out.extend(skip)
+        _conv(out, p + "img_reg.0.", 3, c, 7, False)
+        if not on_obj:
+            _conv(out, p + "attetion_reg_hand.0.", 1, c, 7, False)   # [sic] spelling is part of the checkpoint contract
+            _conv(out, p + "attetion_reg_bg.0.", 1, 2 * c, 7, False)
+
+    unet("obj_model.", obj_dim, obj_cond_dim, True)
+    unet("src_model.", img_dim, img_cond_dim, False)
+    unet("tsf_model.", img_dim, img_cond_dim, False)
+    for L in attn_layers:
+        ch = conv_dim * 2 ** min(L, n_down)
+        _conv(out, f"attn_{L}.fully_connect_layer.0.", ATTN_HIDDEN, 2 * ch, ATTN_K, True)
+        _conv(out, f"attn_{L}.fully_connect_layer.2.", ATTN_K * ATTN_K, ATTN_HIDDEN, 1, True)
+    return out
+
+
+class _StatsArena:
+    """Zero-initialised float64 scratch for per-plane statistics, carved per conv."""
+
+    def __init__(self, device, chunk: int = 1 << 21):
+        self.device, self.chunk, self.buf, self.off = device, chunk, None, 0
+
+    def take(self, n: int, c: int) -> torch.Tensor:
+        need = n * c * 2
+        if self.buf is None or self.off + need > self.buf.numel():
+            self.buf = torch.zeros(max(self.chunk, need), dtype=torch.float64, device=self.device)
+            self.off = 0
+        v = self.buf[self.off:self.off + need]
+        self.off += need
+        return v
+
+
+class GeneratorB200(nn.Module):
+    """B200-native HOGAN generator (see module docstring)."""
+
+    def __init__(self, bg_dim, img_dim, obj_dim, img_cond_dim=0, obj_cond_dim=0, conv_dim=64, repeat_num=6,
+                 spade_layers=[0, 0, 0, 0], attn_layers=[], dtype: torch.dtype = torch.bfloat16):
+        super().__init__()
+        self._name = "generator"
+        self.n_down = 3
+        self.repeat_num = repeat_num
+        self.spade_layers = list(spade_layers)
+        self.attn_layers = list(attn_layers)
+        self.conv_dim = conv_dim
+        self.dims = dict(bg_dim=bg_dim, img_dim=img_dim, obj_dim=obj_dim, img_cond_dim=img_cond_dim, obj_cond_dim=obj_cond_dim)
+        if dtype not in (torch.bfloat16, torch.float32):
+            raise ValueError("GeneratorB200: dtype must be torch.bfloat16 (tensor-core path) or torch.float32 (parity path)")
+        self.compute_dtype = dtype
+        self._layout = parameter_layout(bg_dim, img_dim, obj_dim, img_cond_dim, obj_cond_dim, conv_dim, repeat_num,
+                                        self.n_down, self.spade_layers, self.attn_layers)
+        for top in ("bg_model", "obj_model", "src_model", "tsf_model"):
+            self.add_module(top, _Params())
+        for L in self.attn_layers:
+            self.add_module(f"attn_{L}", _Params())
+        for name, shape, kind in self._layout:
+            top, rest = name.split(".", 1)
+            self._modules[top].add(rest, shape)
+        self._pcache: Dict[str, tuple] = {}
+        self.reset_parameters()
+
+    # ------------------------------------------------------------ nn.Module API
+    @property
+    def name(self):  # models/networks/base_network.py:10-12
+        return self._name
+
+    def reset_parameters(self):
+        """PyTorch default init is irrelevant for parity; use the reference's init_weights
+        distribution for convs and the InstanceNorm defaults (1, 0)."""
+        with torch.no_grad():
+            for name, _, kind in self._layout:
+                prm = self.get_parameter(name)
+                if kind == "conv":
+                    prm.normal_(0.0, 0.02)
+                elif kind == "norm_weight":
+                    prm.fill_(1.0)
+                else:
+                    prm.zero_()
+
+    def init_weights(self):
+        """base_network.py:14-25: N(0,0.02) on every *Conv* weight, conv bias 0; InstanceNorm
+        affine parameters are NOT touched (quirk Q6)."""
+        with torch.no_grad():
+            for name, _, kind in self._layout:
+                prm = self.get_parameter(name)
+                if kind == "conv":
+                    prm.normal_(0.0, 0.02)
+                elif kind == "conv_bias":
+                    prm.zero_()
+
+    def _p(self, name: str) -> torch.Tensor:
+        return self.get_parameter(name)
+
+    # packed-weight cache, keyed by parameter identity and version
+    def _cached(self, key: str, params: Sequence[torch.Tensor], build):
+        sig = tuple((p.data_ptr(), p._version, str(p.device)) for p in params) + (self.compute_dtype,)
+        hit = self._pcache.get(key)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        val = build()
+        self._pcache[key] = (sig, val)
+        return val
+
+    def _w(self, name: str, transposed: bool = False) -> torch.Tensor:
+        prm = self._p(name)
+        return self._cached(name, [prm], lambda: pack_conv_weight(prm, self.compute_dtype, transposed))
+
+    def _f32(self, name: str) -> torch.Tensor:
+        prm = self._p(name)
+        return self._cached(name + "#f32", [prm], lambda: prm.detach().float().contiguous())
+
+    def _gb(self, prefix: str):
+        ps = [self._p(prefix + n) for n in ("mlp_gamma.weight", "mlp_gamma.bias", "mlp_beta.weight", "mlp_beta.bias")]
+        return self._cached(prefix + "#gb", ps, lambda: pack_spade_gamma_beta(*ps, self.compute_dtype))
+
+    # ---------------------------------------------------------------- building blocks
+    def _new(self, n, h, w, c):
+        return torch.empty(n, h, w, c, dtype=self.compute_dtype, device=self._dev)
+
+    def _conv(self, x, wname, cout, k, *, stride=1, pad=None, transposed=False, bias=None, act=ops.ACT_NONE,
+              residual=None, want_stats=False, out=None):
+        n, h, w, _ = x.shape
+        pad = k // 2 if pad is None else pad
+        if transposed:
+            oh, ow, mode = h * 2, w * 2, ops.CONV_TRANSPOSED
+        else:
+            oh, ow, mode = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1, ops.CONV
+        if out is None:
+            out = self._new(n, oh, ow, ceil_to(cout, 8))
+        stats = self._arena.take(n, cout) if want_stats else None
+        ops.conv2d(x, self._w(wname, transposed), out, kh=k, kw=k, stride=2 if transposed else stride, pad=pad, mode=mode,
+                   bias=self._f32(bias) if bias else None, act=act, residual=residual, stats=stats, cout=cout)
+        return out, stats
+
+    def _conv_in_relu(self, x, prefix_conv, prefix_norm, cout, k, *, stride=1, transposed=False, out=None, relu=True,
+                      residual=None):
+        """conv (no bias) -> InstanceNorm2d(affine) -> ReLU   (generator.py:16-21, 99-102, 151-155, 200-209)"""
+        raw, st = self._conv(x, prefix_conv + "weight", cout, k, stride=stride, transposed=transposed, want_stats=True)
+        dst = raw if out is None else out
+        ops.instnorm_apply(raw, st, dst, gamma=self._f32(prefix_norm + "weight"), beta=self._f32(prefix_norm + "bias"),
+                           relu=relu, residual=residual)
+        return dst
+
+    def _seg(self, seg_nchw: torch.Tensor, h: int, cache: dict) -> torch.Tensor:
+        """spade.py:30 nearest resize, NHWC, channels zero-padded to 8."""
+        if h not in cache:
+            b, c = seg_nchw.shape[:2]
+            cache[h] = ops.seg_resize(seg_nchw, self._new(b, h, h, ceil_to(c, 8)))
+        return cache[h]
+
+    def _spade_apply(self, x, stats, prefix, seg_nchw, seg_cache, out=None):
+        """spade.py:24-38 followed by the ReLU every caller applies (generator.py:66-67, 86-88)."""
+        n, h, w, c = x.shape
+        s = self._seg(seg_nchw, h, seg_cache)
+        actv, _ = self._conv(s, prefix + "mlp_shared.0.weight", NHIDDEN, 3, bias=prefix + "mlp_shared.0.bias", act=ops.ACT_RELU)
+        wgb, bgb = self._gb(prefix)
+        gb = self._new(n, h, w, 2 * c)
+        ops.conv2d(actv, wgb, gb, kh=3, kw=3, stride=1, pad=1, bias=bgb)
+        dst = x if out is None else out
+        ops.instnorm_apply(x, stats, dst, gb=gb, relu=True)
+        return dst
+
+    def _residual_block(self, x, p):
+        """generator.py:9-32."""
+        c = x.shape[3]
+        h = self._conv_in_relu(x, p + "main.0.", p + "main.1.", c, 3)
+        return self._conv_in_relu(h, p + "main.3.", p + "main.4.", c, 3, relu=False, residual=x)
+
+    def _spade_residual_block(self, x, x_stats, p, seg, seg_cache, want_stats):
+        """generator.py:35-71 (dim_in == dim_out: identity shortcut).  ``x`` is preserved."""
+        c = x.shape[3]
+        if x_stats is None:
+            x_stats = ops.plane_stats(x, self._arena.take(x.shape[0], c))
+        h = self._spade_apply(x, x_stats, p + "norm_0.", seg, seg_cache, out=torch.empty_like(x))
+        dx, st = self._conv(h, p + "conv_0.weight", c, 3, bias=p + "conv_0.bias", want_stats=True)
+        h = self._spade_apply(dx, st, p + "norm_1.", seg, seg_cache)
+        return self._conv(h, p + "conv_1.weight", c, 3, bias=p + "conv_1.bias", residual=x, want_stats=want_stats)
+
+    def _is_spade_res(self, i: int) -> bool:
+        return bool(self.spade_layers[1] if i < self.repeat_num // 2 else self.spade_layers[2])
+
+    def _encoder(self, net, i, x, seg, seg_cache, out):
+        c = x.shape[3] * 2
+        p = f"{net}.encoders.{i}."
+        if self.spade_layers[0]:  # SPADEBlock, generator.py:74-90
+            raw, st = self._conv(x, p + "conv.weight", c, 3, stride=2, want_stats=True)
+            return self._spade_apply(raw, st, p + "norm.", seg, seg_cache, out=out)
+        return self._conv_in_relu(x, p + "0.", p + "1.", c, 3, stride=2, out=out)
+
+    def _resnet(self, net, i, x, x_stats, seg, seg_cache, want_stats):
+        p = f"{net}.resnets.{i}."
+        if self._is_spade_res(i):
+            return self._spade_residual_block(x, x_stats, p, seg, seg_cache, want_stats)
+        return self._residual_block(x, p), None
+
+    def _decode(self, net, x, cats, seg, seg_cache, final_out):
+        """generator.py:298-309.  ``cats[j]`` is the 2c-wide buffer whose first half already holds
+        encoder output j; the up-sampled tensor is normalised straight into its second half."""
+        d = x
+        for i in range(self.n_down):
+            c = d.shape[3] // 2
+            cat = cats[self.n_down - 1 - i]
+            p = f"{net}.decoders.{i}."
+            if self.spade_layers[3]:
+                raw, st = self._conv(d, p + "conv.weight", c, 3, transposed=True, want_stats=True)
+                self._spade_apply(raw, st, p + "norm.", seg, seg_cache, out=cat[..., c:])
+            else:
+                self._conv_in_relu(d, p + "0.", p + "1.", c, 3, transposed=True, out=cat[..., c:])
+            out = final_out if (i == self.n_down - 1 and final_out is not None) else None
+            d = self._conv_in_relu(cat, f"{net}.skippers.{i}.0.", f"{net}.skippers.{i}.1.", c, 3, out=out)
+        return d
+
+    def _head(self, name, x, cout, act):
+        """generator.py:311-315 (7x7 conv + tanh / sigmoid), returned as NCHW fp32."""
+        y, _ = self._conv(x, name + ".0.weight", cout, 7, act=act)
+        return ops.nhwc_to_nchw(y, cout)
+
+    def _warp(self, layer, src, tsf, T, flows):
+        """generator.py:480-491 + the residual add of :407/:427/:446; writes into ``tsf`` in place."""
+        h = src.shape[1]
+        attn = layer in self.attn_layers
+        key = (h, attn)
+        if key not in flows:
+            flows[key] = ops.resize_flow(T, h, subtract_identity=attn)
+        if not attn:
+            return ops.grid_sample(src, flows[key], tsf, tgt=tsf)
+        p = f"attn_{layer}.fully_connect_layer."
+        n, _, _, c = src.shape
+        hidden = self._new(n, h, h, ATTN_HIDDEN)
+        ops.conv2d(tsf, self._w(p + "0.weight"), hidden, kh=ATTN_K, kw=ATTN_K, stride=ATTN_K, pad=0, mode=ops.CONV_LOCAL_ATTN,
+                   x1=src, bias=self._f32(p + "0.bias"), act=ops.ACT_LEAKY, flow=flows[key])
+        w2 = self._cached(p + "2#w2", [self._p(p + "2.weight")],
+                          lambda: self._p(p + "2.weight").detach().float().reshape(ATTN_K * ATTN_K, ATTN_HIDDEN).contiguous())
+        return ops.attn_finish(hidden, w2, self._f32(p + "2.bias"), src, flows[key], tsf, tsf, ATTN_K)
+
+    def _to_nhwc(self, parts: Sequence[torch.Tensor]) -> torch.Tensor:
+        x = parts[0] if len(parts) == 1 else torch.cat(list(parts), 1)
+        x = x.float().contiguous()
+        b, c, h, w = x.shape
+        return ops.nchw_to_nhwc(x, self._new(b, h, w, ceil_to(c, 8)))
+
+    def _bg(self, x_nhwc):
+        """ResNetGenerator.forward, generator.py:93-135."""
+        p, i, c = "bg_model.model.", 0, self.conv_dim
+        h = self._conv_in_relu(x_nhwc, f"{p}{i}.", f"{p}{i + 1}.", c, 7); i += 3
+        for _ in range(self.n_down):
+            c *= 2
+            h = self._conv_in_relu(h, f"{p}{i}.", f"{p}{i + 1}.", c, 3, stride=2); i += 3
+        for _ in range(self.repeat_num):
+            h = self._residual_block(h, f"{p}{i}."); i += 1
+        for _ in range(self.n_down):
+            c //= 2
+            h = self._conv_in_relu(h, f"{p}{i}.", f"{p}{i + 1}.", c, 3, transposed=True); i += 3
+        y, _ = self._conv(h, f"{p}{i}.weight", 3, 7, act=ops.ACT_TANH)
+        return ops.nhwc_to_nchw(y, 3)
+
+    def _unet_features(self, net, x_nhwc, seg, seg_cache, final_out):
+        """ResUnetGenerator.forward (generator.py:260-281) up to the decoder output (obj_model)."""
+        n, H, W, _ = x_nhwc.shape
+        c = self.conv_dim
+        cats = []
+        cat0 = self._new(n, H, W, 2 * c)
+        h = self._conv_in_relu(x_nhwc, f"{net}.encoders.0.0.", f"{net}.encoders.0.1.", c, 7, out=cat0[..., :c])
+        cats.append(cat0)
+        for i in range(1, self.n_down + 1):
+            c *= 2
+            hh = h.shape[1] // 2
+            if i < self.n_down:
+                cat = self._new(n, hh, hh, 2 * c)
+                cats.append(cat)
+                out = cat[..., :c]
+            else:
+                out = None
+            h = self._encoder(net, i, h, seg, seg_cache, out)
+        st = None
+        for i in range(self.repeat_num):
+            nxt = i + 1 < self.repeat_num and self._is_spade_res(i + 1)
+            h, st = self._resnet(net, i, h, st, seg, seg_cache, want_stats=nxt)
+        return self._decode(net, h, cats, seg, seg_cache, final_out)
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, bg_inputs, src_obj_inputs, tsf_obj_inputs, src_hand_inputs, tsf_hand_inputs, T,
+                src_obj_conds=None, src_hand_conds=None, tsf_obj_conds=None, tsf_hand_conds=None,
+                src_armask=None, tsf_armask=None):
+        """generator.py:347-376.  Inputs NCHW fp32 CUDA tensors, ``T`` (B,H,W,2); returns the
+        reference's 10-tuple of NCHW fp32 tensors."""
+        self._dev = bg_inputs.device
+        self._arena = _StatsArena(self._dev)
+        # generator.py:351-365 background input assembly
+        src_bg = [bg_inputs, src_obj_inputs[:, 3:] if (src_obj_conds is None or src_hand_conds is None) else src_hand_conds]
+        tsf_bg = [bg_inputs, tsf_hand_inputs[:, 3:] if (tsf_obj_conds is None or tsf_hand_conds is None) else tsf_hand_conds]
+        if src_armask is not None:
+            src_bg.append(src_armask)
+        if tsf_armask is not None:
+            tsf_bg.append(tsf_armask)
+        src_img_bg = self._bg(self._to_nhwc(src_bg))
+        tsf_img_bg = self._bg(self._to_nhwc(tsf_bg))
+        outs = self._infer_front(src_obj_inputs, tsf_obj_inputs, src_hand_inputs, tsf_hand_inputs, T.float().contiguous(),
+                                 src_obj_conds, src_hand_conds, tsf_obj_conds, tsf_hand_conds)
+        self._arena = None
+        return (src_img_bg, tsf_img_bg) + outs
+
+    def _infer_front(self, src_obj_inputs, tsf_obj_inputs, src_hand_inputs, tsf_hand_inputs, T,
+                     src_obj_conds, src_hand_conds, tsf_obj_conds, tsf_hand_conds):
+        """generator.py:379-464."""
+        nd, c0 = self.n_down, self.conv_dim
+        seg_s, seg_t = {}, {}
+        flows: dict = {}
+        conds = [c.float().contiguous() if c is not None else None for c in (src_hand_conds, tsf_hand_conds, src_obj_conds, tsf_obj_conds)]
+        src_hand_conds, tsf_hand_conds, src_obj_conds, tsf_obj_conds = conds
+        xs = self._to_nhwc([src_hand_inputs])
+        xt = self._to_nhwc([tsf_hand_inputs])
+        n, H, W, _ = xs.shape
+
+        def cat_buf(level):
+            return self._new(n, H >> level, W >> level, 2 * c0 * 2 ** level)
+
+        s_cats, t_cats = [cat_buf(0)], [cat_buf(0)]
+        sx = self._conv_in_relu(xs, "src_model.encoders.0.0.", "src_model.encoders.0.1.", c0, 7, out=s_cats[0][..., :c0])
+        tx = self._conv_in_relu(xt, "tsf_model.encoders.0.0.", "tsf_model.encoders.0.1.", c0, 7, out=t_cats[0][..., :c0])
+        c = c0
+        for i in range(1, nd + 1):
+            c *= 2
+            if i < nd:
+                s_cats.append(cat_buf(i)); t_cats.append(cat_buf(i))
+                so, to = s_cats[i][..., :c], t_cats[i][..., :c]
+            else:
+                so = to = None
+            sx = self._encoder("src_model", i, sx, src_hand_conds, seg_s, so)
+            tx = self._encoder("tsf_model", i, tx, tsf_hand_conds, seg_t, to)
+            tx = self._warp(i, sx, tx, T, flows)            # tsf_x = tsf_x + warp   (:407)
+        s_st = None
+        for i in range(self.repeat_num):
+            nxt = i + 1 < self.repeat_num and self._is_spade_res(i + 1)
+            sx, s_st = self._resnet("src_model", i, sx, s_st, src_hand_conds, seg_s, want_stats=nxt)
+            tx, _ = self._resnet("tsf_model", i, tx, None, tsf_hand_conds, seg_t, want_stats=False)
+            tx = self._warp(i + nd + 1, sx, tx, T, flows)    # (:427, :446)
+        # decoders (:449-461): hand and object decoder outputs share one 2c-wide buffer per side so
+        # attetion_reg_bg's cat[x, y] input is a plain view
+        s_xy, t_xy = self._new(n, H, W, 2 * c0), self._new(n, H, W, 2 * c0)
+        seg_so, seg_to = {}, {}
+        self._unet_features("obj_model", self._to_nhwc([src_obj_inputs]), src_obj_conds, seg_so, s_xy[..., c0:])
+        self._unet_features("obj_model", self._to_nhwc([tsf_obj_inputs]), tsf_obj_conds, seg_to, t_xy[..., c0:])
+        self._decode("src_model", sx, s_cats, src_hand_conds, seg_s, s_xy[..., :c0])
+        self._decode("tsf_model", tx, t_cats, tsf_hand_conds, seg_t, t_xy[..., :c0])
+        res = {}
+        for tag, net, xy in (("src", "src_model", s_xy), ("tsf", "tsf_model", t_xy)):
+            res[tag + "_hand"] = self._head(net + ".img_reg", xy[..., :c0], 3, ops.ACT_TANH)
+            res[tag + "_mask_hand"] = self._head(net + ".attetion_reg_hand", xy[..., :c0], 1, ops.ACT_SIGMOID)
+            res[tag + "_mask_bg"] = self._head(net + ".attetion_reg_bg", xy, 1, ops.ACT_SIGMOID)
+            res[tag + "_obj"] = self._head("obj_model.img_reg", xy[..., c0:], 3, ops.ACT_TANH)
+        return (res["src_obj"], res["src_hand"], res["src_mask_bg"], res["src_mask_hand"],
+                res["tsf_obj"], res["tsf_hand"], res["tsf_mask_bg"], res["tsf_mask_hand"])
+
+
+def composite(img_bg, obj, hand, mask_bg, mask_hand):
+    """models/trainer.py:400-401 on device."""
+    return ops.composite(img_bg.contiguous(), obj.contiguous(), hand.contiguous(), mask_bg.contiguous(), mask_hand.contiguous())
+
+
+def create(network_name: str = "generator_spade_attn", dtype: torch.dtype = torch.bfloat16, **kwargs) -> GeneratorB200:
+    """Mirror of ``NetworksFactory.get_by_name`` (models/networks/__init__.py:9-36) for the generator names."""
+    table = {
+        "generator_base": dict(),
+        "generator_spade": dict(spade_layers=[1, 1, 0, 0]),
+        "generator_spade_attn": dict(spade_layers=[1, 1, 0, 0], attn_layers=[1, 2, 3, 4, 5, 6, 7, 8, 9]),
+        "generator_spade_attn_tiny": dict(spade_layers=[0, 0, 1, 1], attn_layers=[1, 2, 3, 4, 5, 6, 7, 8, 9]),
+    }
+    if network_name not in table:
+        raise ValueError("Network %s not recognized." % network_name)
+    return GeneratorB200(**kwargs, **table[network_name], dtype=dtype)

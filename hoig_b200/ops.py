@@ -1,0 +1,267 @@
+"""Tensor-level wrappers over the C ABI (``include/hoig_b200.h``).
+
+PyTorch is used for device memory and streams only.  Activations inside the
+generator are NHWC tensors ``(N, H, W, C)`` whose channel dimension may be a
+slice of a wider buffer (``stride(2) = ld >= C``).  Every function launches on
+the current torch stream and raises ``RuntimeError`` on a non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, CONV, CONV_LOCAL_ATTN,  # noqa: F401
+                   CONV_TRANSPOSED, HOIG_BF16, HOIG_F32, ConvDesc)
+
+_DT = {torch.float32: HOIG_F32, torch.bfloat16: HOIG_BF16}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"hoig_b200: unsupported dtype {t.dtype}") from None
+
+
+def _nhwc(t: torch.Tensor, name: str):
+    """(ptr, ld) of an NHWC view; validates the layout."""
+    if t.dim() != 4 or not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA (N,H,W,C) tensor, got {tuple(t.shape)} on {t.device}")
+    n, h, w, c = t.shape
+    ld = t.stride(2)
+    if t.stride(3) != 1 or t.stride(1) != w * ld or (n > 1 and t.stride(0) != h * w * ld) or ld < c:
+        raise ValueError(f"{name}: not an NHWC view (shape {tuple(t.shape)}, strides {t.stride()})")
+    return t.data_ptr(), ld
+
+
+def _f32c(t: torch.Tensor, name: str) -> int:
+    if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+        raise ValueError(f"{name}: expected a contiguous CUDA float32 tensor")
+    return t.data_ptr()
+
+
+def packed_dims(cout: int, kh: int, kw: int, cin: int):
+    r, c = ctypes.c_int(), ctypes.c_int()
+    _lib.load().hoig_conv_packed_dims(cout, kh, kw, cin, ctypes.byref(r), ctypes.byref(c))
+    return r.value, c.value
+
+
+# ------------------------------------------------------------------ stage R
+def rasterize(faces: torch.Tensor, image_size: int = 256, near: float = 0.1, far: float = 100.0,
+              flip_y: bool = True, return_depth: bool = False):
+    """faces (B,F,3,3) f32 -> fim (B,is,is) int32, wim (B,is,is,3) f32[, depth (B,is,is)]."""
+    B, F = faces.shape[:2]
+    fp = _f32c(faces, "faces")
+    fim = torch.empty(B, image_size, image_size, dtype=torch.int32, device=faces.device)
+    wim = torch.empty(B, image_size, image_size, 3, dtype=torch.float32, device=faces.device)
+    depth = torch.empty(B, image_size, image_size, dtype=torch.float32, device=faces.device) if return_depth else None
+    L = _lib.lib()
+    _lib.check(L.hoig_rasterize_fim_wim(fp, B, F, image_size, near, far, int(flip_y), fim.data_ptr(), wim.data_ptr(),
+                                        depth.data_ptr() if depth is not None else None, None, 0, _stream()),
+               "rasterize_fim_wim")
+    return (fim, wim, depth) if return_depth else (fim, wim)
+
+
+def face_inv(faces: torch.Tensor, image_size: int) -> torch.Tensor:
+    out = torch.zeros(faces.shape[0], faces.shape[1], 9, dtype=torch.float32, device=faces.device)
+    _lib.check(_lib.lib().hoig_face_inv(_f32c(faces, "faces"), faces.shape[0] * faces.shape[1], image_size,
+                                        out.data_ptr(), _stream()), "face_inv")
+    return out
+
+
+def project_faces(verts: torch.Tensor, cam: torch.Tensor, faces_idx: torch.Tensor, eye_z: float) -> torch.Tensor:
+    B, V = verts.shape[:2]
+    F = faces_idx.shape[0]
+    assert faces_idx.dtype == torch.int32 and faces_idx.is_contiguous()
+    out = torch.empty(B, F, 3, 3, dtype=torch.float32, device=verts.device)
+    _lib.check(_lib.lib().hoig_project_faces(_f32c(verts, "verts"), _f32c(cam, "cam"), faces_idx.data_ptr(), B, V, F,
+                                             eye_z, out.data_ptr(), _stream()), "project_faces")
+    return out
+
+
+def condition_maps(fim: torch.Tensor, map_fn: torch.Tensor, sem_full: torch.Tensor, n_hand_faces: int):
+    B, H, W = fim.shape
+    F = map_fn.shape[0] - 1
+    dev = fim.device
+    cond = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev)
+    seg = torch.empty(B, 15, H, W, dtype=torch.float32, device=dev)
+    not_hand = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev)
+    _lib.check(_lib.lib().hoig_condition_maps(fim.data_ptr(), B, F, H, _f32c(map_fn, "map_fn"),
+                                              _f32c(sem_full.reshape(-1), "sem_full"), n_hand_faces, cond.data_ptr(),
+                                              seg.data_ptr(), not_hand.data_ptr(), _stream()), "condition_maps")
+    return cond, seg, not_hand
+
+
+def bc_transform(src_faces: torch.Tensor, fim_ref: torch.Tensor, wim_ref: torch.Tensor) -> torch.Tensor:
+    B, F = src_faces.shape[:2]
+    H = fim_ref.shape[1]
+    T = torch.empty(B, H, H, 2, dtype=torch.float32, device=fim_ref.device)
+    _lib.check(_lib.lib().hoig_bc_transform(_f32c(src_faces, "src_faces"), fim_ref.data_ptr(), _f32c(wim_ref, "wim"),
+                                            B, F, H, T.data_ptr(), _stream()), "bc_transform")
+    return T
+
+
+def erode(mask: torch.Tensor, ks: int) -> torch.Tensor:
+    B, _, H, W = mask.shape
+    out = torch.empty_like(mask)
+    _lib.check(_lib.lib().hoig_erode(_f32c(mask, "mask"), out.data_ptr(), B, H, W, ks, _stream()), "erode")
+    return out
+
+
+# ------------------------------------------------------- reference op boundary
+def block_extract(source: torch.Tensor, flow: torch.Tensor, out: torch.Tensor, k: int) -> torch.Tensor:
+    B, C, Hs, Ws = source.shape
+    _, two, Hf, Wf = flow.shape
+    if two != 2 or out.shape != (B, C, k * Hf, k * Wf):
+        raise ValueError("block_extract: shape mismatch")
+    _lib.check(_lib.lib().hoig_block_extract_f32(_f32c(source, "source"), _f32c(flow, "flow"), _f32c(out, "output"),
+                                                 B, C, Hs, Ws, Hf, Wf, k, _stream()), "block_extract_f32")
+    return out
+
+
+def local_attn_reshape(inputs: torch.Tensor, out: torch.Tensor, k: int) -> torch.Tensor:
+    B, kk, H, W = inputs.shape
+    if kk != k * k or out.shape != (B, 1, k * H, k * W):
+        raise ValueError("local_attn_reshape: shape mismatch")
+    _lib.check(_lib.lib().hoig_local_attn_reshape_f32(_f32c(inputs, "inputs"), _f32c(out, "output"), B, k, H, W,
+                                                      _stream()), "local_attn_reshape_f32")
+    return out
+
+
+# ------------------------------------------------------------------ stage G
+def conv2d(x0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, *, kh: int, kw: int, stride: int = 1,
+           pad: int = 0, mode: int = CONV, x1: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+           act: int = ACT_NONE, residual: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
+           flow: Optional[torch.Tensor] = None, cout: Optional[int] = None, simt: bool = False) -> torch.Tensor:
+    """Implicit-GEMM convolution; see ``hoigConvDesc``.  ``weight`` is the packed matrix
+    from :func:`hoig_b200.packing.pack_conv_weight`; ``out`` is an NHWC view."""
+    d = ConvDesc()
+    d.dtype, d.mode = _dt(x0), mode
+    N, H, W, C0 = x0.shape
+    d.N, d.H, d.W, d.C0 = N, H, W, C0
+    d.src0, d.ld0 = _nhwc(x0, "x0")
+    if x1 is not None:
+        if x1.shape[:3] != x0.shape[:3] or x1.dtype != x0.dtype:
+            raise ValueError("conv2d: x1 must match x0 in batch/spatial size and dtype")
+        d.C1 = x1.shape[3]
+        d.src1, d.ld1 = _nhwc(x1, "x1")
+    else:
+        d.C1, d.src1, d.ld1 = 0, None, 0
+    No, OH, OW, Co = out.shape
+    d.OH, d.OW, d.Cout = OH, OW, (cout if cout is not None else Co)
+    d.KH, d.KW, d.stride, d.pad = kh, kw, stride, pad
+    rows, cols = packed_dims(d.Cout, kh, kw, d.C0 + d.C1)
+    if tuple(weight.shape) != (rows, cols) or weight.dtype != x0.dtype or not weight.is_contiguous():
+        raise ValueError(f"conv2d: packed weight must be {(rows, cols)} {x0.dtype}, got {tuple(weight.shape)} {weight.dtype}")
+    if No != N or out.dtype != x0.dtype:
+        raise ValueError("conv2d: output batch/dtype mismatch")
+    d.weight = weight.data_ptr()
+    d.bias = _f32c(bias, "bias") if bias is not None else None
+    d.act = act
+    if residual is not None:
+        d.residual, d.ldr = _nhwc(residual, "residual")
+    else:
+        d.residual, d.ldr = None, 0
+    d.dst, d.ldd = _nhwc(out, "out")
+    d.stats = stats.data_ptr() if stats is not None else None
+    if stats is not None and (stats.dtype != torch.float64 or stats.numel() != N * d.Cout * 2):
+        raise ValueError("conv2d: stats must be float64 [N, Cout, 2]")
+    d.flow = _f32c(flow, "flow") if flow is not None else None
+    L = _lib.lib()
+    fn = L.hoig_conv2d_simt if simt else L.hoig_conv2d
+    _lib.check(fn(ctypes.byref(d), _stream()), "conv2d")
+    return out
+
+
+def nchw_to_nhwc(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    B, C, H, W = x.shape
+    ptr, ld = _nhwc(out, "out")
+    _lib.check(_lib.lib().hoig_nchw_to_nhwc(_f32c(x, "x"), B, C, H, W, ptr, ld, out.shape[3], _dt(out), _stream()),
+               "nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, channels: int) -> torch.Tensor:
+    N, H, W, _ = x.shape
+    ptr, ld = _nhwc(x, "x")
+    out = torch.empty(N, channels, H, W, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().hoig_nhwc_to_nchw(ptr, ld, _dt(x), N, channels, H, W, out.data_ptr(), _stream()), "nhwc_to_nchw")
+    return out
+
+
+def seg_resize(seg: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    B, C, Hi, Wi = seg.shape
+    _, Ho, Wo, Cpad = out.shape
+    ptr, ld = _nhwc(out, "out")
+    _lib.check(_lib.lib().hoig_seg_resize_nearest(_f32c(seg, "seg"), B, C, Hi, Wi, ptr, ld, Cpad, Ho, Wo, _dt(out),
+                                                  _stream()), "seg_resize_nearest")
+    return out
+
+
+def plane_stats(x: torch.Tensor, stats: torch.Tensor) -> torch.Tensor:
+    N, H, W, C = x.shape
+    ptr, ld = _nhwc(x, "x")
+    _lib.check(_lib.lib().hoig_plane_stats(ptr, ld, _dt(x), N, H * W, C, stats.data_ptr(), _stream()), "plane_stats")
+    return stats
+
+
+def instnorm_apply(x: torch.Tensor, stats: torch.Tensor, out: torch.Tensor, *, gamma=None, beta=None, gb=None,
+                   residual=None, relu: bool = False, eps: float = 1e-5) -> torch.Tensor:
+    N, H, W, C = x.shape
+    xp, ldx = _nhwc(x, "x")
+    op, ldo = _nhwc(out, "out")
+    gp, ldg = _nhwc(gb, "gb") if gb is not None else (None, 0)
+    rp, ldr = _nhwc(residual, "residual") if residual is not None else (None, 0)
+    _lib.check(_lib.lib().hoig_instnorm_apply(xp, ldx, stats.data_ptr(),
+                                              _f32c(gamma, "gamma") if gamma is not None else None,
+                                              _f32c(beta, "beta") if beta is not None else None,
+                                              gp, ldg, rp, ldr, int(relu), op, ldo, _dt(x), N, H * W, C, eps, _stream()),
+               "instnorm_apply")
+    return out
+
+
+def resize_flow(T: torch.Tensor, h: int, subtract_identity: bool = True) -> torch.Tensor:
+    B, Hi, Wi, _ = T.shape
+    flow = torch.empty(B, h, h, 2, dtype=torch.float32, device=T.device)
+    _lib.check(_lib.lib().hoig_resize_flow(_f32c(T, "T"), B, Hi, Wi, h, int(subtract_identity), flow.data_ptr(),
+                                           _stream()), "resize_flow")
+    return flow
+
+
+def attn_finish(hidden: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, src: torch.Tensor, flow: torch.Tensor,
+                tgt: torch.Tensor, out: torch.Tensor, k: int) -> torch.Tensor:
+    N, h, _, C = src.shape
+    hp, ldh = _nhwc(hidden, "hidden")
+    sp, lds = _nhwc(src, "src")
+    tp, ldt = _nhwc(tgt, "tgt")
+    op, ldo = _nhwc(out, "out")
+    _lib.check(_lib.lib().hoig_attn_finish(hp, ldh, hidden.shape[3], _f32c(w2, "w2"), _f32c(b2, "b2"), sp, lds,
+                                           _f32c(flow, "flow"), tp, ldt, op, ldo, _dt(src), N, h, C, k, _stream()),
+               "attn_finish")
+    return out
+
+
+def grid_sample(x: torch.Tensor, grid: torch.Tensor, out: torch.Tensor, tgt: Optional[torch.Tensor] = None):
+    N, h, _, C = x.shape
+    xp, ldx = _nhwc(x, "x")
+    op, ldo = _nhwc(out, "out")
+    tp, ldt = _nhwc(tgt, "tgt") if tgt is not None else (None, 0)
+    _lib.check(_lib.lib().hoig_grid_sample(xp, ldx, _f32c(grid, "grid"), tp, ldt, op, ldo, _dt(x), N, h, C, _stream()),
+               "grid_sample")
+    return out
+
+
+def composite(img_bg, obj, hand, mask_bg, mask_hand) -> torch.Tensor:
+    B, _, H, W = img_bg.shape
+    out = torch.empty_like(img_bg)
+    _lib.check(_lib.lib().hoig_composite(_f32c(img_bg, "img_bg"), _f32c(obj, "obj"), _f32c(hand, "hand"),
+                                         _f32c(mask_bg, "mask_bg"), _f32c(mask_hand, "mask_hand"), out.data_ptr(), B,
+                                         H * W, _stream()), "composite")
+    return out

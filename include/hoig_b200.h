@@ -1,0 +1,176 @@
+/*
+ * hoig_b200.h -- C ABI of the B200-native HOGAN generator hot path.
+ *
+ * One shared library (libhoig_b200.so), plain pointers and sizes, explicit
+ * stream, no torch types.  Every entry point returns 0 on success or a
+ * negative hoigStatus; none allocates device memory (workspaces are passed
+ * in), none throws, all are asynchronous on `stream`.  hoig_last_error()
+ * returns a thread-local description of the most recent failure.
+ *
+ * Each function cites the reference interface it replaces
+ * (paths relative to /root/reference/HOIG_HOv3).
+ *
+ * Activation tensors inside the generator are NHWC ("pixel-major"): element
+ * (n,y,x,c) of a tensor with pixel stride `ld` lives at
+ * base[((n*H + y)*W + x)*ld + c].  `ld >= C` lets a tensor be a channel slice
+ * of a wider buffer (the U-Net skip concatenations are never materialised
+ * separately).  dtype: HOIG_F32 (SIMT fp32 parity path) or HOIG_BF16
+ * (tcgen05 tensor-core path, fp32 accumulate).
+ */
+#ifndef HOIG_B200_H_
+#define HOIG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *hoigStream_t; /* a cudaStream_t */
+
+typedef enum {
+    HOIG_OK = 0,
+    HOIG_ERR_INVALID = -1,   /* bad argument (shape, alignment, null) */
+    HOIG_ERR_WORKSPACE = -2, /* workspace too small */
+    HOIG_ERR_CUDA = -3,      /* a CUDA runtime/driver call or launch failed */
+    HOIG_ERR_ARCH = -4       /* device is not sm_100 */
+} hoigStatus;
+
+typedef enum { HOIG_F32 = 0, HOIG_BF16 = 1 } hoigDType;
+typedef enum { HOIG_ACT_NONE = 0, HOIG_ACT_RELU = 1, HOIG_ACT_LEAKY = 2, HOIG_ACT_TANH = 3, HOIG_ACT_SIGMOID = 4 } hoigAct;
+typedef enum { HOIG_CONV = 0, HOIG_CONV_TRANSPOSED = 1, HOIG_CONV_LOCAL_ATTN = 2 } hoigConvMode;
+
+const char *hoig_version(void);
+const char *hoig_last_error(void);
+/* 0 if the current device is compute capability 10.x, else HOIG_ERR_ARCH / HOIG_ERR_CUDA. */
+int hoig_check_device(void);
+
+/* ------------------------------------------------------------------ stage R
+ * Condition rasterizer.  Replaces
+ *   thirdparty/neural_renderer/neural_renderer/cuda/rasterize_cuda.cpp:70-95
+ *   (forward_face_index_map: kernels _1 and _2 of rasterize_cuda_kernel.cu:41-186)
+ * plus the output initialisation of rasterize.py:50-52 and the vertical flip
+ * of rasterize.py:335-338, batched over B meshes in one call.
+ *   faces  (B,F,3,3) f32 camera-space xyz per face vertex
+ *   fim    (B,is,is) int32, -1 = background        [bit-exact with the reference]
+ *   wim    (B,is,is,3) f32 barycentric weights, 0 on background
+ *   depth  (B,is,is) f32 or NULL, `far` on background
+ *   flip_y != 0 writes row (is-1-y), i.e. torch.flip(dims=(1,)).
+ * image_size must be a multiple of 16.  Workspace: hoig_rasterize_workspace_bytes. */
+size_t hoig_rasterize_workspace_bytes(int B, int F, int image_size);
+int hoig_rasterize_fim_wim(const float *faces, int B, int F, int image_size, float near, float far,
+                           int flip_y, int32_t *fim, float *wim, float *depth,
+                           void *workspace, size_t workspace_bytes, hoigStream_t stream);
+
+/* Per-face inverse matrices only (kernel _1, rasterize_cuda_kernel.cu:41-84);
+ * faces_inv (B*F,9) must be zero-filled by the caller like rasterize.py:164. */
+int hoig_face_inv(const float *faces, int64_t BF, int image_size, float *faces_inv, hoigStream_t stream);
+
+/* R0: projection + look_at + vertices_to_faces fused (utils/nmr.py:109-140,:506;
+ * neural_renderer/look_at.py:6-62 with eye (0,0,eye_z), identity rotation;
+ * vertices_to_faces.py:4-22).  verts (B,V,3), cam (B,15), faces_idx (F,3) int32
+ * shared by the batch -> faces (B,F,3,3). */
+int hoig_project_faces(const float *verts, const float *cam, const int32_t *faces_idx,
+                       int B, int V, int F, float eye_z, float *faces, hoigStream_t stream);
+
+/* R4-R7: condition maps from fim/wim (utils/nmr.py:567-595 encode_fim/encode_sem,
+ * models/trainer.py:71-72 one-hot seg + hand mask, utils/nmr.py:874-925
+ * cal_bc_transform's T).  Outputs NCHW f32:
+ *   cond (B,3,is,is) = map_fn[fim]; seg (B,15,is,is) = (sem_full[fim]==i), i=1..15;
+ *   not_hand (B,1,is,is) = 1 - [(fim!=-1)&(fim<n_hand_faces)]   (pre-erosion);
+ *   T (B,is,is,2) or NULL: sum_k src_faces[fim_ref][k].xy(y negated) * wim_ref[k], -2 where fim_ref==-1.
+ * map_fn (F+1,3), sem_full (F+1) with the background row last (fim=-1). */
+int hoig_condition_maps(const int32_t *fim, int B, int F, int image_size, const float *map_fn,
+                        const float *sem_full, int n_hand_faces, float *cond, float *seg,
+                        float *not_hand, hoigStream_t stream);
+int hoig_bc_transform(const float *src_faces, const int32_t *fim_ref, const float *wim_ref,
+                      int B, int F, int image_size, float *T, hoigStream_t stream);
+/* R6 utils/util.py:142-153 erode (pad value 1, all-ones ks x ks window). in/out (B,1,H,W) f32. */
+int hoig_erode(const float *in, float *out, int B, int H, int W, int ks, hoigStream_t stream);
+
+/* ------------------------------------------------- reference op boundary B2
+ * thirdparty/block_extractor/block_extractor_cuda.cc:5-16 (forward):
+ *   source (B,C,Hs,Ws), flow (B,2,Hf,Wf), out (B,C,k*Hf,k*Wf), all NCHW f32. */
+int hoig_block_extract_f32(const float *source, const float *flow, float *out, int B, int C,
+                           int Hs, int Ws, int Hf, int Wf, int k, hoigStream_t stream);
+/* thirdparty/local_attn_reshape/local_attn_reshape_cuda.cc:5-13 (forward):
+ *   in (B,k*k,H,W) -> out (B,1,k*H,k*W). */
+int hoig_local_attn_reshape_f32(const float *in, float *out, int B, int k, int H, int W, hoigStream_t stream);
+
+/* ----------------------------------------------------------------- stage G
+ * Building blocks of Generator.forward (models/networks/generator.py:347-491,
+ * spade.py:24-38, extract_attn.py:23-29).  The host-side schedule lives in
+ * hoig_b200/generator.py (GeneratorB200, drop-in for the reference Generator). */
+
+typedef struct {
+    int dtype;          /* hoigDType of activations and packed weights */
+    int mode;           /* hoigConvMode */
+    int N, H, W;        /* input batch / spatial size */
+    int C0, C1;         /* channels taken from src0 / src1 (C1 = 0: single source); multiples of 8 */
+    int OH, OW, Cout;   /* output size; Cout = logical output channels */
+    int KH, KW, stride, pad;
+    const void *src0; int64_t ld0;
+    const void *src1; int64_t ld1;
+    const void *weight; /* packed [Cout_pad][K_pad], k = (r*KW + s)*(C0+C1) + c; see hoig_conv_packed_dims */
+    const float *bias;  /* [Cout] or NULL */
+    int act;            /* hoigAct applied after bias (+ residual) */
+    const void *residual; int64_t ldr; /* NHWC (N,OH,OW,Cout) added before `act`, or NULL */
+    void *dst; int64_t ldd;            /* NHWC (N,OH,OW,>=Cout) */
+    double *stats;      /* NULL or [N][Cout][2]: += per-plane sum / sum of squares of the stored values */
+    const float *flow;  /* HOIG_CONV_LOCAL_ATTN only: (N,H,W,2) pixel-unit offsets (x,y) */
+} hoigConvDesc;
+
+/* Rows / columns of the packed weight matrix for a given problem
+ * (Cout padded to 16, K padded to 64 elements). */
+int hoig_conv_packed_dims(int Cout, int KH, int KW, int Cin, int *rows, int *cols);
+/* Implicit-GEMM convolution (nn.Conv2d / nn.ConvTranspose2d k3 s2 p1 op1 /
+ * the k5 s5 conv over cat[BlockExtractor(tgt,0), BlockExtractor(src,flow)] of
+ * extract_attn.py:24-26 with both extractions fused into the operand gather).
+ * dtype BF16: tcgen05.mma (kind::f16, fp32 accumulators in TMEM), weights by TMA.
+ * dtype F32 : SIMT fp32 FFMA. */
+int hoig_conv2d(const hoigConvDesc *desc, hoigStream_t stream);
+
+/* NCHW f32 (B,C,H,W) -> NHWC dtype with `Cpad` channels (extra channels zero). */
+int hoig_nchw_to_nhwc(const float *src, int B, int C, int H, int W, void *dst, int64_t ldd, int Cpad,
+                      int dtype, hoigStream_t stream);
+/* NHWC dtype -> NCHW f32 (first C channels). */
+int hoig_nhwc_to_nchw(const void *src, int64_t lds, int dtype, int B, int C, int H, int W, float *dst,
+                      hoigStream_t stream);
+/* spade.py:30 F.interpolate(segmap, size, 'nearest') fused with the layout change:
+ * seg NCHW f32 (B,C,Hi,Wi) -> NHWC dtype (B,Ho,Wo,Cpad). */
+int hoig_seg_resize_nearest(const float *seg, int B, int C, int Hi, int Wi, void *dst, int64_t ldd, int Cpad,
+                            int Ho, int Wo, int dtype, hoigStream_t stream);
+/* per-(n,c) sum / sum-of-squares of an NHWC tensor into stats [N][C][2] (+=). */
+int hoig_plane_stats(const void *x, int64_t ldx, int dtype, int N, int HW, int C, double *stats, hoigStream_t stream);
+/* nn.InstanceNorm2d (eps 1e-5, biased variance) finalisation:
+ *   y = (x-mean)*rstd;  affine: y = y*gamma[c]+beta[c]   (generator.py:16-22 ...)
+ *   SPADE (spade.py:36): y = y*(1+gb[...,c]) + gb[...,C+c]   (gb NHWC with 2C channels)
+ *   y += residual (optional, generator.py:31);  relu optional. */
+int hoig_instnorm_apply(const void *x, int64_t ldx, const double *stats, const float *gamma, const float *beta,
+                        const void *gb, int64_t ldgb, const void *residual, int64_t ldr, int relu,
+                        void *dst, int64_t ldd, int dtype, int N, int HW, int C, float eps, hoigStream_t stream);
+/* generator.py:466-473 resize_trans (bilinear, align_corners=True, size=(h,h)) fused with
+ * generator.py:484-488  flow = T_scale - idt   ('ij' identity grid, quirks Q1-Q3).
+ * T (B,Hi,Wi,2) f32 -> flow (B,h,h,2) f32.  subtract_identity = 0 returns T_scale itself
+ * (the grid generator.py:475-478 hands to grid_sample for the non-attention variants). */
+int hoig_resize_flow(const float *T, int B, int Hi, int Wi, int h, int subtract_identity, float *flow,
+                     hoigStream_t stream);
+/* extract_attn.py:24-28 tail: logits = W2 . hidden + b2 (conv1x1 128->k*k), softmax over k*k,
+ * out = tgt + (1/k^2) * sum_t softmax_t * BlockExtractor(src,flow)[tap t]   (avg_pool of attn*block)
+ * hidden (N,h,h,Chid) dtype, w2 [k*k][Chid] f32, b2 [k*k] f32; src/tgt/dst NHWC (N,h,h,C). */
+int hoig_attn_finish(const void *hidden, int64_t ldh, int Chid, const float *w2, const float *b2,
+                     const void *src, int64_t lds, const float *flow, const void *tgt, int64_t ldt,
+                     void *dst, int64_t ldd, int dtype, int N, int h, int C, int k, hoigStream_t stream);
+/* generator.py:475-478 stn: F.grid_sample(x, grid) bilinear / zeros / align_corners=False;
+ * x, dst NHWC (N,h,h,C); grid (N,h,h,2) f32; dst = tgt + sample when tgt != NULL. */
+int hoig_grid_sample(const void *x, int64_t ldx, const float *grid, const void *tgt, int64_t ldt,
+                     void *dst, int64_t ldd, int dtype, int N, int h, int C, hoigStream_t stream);
+/* models/trainer.py:400-401: img = m_bg*bg + (1-m_bg)*(obj*m_hand + hand*(1-m_hand)); NCHW f32, 3 channels. */
+int hoig_composite(const float *img_bg, const float *obj, const float *hand, const float *mask_bg,
+                   const float *mask_hand, float *out, int B, int HW, hoigStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOIG_B200_H_ */

@@ -1,0 +1,146 @@
+"""Torch-CPU emulation of the ``hoig_b200.ops`` contracts -- TEST INFRASTRUCTURE ONLY.
+
+Lets the host-side schedule and weight packing of ``GeneratorB200`` be checked
+against the oracle in a container without a GPU.  Each function implements the
+documented contract of the C-ABI op of the same name (include/hoig_b200.h) with
+plain torch ops; it is also the executable specification the CUDA kernels are
+tested against on the GPU box.  Never imported by the product.
+"""
+import torch
+import torch.nn.functional as F
+
+from hoig_b200 import ops as real_ops
+from hoig_b200.packing import ceil_to
+from oracle import generator_ref as gr
+
+ACT = {0: lambda v: v, 1: F.relu, 2: lambda v: F.leaky_relu(v, 0.01), 3: torch.tanh, 4: torch.sigmoid}
+
+
+def _q(t, like):
+    """Round through the storage dtype (bf16 path) so emulation mirrors kernel rounding points."""
+    return t.to(like.dtype)
+
+
+def unpack_weight(wp, cout, kh, kw, cin_p):
+    w = wp.float()[:cout, : kh * kw * cin_p].reshape(cout, kh, kw, cin_p)
+    return w.permute(0, 3, 1, 2).contiguous()  # OIHW over padded input channels
+
+
+def conv2d(x0, weight, out, *, kh, kw, stride=1, pad=0, mode=0, x1=None, bias=None, act=0, residual=None, stats=None,
+           flow=None, cout=None, simt=False):
+    x = x0 if x1 is None else torch.cat([x0, x1], 3)
+    cin_p = x.shape[3]
+    cout = out.shape[3] if cout is None else cout
+    w = unpack_weight(weight, cout, kh, kw, cin_p)
+    xn = x.float().permute(0, 3, 1, 2)
+    if mode == real_ops.CONV:
+        y = F.conv2d(xn, w, None, stride=stride, padding=pad)
+    elif mode == real_ops.CONV_TRANSPOSED:
+        y = F.conv_transpose2d(xn, w.permute(1, 0, 2, 3), None, stride=stride, padding=pad, output_padding=1)
+    else:
+        c = x0.shape[3]
+        tgt, src = xn[:, :c], xn[:, c:]
+        fl = flow.permute(0, 3, 1, 2)
+        bs = _q(gr.block_extract(src, fl, kh), x0).float()
+        bt = gr.block_extract(tgt, torch.zeros_like(fl), kh)
+        y = F.conv2d(torch.cat([bt, bs], 1), w, None, stride=kh)
+    if bias is not None:
+        y = y + bias.view(1, -1, 1, 1)
+    y = y.permute(0, 2, 3, 1)
+    if residual is not None:
+        y = y + residual[..., :cout].float()
+    y = _q(ACT[act](y), out)
+    out[..., :cout] = y
+    if stats is not None:
+        yf = y.double()
+        st = torch.stack([yf.sum((1, 2)), (yf * yf).sum((1, 2))], 2)  # (N, C, 2)
+        stats += st.reshape(-1)
+    return out
+
+
+def nchw_to_nhwc(x, out):
+    out.zero_()
+    out[..., : x.shape[1]] = x.permute(0, 2, 3, 1).to(out.dtype)
+    return out
+
+
+def nhwc_to_nchw(x, channels):
+    return x[..., :channels].float().permute(0, 3, 1, 2).contiguous()
+
+
+def seg_resize(seg, out):
+    s = F.interpolate(seg, size=out.shape[1:3], mode="nearest")
+    return nchw_to_nhwc(s, out)
+
+
+def plane_stats(x, stats):
+    xf = x.double()
+    stats += torch.stack([xf.sum((1, 2)), (xf * xf).sum((1, 2))], 2).reshape(-1)
+    return stats
+
+
+def instnorm_apply(x, stats, out, *, gamma=None, beta=None, gb=None, residual=None, relu=False, eps=1e-5):
+    n, h, w, c = x.shape
+    st = stats.reshape(n, c, 2)
+    mean = st[..., 0] / (h * w)
+    var = (st[..., 1] / (h * w) - mean * mean).clamp_min(0)
+    rstd = (1.0 / torch.sqrt(var + eps)).float()
+    y = (x.float() - mean.float()[:, None, None, :]) * rstd[:, None, None, :]
+    if gamma is not None:
+        y = y * gamma + beta
+    if gb is not None:
+        y = y * (1 + gb[..., :c].float()) + gb[..., c:2 * c].float()
+    if residual is not None:
+        y = y + residual.float()
+    if relu:
+        y = F.relu(y)
+    out.copy_(y.to(out.dtype))
+    return out
+
+
+def resize_flow(T, h, subtract_identity=True):
+    t = gr.resize_trans(T, h)
+    if subtract_identity:
+        t = t - gr.identity_grid(h, T.device)
+    return t.contiguous()
+
+
+def attn_finish(hidden, w2, b2, src, flow, tgt, out, k):
+    n, h, _, c = src.shape
+    logits = hidden.float() @ w2.t() + b2                      # (N,h,h,k*k)
+    a = F.softmax(logits, 3).permute(0, 3, 1, 2)
+    bs = gr.block_extract(src.float().permute(0, 3, 1, 2), flow.permute(0, 3, 1, 2), k)
+    res = F.avg_pool2d(gr.local_attn_reshape(a, k) * bs, k, k).permute(0, 2, 3, 1)
+    out.copy_((tgt.float() + res).to(out.dtype))
+    return out
+
+
+def grid_sample(x, grid, out, tgt=None):
+    y = F.grid_sample(x.float().permute(0, 3, 1, 2), grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+    y = y.permute(0, 2, 3, 1)
+    if tgt is not None:
+        y = y + tgt.float()
+    out.copy_(y.to(out.dtype))
+    return out
+
+
+def composite(img_bg, obj, hand, mask_bg, mask_hand):
+    return gr.composite(img_bg, obj, hand, mask_bg, mask_hand)
+
+
+def install(monkeypatch):
+    """Route hoig_b200.generator's op calls to this module (CPU)."""
+    import hoig_b200.generator as G
+
+    class _Ops:
+        pass
+
+    emu = _Ops()
+    for k in dir(real_ops):
+        if k.isupper():
+            setattr(emu, k, getattr(real_ops, k))
+    for name in ("conv2d", "nchw_to_nhwc", "nhwc_to_nchw", "seg_resize", "plane_stats", "instnorm_apply", "resize_flow",
+                 "attn_finish", "grid_sample", "composite"):
+        setattr(emu, name, globals()[name])
+    monkeypatch.setattr(G, "ops", emu)
+    return emu
