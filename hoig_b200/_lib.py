@@ -57,6 +57,7 @@ _SIGNATURES = {
     "hoig_conv_packed_dims": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
     "hoig_conv2d": (c_int, [POINTER(ConvDesc), c_void_p]),
     "hoig_conv2d_simt": (c_int, [POINTER(ConvDesc), c_void_p]),
+    "hoig_set_umma_gather_only": (None, [c_int]),
     "hoig_nchw_to_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "hoig_nhwc_to_nchw": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hoig_seg_resize_nearest": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_int,
@@ -101,11 +102,68 @@ def check(status: int, what: str) -> None:
         raise RuntimeError(f"hoig_b200.{what} failed (status {status}): {msg}")
 
 
-def lib() -> ctypes.CDLL:
+class LaunchRecorder:
+    """Counts kernel launches made through the C ABI and, when ``timing`` is on, brackets each
+    with CUDA events on the launching (current torch) stream.  Used by bench.py / profiling."""
+
+    def __init__(self):
+        self.launches = 0
+        self.timing = False
+        self.records = []   # (entry point, start event, end event)
+
+    def reset(self, timing: bool = False):
+        self.launches, self.timing, self.records = 0, timing, []
+
+    def summary(self):
+        """{entry point: (launch count, total ms)} -- call after torch.cuda.synchronize()."""
+        out = {}
+        for name, s, e in self.records:
+            n, t = out.get(name, (0, 0.0))
+            out[name] = (n + 1, t + s.elapsed_time(e))
+        return out
+
+
+recorder = LaunchRecorder()
+_NO_LAUNCH = {"hoig_version", "hoig_last_error", "hoig_check_device", "hoig_conv_packed_dims",
+              "hoig_rasterize_workspace_bytes", "hoig_set_umma_gather_only"}
+
+
+class _Proxy:
+    def __init__(self, L):
+        self._L = L
+
+    def __getattr__(self, name):
+        fn = getattr(self._L, name)
+        if name in _NO_LAUNCH:
+            return fn
+
+        def launch(*args):
+            rec = recorder
+            if rec.timing:
+                import torch
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                r = fn(*args)
+                e.record()
+                rec.records.append((name, s, e))
+            else:
+                r = fn(*args)
+            rec.launches += 1
+            return r
+
+        setattr(self, name, launch)
+        return launch
+
+
+_proxy = None
+
+
+def lib():
     """Library handle for compute calls; verifies once that the device is sm_100."""
-    global _device_checked
-    L = load()
+    global _device_checked, _proxy
+    if _proxy is None:
+        _proxy = _Proxy(load())
     if not _device_checked:
-        check(L.hoig_check_device(), "check_device")
+        check(load().hoig_check_device(), "check_device")
         _device_checked = True
-    return L
+    return _proxy

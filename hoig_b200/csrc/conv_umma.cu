@@ -495,9 +495,9 @@ int make_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t *dim
     return HOIG_OK;
 }
 
-int g_force_gather = -1;
-
 }  // namespace
+
+int g_force_gather = -1;
 
 int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
 {
@@ -569,3 +569,7 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
 }
 
 }  // namespace hoig
+
+// Diagnostic switch: route every bf16 conv through the cp.async gather A-operand path
+// (1) or let eligible convs use TMA boxes (0).
+extern "C" void hoig_set_umma_gather_only(int on) { hoig::g_force_gather = on ? 1 : 0; }

@@ -1,0 +1,74 @@
+"""Stage R host side: batched replacements for the reference's per-sample renderer calls.
+
+Boundary B3 of SURVEY.md section 8b (paths relative to /root/reference/HOIG_HOv3):
+  * ``nr.rasterize_face_index_map_and_weight_map`` (thirdparty/neural_renderer/neural_renderer/rasterize.py:543-571)
+  * ``MANORenderer.render_fim_wim``                (utils/nmr.py:496-513)
+  * ``MANORenderer.encode_fim / encode_sem``       (utils/nmr.py:567-595)
+  * ``MANORenderer.cal_bc_transform``              (utils/nmr.py:874-968; T only, O is discarded by the caller)
+  * ``util.morph(mode='erode')``                   (utils/util.py:142-153)
+The reference loops over the batch in Python (models/trainer.py:63-97); here every call is one
+launch over the whole batch.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import ops
+
+EYE_Z = -(1.0 / math.tan(math.radians(30.0)) + 1.0)  # utils/nmr.py:357
+N_HAND_FACES = 1538                                  # models/trainer.py:72
+
+
+def rasterize_face_index_map_and_weight_map(faces, image_size=256, anti_aliasing=False, near=0.1, far=100.0, eps=1e-4):
+    """Same result as the reference function: ``(fim (B,is,is) int32, wim (B,is,is,3) f32)``, already flipped."""
+    if anti_aliasing:
+        raise NotImplementedError("HOGAN calls the face-index rasterizer with anti_aliasing=False (utils/nmr.py:512)")
+    return ops.rasterize(faces.contiguous().float(), image_size, near, far, flip_y=True)
+
+
+def render_fim_wim_batched(cam: torch.Tensor, vertices: torch.Tensor, faces_idx: torch.Tensor, image_size: int = 256):
+    """cam (B,15), vertices (B,V,3), faces_idx (F,3) int32 -> (faces (B,F,3,3), fim, wim)."""
+    faces = ops.project_faces(vertices.contiguous().float(), cam.contiguous().float(), faces_idx.contiguous().int(), EYE_Z)
+    fim, wim = ops.rasterize(faces, image_size)
+    return faces, fim, wim
+
+
+def condition_inputs(src_img, faces_src, fim_src, fim_ref, wim_ref, map_fn, sem_full, render_img_src=None,
+                     render_img_ref=None, n_hand_faces: int = N_HAND_FACES):
+    """Batched ``HandRecoveryFlow.forward`` tail (models/trainer.py:66-145) given the rasterizer outputs.
+
+    ``render_img_*`` are the UV-texture re-renderings (stage R8, a "next" row); when omitted the source image
+    stands in so the tensor shapes match.  Returns the dict of generator inputs plus the masks.
+    """
+    out = {}
+    side = {}
+    for tag, fim in (("src", fim_src), ("ref", fim_ref)):
+        cond, seg, not_hand = ops.condition_maps(fim, map_fn, sem_full, n_hand_faces)
+        m_hand = ops.erode(not_hand, 3)                                   # trainer.py:72
+        m_bg = ops.erode(cond[:, -1:].contiguous(), 3)                    # trainer.py:109-110
+        hm = (cond[:, :1] < 1.5).float()                                  # trainer.py:112-124
+        om = (cond[:, :1] > 1.5).float()
+        cond_hand = torch.cat([hm * cond[:, :2], cond[:, 2:] + 1 - hm], 1)
+        cond_obj = torch.cat([om * cond[:, :2], cond[:, 2:] + 1 - om], 1)
+        side[tag] = dict(cond=cond, seg=seg, m_hand=m_hand, m_bg=m_bg, cond_hand=cond_hand, cond_obj=cond_obj)
+    T = ops.bc_transform(faces_src, fim_ref, wim_ref)                     # nmr.py:874-925 (+ y flip of trainer.py:67-68)
+    mh = side["ref"]["m_hand"][:, 0][:, :, :, None]
+    T_hand = torch.where(mh == 1, torch.full_like(T, -2.0), T)            # trainer.py:81
+    r_src = src_img if render_img_src is None else render_img_src
+    r_ref = src_img if render_img_ref is None else render_img_ref
+    s, r = side["src"], side["ref"]
+    bg_mask = ops.erode(s["cond"][:, -1:].contiguous(), 15)               # trainer.py:135
+    out["bg_inputs"] = torch.cat([src_img * bg_mask, bg_mask], 1)
+    out["src_obj_inputs"] = r_src * (s["m_hand"] - s["m_bg"])             # trainer.py:127 (rgb part)
+    out["src_obj_conds"] = torch.cat([s["cond_obj"], s["seg"][:, 6:]], 1)
+    out["src_hand_inputs"] = src_img * (1 - s["m_hand"])                  # trainer.py:128
+    out["src_hand_conds"] = s["cond_hand"]
+    out["tsf_obj_inputs"] = r_ref * (r["m_hand"] - r["m_bg"])             # trainer.py:131
+    out["tsf_obj_conds"] = torch.cat([r["cond_obj"], r["seg"][:, 6:]], 1)
+    out["tsf_hand_inputs"] = r_ref * (1 - r["m_hand"])                    # trainer.py:132
+    out["tsf_hand_conds"] = r["cond_hand"]
+    out["T"] = T_hand
+    masks = dict(src_mask_bg=s["m_bg"], ref_mask_bg=r["m_bg"], src_mask_hand=s["m_hand"], ref_mask_hand=r["m_hand"])
+    return out, masks

@@ -130,6 +130,10 @@ int hoig_conv_packed_dims(int Cout, int KH, int KW, int Cin, int *rows, int *col
  * dtype BF16: tcgen05.mma (kind::f16, fp32 accumulators in TMEM), weights by TMA.
  * dtype F32 : SIMT fp32 FFMA. */
 int hoig_conv2d(const hoigConvDesc *desc, hoigStream_t stream);
+/* Test hooks (not used by the product schedule): the SIMT kernel for any dtype, and a switch that
+ * forces the bf16 kernel's A operand through the cp.async gather path instead of TMA boxes. */
+int hoig_conv2d_simt(const hoigConvDesc *desc, hoigStream_t stream);
+void hoig_set_umma_gather_only(int on);
 
 /* NCHW f32 (B,C,H,W) -> NHWC dtype with `Cpad` channels (extra channels zero). */
 int hoig_nchw_to_nhwc(const float *src, int B, int C, int H, int W, void *dst, int64_t ldd, int Cpad,

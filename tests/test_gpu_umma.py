@@ -1,0 +1,85 @@
+"""tcgen05 implicit-GEMM convolution (bf16) against the op contract and the SIMT kernel.
+
+Kept in its own file so a protocol bug in the tensor-core kernel (which traps
+instead of hanging) cannot take the other GPU tests' CUDA context down with it.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from hoig_b200 import ops
+from hoig_b200.packing import pack_conv_weight
+
+from . import emu_ops
+from .test_gpu_ops import CONV_CASES, _rand, _report, _run_conv
+
+pytestmark = pytest.mark.gpu
+
+
+def _dump_pattern(tag, out, ref):
+    """On mismatch print which rows / columns / k-ranges are wrong (descriptor debugging aid)."""
+    err = (out.float().cpu() - ref.float().cpu()).abs()
+    N, H, W, C = err.shape
+    e = err.reshape(-1, C)
+    bad = e > (2e-2 + 2e-2 * ref.float().cpu().reshape(-1, C).abs())
+    rows = bad.any(1).nonzero().flatten()
+    cols = bad.any(0).nonzero().flatten()
+    print(f"[{tag}] bad rows {rows.numel()}/{e.shape[0]} first {rows[:16].tolist()} | bad cols {cols.numel()}/{C} first {cols[:16].tolist()}")
+    print(f"[{tag}] out[0,0,0,:8]={out.float().cpu()[0,0,0,:8].tolist()}")
+    print(f"[{tag}] ref[0,0,0,:8]={ref.float().cpu()[0,0,0,:8].tolist()}")
+
+
+def test_umma_plain_gemm_identity_weight():
+    """1x1 conv with an identity weight: output must reproduce the input exactly. Isolates the
+    smem descriptors / swizzle / TMEM addressing from numerics."""
+    g = torch.Generator().manual_seed(0)
+    x = _rand(g, 1, 16, 16, 64).to(torch.bfloat16)   # 256 pixels = 2 M tiles, K = 64 (one k-block)
+    w = torch.eye(64).view(64, 64, 1, 1)
+    wp = pack_conv_weight(w, torch.bfloat16)
+    out = torch.zeros(1, 16, 16, 64, dtype=torch.bfloat16, device="cuda")
+    ops.conv2d(x.cuda(), wp.cuda(), out, kh=1, kw=1, stride=1, pad=0)
+    torch.cuda.synchronize()
+    if not torch.equal(out.cpu(), x):
+        _dump_pattern("identity", out, x)
+    assert torch.equal(out.cpu(), x)
+
+
+@pytest.mark.parametrize("gather_only", [False, True], ids=["tma_a", "gather"])
+def test_umma_3x3_both_operand_paths(gather_only, monkeypatch):
+    """The same stride-1 conv through the TMA-box A path and the cp.async gather A path."""
+    import hoig_b200._lib as L
+    case = ("3x3_s1_c128", 2, 32, 128, 256, 3, 1, "conv", dict(bias=True, stats=True))
+    L.lib().hoig_set_umma_gather_only(int(gather_only))
+    try:
+        out, ref, st, st_ref = _run_conv(case, torch.bfloat16)
+    finally:
+        L.lib().hoig_set_umma_gather_only(0)
+    ok, rel = _report(f"umma 3x3 gather_only={gather_only}", out, ref, 2e-2, 2e-2)
+    if not ok:
+        _dump_pattern("3x3", out, ref)
+    assert ok and rel < 1e-2
+    assert torch.allclose(st.cpu(), st_ref, rtol=2e-3, atol=0.5)
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_bf16_umma(case):
+    out, ref, st, st_ref = _run_conv(case, torch.bfloat16)
+    Cout = case[4]
+    ok, rel = _report("umma " + case[0], out[..., :Cout], ref[..., :Cout], 2e-2, 2e-2)
+    if not ok:
+        _dump_pattern(case[0], out[..., :Cout], ref[..., :Cout])
+    assert ok and rel < 1e-2
+    if st is not None:
+        assert torch.allclose(st.cpu(), st_ref, rtol=2e-3, atol=0.5)
+
+
+def test_umma_matches_simt_bf16_bitwise_mostly():
+    """Same bf16 inputs, fp32 accumulation in both kernels: results agree to bf16 rounding."""
+    case = ("3x3_s1_k4608", 1, 32, 512, 512, 3, 1, "conv", dict(stats=True))
+    a, _, _, _ = _run_conv(case, torch.bfloat16)
+    b, _, _, _ = _run_conv(case, torch.bfloat16, simt=True)
+    diff = (a.float() - b.float()).abs()
+    print("umma vs simt: maxabs", diff.max().item(), "fraction differing", (diff > 0).float().mean().item())
+    assert diff.max().item() <= 3e-2
