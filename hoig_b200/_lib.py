@@ -109,17 +109,26 @@ class LaunchRecorder:
     def __init__(self):
         self.launches = 0
         self.timing = False
-        self.records = []   # (entry point, start event, end event)
+        self.records = []   # (entry point, start event, end event, tag)
+        self.tag = None     # optional label set by the caller for the next launch
 
     def reset(self, timing: bool = False):
-        self.launches, self.timing, self.records = 0, timing, []
+        self.launches, self.timing, self.records, self.tag = 0, timing, [], None
 
     def summary(self):
         """{entry point: (launch count, total ms)} -- call after torch.cuda.synchronize()."""
         out = {}
-        for name, s, e in self.records:
+        for name, s, e, _ in self.records:
             n, t = out.get(name, (0, 0.0))
             out[name] = (n + 1, t + s.elapsed_time(e))
+        return out
+
+    def by_tag(self):
+        """{(entry point, tag): (launch count, total ms)}."""
+        out = {}
+        for name, s, e, tag in self.records:
+            n, t = out.get((name, tag), (0, 0.0))
+            out[(name, tag)] = (n + 1, t + s.elapsed_time(e))
         return out
 
 
@@ -145,7 +154,8 @@ class _Proxy:
                 s.record()
                 r = fn(*args)
                 e.record()
-                rec.records.append((name, s, e))
+                rec.records.append((name, s, e, rec.tag))
+                rec.tag = None
             else:
                 r = fn(*args)
             rec.launches += 1

@@ -175,6 +175,9 @@ def conv2d(x0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, *, kh: int
         raise ValueError("conv2d: stats must be float64 [N, Cout, 2]")
     d.flow = _f32c(flow, "flow") if flow is not None else None
     L = _lib.lib()
+    if _lib.recorder.timing:
+        _lib.recorder.tag = (f"{('conv', 'convT', 'attn')[mode]} k{kh} s{stride} Cin{d.C0 + d.C1} Cout{d.Cout} "
+                             f"{H}x{W}->{OH}x{OW} N{N}")
     fn = L.hoig_conv2d_simt if simt else L.hoig_conv2d
     _lib.check(fn(ctypes.byref(d), _stream()), "conv2d")
     return out

@@ -1,0 +1,40 @@
+"""Per-shape timing of every conv launch in one generator forward (CUDA events on the launching stream)."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import CFG, GFLOP_PER_IMAGE  # noqa: E402
+from hoig_b200 import _lib, synth  # noqa: E402
+from hoig_b200.generator import create  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+dtype = torch.bfloat16 if (len(sys.argv) < 3 or sys.argv[2] == "bf16") else torch.float32
+g = create("generator_spade_attn", dtype=dtype, **CFG).cuda()
+inp = {k: v.cuda() for k, v in synth.generator_inputs(B, seed=1, size=256).items()}
+for _ in range(2):
+    g(**inp)
+torch.cuda.synchronize()
+_lib.recorder.reset(timing=True)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); g(**inp); e1.record()
+torch.cuda.synchronize()
+total = e0.elapsed_time(e1)
+rows = sorted(_lib.recorder.by_tag().items(), key=lambda kv: -kv[1][1])
+print(f"forward B={B} {dtype}: {total:.2f} ms  ({B / total * 1e3:.1f} img/s), {_lib.recorder.launches} launches")
+acc = 0.0
+for (name, tag), (n, ms) in rows[:60]:
+    acc += ms
+    extra = ""
+    if tag:
+        import re
+        m = re.match(r"(\w+) k(\d+) s(\d+) Cin(\d+) Cout(\d+) (\d+)x(\d+)->(\d+)x(\d+) N(\d+)", tag)
+        mode, k, s, cin, cout, h, w, oh, ow, nn = m.group(1), *map(int, m.groups()[1:])
+        px = (h * w) if mode == "convT" else (oh * ow)
+        fl = 2.0 * nn * px * cout * cin * k * k
+        extra = f" {fl * n / ms / 1e9:8.1f} TFLOP/s(padded)"
+    print(f"{ms:9.3f} ms {100 * ms / total:5.1f}% n={n:3d} {name.replace('hoig_', ''):16s} {tag or ''}{extra}")
+print(f"listed {acc:.1f} ms of {total:.1f}")
