@@ -35,6 +35,7 @@ class ConvDesc(Structure):
         ("dst", c_void_p), ("ldd", c_int64),
         ("stats", c_void_p),
         ("flow", c_void_p),
+        ("act_table", c_void_p),
     ]
 
 
@@ -54,7 +55,7 @@ _SIGNATURES = {
     "hoig_erode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "hoig_block_extract_f32": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
     "hoig_local_attn_reshape_f32": (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
-    "hoig_conv_packed_dims": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
+    "hoig_conv_packed_dims": (c_int, [c_int] * 7 + [POINTER(c_int), POINTER(c_int)]),
     "hoig_conv2d": (c_int, [POINTER(ConvDesc), c_void_p]),
     "hoig_conv2d_simt": (c_int, [POINTER(ConvDesc), c_void_p]),
     "hoig_set_umma_gather_only": (None, [c_int]),

@@ -1,43 +1,62 @@
 // conv_common.cuh -- implicit-GEMM problem description shared by the SIMT fp32
 // kernel (conv_simt.cu) and the tcgen05 kernel (conv_umma.cu).
 //
-// GEMM view:  D[m][n] = sum_k A[m][k] * Wp[n][k]
-//   m = output pixel (image-major: m = n_img*OH*OW + oy*OW + ox; an M tile never
-//       straddles two images so per-plane statistics reduce inside a tile)
+// GEMM view of one launch:  D[m][n] = sum_k A[m][k] * Wp[n][k]
+//   m = pixel of the launch grid (image-major; an M tile never straddles two images so
+//       per-plane statistics reduce inside a tile)
 //   n = output channel
-//   k = tap*Cin + c,  tap = r*KW + s,  Cin = C0 + C1 (c < C0 reads src0, else src1)
-// A is never materialised: 8-channel chunks (k multiple of 8) are gathered on
-// the fly by mode:
-//   HOIG_CONV            iy = oy*stride - pad + r                       (nn.Conv2d)
-//   HOIG_CONV_TRANSPOSED iy = (oy + pad - r)/stride when divisible      (nn.ConvTranspose2d)
-//   HOIG_CONV_LOCAL_ATTN 5x5 taps of BlockExtractor(tgt,0) | BlockExtractor(src,flow)
-//                        (extract_attn.py:24-26 + block_extractor_kernel.cu:52-84)
+//   k = t*Cin + c,  t = tap index into the launch's tap table,  Cin = C0 + C1
+// A is never materialised.  A tap is an input offset (dy, dx) plus the id of the input view
+// ("phase") it reads:   input pixel = (gy*stride + dy, gx*stride + dx) of view `tap_map[t]`.
+// That one table covers
+//   nn.Conv2d              taps (r - pad, s - pad); stride-2 convs read the four parity
+//                          sub-images of the input as four strided views with offsets in {-1,0},
+//                          which makes them stride-1 (TMA-box friendly) problems;
+//   nn.ConvTranspose2d     four launches, one per output parity (a,b): a stride-1 conv over the
+//                          INPUT grid with 1/2/2/4 taps whose result lands at (2*gy+a, 2*gx+b)
+//                          -- no zero-insertion, 4x fewer MACs than the gather formulation;
+//   local attention        5x5 taps of BlockExtractor(tgt,0) | BlockExtractor(src,flow)
+//                          (extract_attn.py:24-26 + block_extractor_kernel.cu:52-84).
 #pragma once
 #include "common.cuh"
 
 namespace hoig {
 
-struct ConvParams {
-    int mode;
-    int N, H, W, C0, C1, Cin;
-    int OH, OW, Cout;
-    int KH, KW, stride, pad;
-    int K;       // KH*KW*Cin (logical)
-    int Kpad;    // padded to 64
-    int Npad;    // Cout padded to 16
-    const void *src0; int64_t ld0;
-    const void *src1; int64_t ld1;
-    const void *weight;
-    const float *bias;
-    int act;
-    const void *residual; int64_t ldr;
-    void *dst; int64_t ldd;
-    double *stats;
-    const float *flow;
-    int tiles_per_image;  // ceil(OH*OW / BM)
+constexpr int kMaxTaps = 64;
+constexpr int kMaxViews = 4;
+
+struct InputView {          // strided NHWC view of a source tensor
+    const void *base;
+    int H, W;               // extent of the view
+    int64_t sx, sy, sn;     // element strides between view pixels / rows / images
 };
 
-// Bilinear tap set of BlockExtractor for one (pixel, 5x5 tap): indices into the
+struct ConvParams {
+    int mode;               // HOIG_CONV (also used for transposed phases) or HOIG_CONV_LOCAL_ATTN
+    int N, C0, C1, Cin;
+    int GH, GW;             // launch grid (pixels enumerated by m)
+    int Cout;
+    int ntaps, stride;      // stride of the input walk (1 after phase decomposition)
+    int8_t tap_dy[kMaxTaps], tap_dx[kMaxTaps], tap_map[kMaxTaps];
+    InputView view[kMaxViews];   // views of src0 (channels [0,C0))
+    InputView view1;             // single view of src1 (channels [C0,Cin)), only with nviews == 1
+    int nviews;
+    int K, Kpad, Npad;
+    const void *weight;     // [Npad][ldw], this launch's columns start at `weight`
+    int64_t ldw;
+    const float *bias;
+    int act;
+    const int *act_table;   // optional per-output-channel activation codes
+    const void *residual; int64_t ldr;
+    void *dst; int64_t ldd;
+    int OHf, OWf, os, ooy, oox;   // output pixel = (gy*os + ooy, gx*os + oox) in an OHf x OWf image
+    double *stats;
+    const float *flow;
+    int KH;                 // local attention: kernel size (5)
+    int tiles_per_image;
+};
+
+// Bilinear tap set of BlockExtractor for one (pixel, k x k tap): indices into the
 // (H,W) source plane and the four products xP*yP, in the kernel's order LT,RT,LB,RB
 // (block_extractor_kernel.cu:57-82, same float op order).
 struct BETap {
@@ -63,9 +82,15 @@ __device__ __forceinline__ BETap be_tap(float flow_x, float flow_y, int yf, int 
     return t;
 }
 
-// Gather 8 consecutive k (one chunk) of A row (n_img, oy, ox) as floats.
+// element offset of pixel (n, y, x) in a view
+__device__ __forceinline__ int64_t view_off(const InputView &v, int n, int y, int x)
+{
+    return (int64_t)n * v.sn + (int64_t)y * v.sy + (int64_t)x * v.sx;
+}
+
+// Gather 8 consecutive k (one chunk) of the A row of grid pixel (n_img, gy, gx) as floats.
 template <typename T>
-__device__ __forceinline__ void gather_chunk(const ConvParams &p, int n_img, int oy, int ox, int kchunk, float v[8])
+__device__ __forceinline__ void gather_chunk(const ConvParams &p, int n_img, int gy, int gx, int kchunk, float v[8])
 {
     const int k0 = kchunk * 8;
 #pragma unroll
@@ -73,34 +98,29 @@ __device__ __forceinline__ void gather_chunk(const ConvParams &p, int n_img, int
     if (k0 >= p.K) return;
     const int tap = k0 / p.Cin;
     int c = k0 - tap * p.Cin;
-    const int r = tap / p.KW, s = tap - r * p.KW;
-    const T *base;
-    int64_t ld;
     const bool second = c >= p.C0;
-    if (second) { base = static_cast<const T *>(p.src1); ld = p.ld1; c -= p.C0; }
-    else        { base = static_cast<const T *>(p.src0); ld = p.ld0; }
-    if (p.mode == HOIG_CONV) {
-        const int iy = oy * p.stride - p.pad + r, ix = ox * p.stride - p.pad + s;
-        if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) return;
-        load8(base + ((int64_t)(n_img * p.H + iy) * p.W + ix) * ld + c, v);
-    } else if (p.mode == HOIG_CONV_TRANSPOSED) {
-        const int ty = oy + p.pad - r, tx = ox + p.pad - s;
-        if (ty < 0 || tx < 0 || (ty % p.stride) || (tx % p.stride)) return;
-        const int iy = ty / p.stride, ix = tx / p.stride;
-        if (iy >= p.H || ix >= p.W) return;
-        load8(base + ((int64_t)(n_img * p.H + iy) * p.W + ix) * ld + c, v);
-    } else {  // HOIG_CONV_LOCAL_ATTN: src0 = target (zero flow), src1 = source (flow)
-        const int64_t plane = (int64_t)n_img * p.H * p.W;
+    if (p.mode != HOIG_CONV_LOCAL_ATTN) {
+        const InputView &vw = second ? p.view1 : p.view[p.tap_map[tap]];
+        if (second) c -= p.C0;
+        const int iy = gy * p.stride + p.tap_dy[tap], ix = gx * p.stride + p.tap_dx[tap];
+        if (iy < 0 || iy >= vw.H || ix < 0 || ix >= vw.W) return;
+        load8(static_cast<const T *>(vw.base) + view_off(vw, n_img, iy, ix) + c, v);
+    } else {  // view[0] = target (zero flow), view1 = source (flow)
+        const int r = tap / p.KH, s = tap - r * p.KH;
         if (!second) {
-            const int iy = max(min(oy + r - p.KH / 2, p.H - 1), 0), ix = max(min(ox + s - p.KW / 2, p.W - 1), 0);
-            load8(base + (plane + (int64_t)iy * p.W + ix) * ld + c, v);
+            const InputView &vw = p.view[0];
+            const int iy = max(min(gy + r - p.KH / 2, vw.H - 1), 0), ix = max(min(gx + s - p.KH / 2, vw.W - 1), 0);
+            load8(static_cast<const T *>(vw.base) + view_off(vw, n_img, iy, ix) + c, v);
         } else {
-            const float *fl = p.flow + (plane + (int64_t)oy * p.W + ox) * 2;
-            const BETap t = be_tap(fl[0], fl[1], oy, ox, r, s, p.KH, p.H, p.W);
+            const InputView &vw = p.view1;
+            c -= p.C0;
+            const float *fl = p.flow + (((int64_t)n_img * p.GH + gy) * p.GW + gx) * 2;
+            const BETap t = be_tap(fl[0], fl[1], gy, gx, r, s, p.KH, vw.H, vw.W);
+            const T *base = static_cast<const T *>(vw.base) + (int64_t)n_img * vw.sn + c;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float u[8];
-                load8(base + (plane + t.idx[q]) * ld + c, u);
+                load8(base + (int64_t)t.idx[q] * vw.sx, u);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = __fmaf_rn(t.w[q], u[j], v[j]);
             }
@@ -108,6 +128,24 @@ __device__ __forceinline__ void gather_chunk(const ConvParams &p, int n_img, int
     }
 }
 
-int fill_conv_params(const hoigConvDesc *d, int BM, ConvParams *p);  // validates; returns hoigStatus
+// output element offset of grid pixel (n_img, pix) for channel 0
+__device__ __forceinline__ int64_t out_pixel(const ConvParams &p, int n_img, int pix)
+{
+    if (p.os == 1) return (int64_t)n_img * p.GH * p.GW + pix;
+    const int gy = pix / p.GW, gx = pix - gy * p.GW;
+    return ((int64_t)n_img * p.OHf + gy * p.os + p.ooy) * p.OWf + gx * p.os + p.oox;
+}
+
+__device__ __forceinline__ int act_of(const ConvParams &p, int n) { return p.act_table ? p.act_table[n] : p.act; }
+
+// Host side: expands a hoigConvDesc into 1 launch (conv / local attention) or 4 (transposed).
+struct ConvPlan {
+    int n;
+    ConvParams launch[4];
+};
+int plan_conv(const hoigConvDesc *d, int BM, ConvPlan *plan);  // validates; returns hoigStatus
+// columns of the packed weight matrix occupied by launch `i` of the plan for this geometry
+void packed_layout(int mode, int Cout, int KH, int KW, int Cin, int stride, int pad, int *rows, int *cols, int col_off[4],
+                   int col_len[4]);
 
 }  // namespace hoig

@@ -3,20 +3,24 @@
 // D[128 pixels][BN channels] (fp32, TMEM) += A[128][64] (bf16, smem) * W[BN][64]^T (bf16, smem)
 // per k-block, tcgen05.mma.cta_group::1.kind::f16, UMMA 128 x BN x 16, BN <= 256.
 //
-// Persistent, warp-specialised CTA (one per SM, 320 threads):
-//   warps 0-3  epilogue: tcgen05.ld TMEM -> regs, +bias (+residual), activation, bf16 store,
-//              per-plane sum / sum-of-squares (instance-norm statistics) by warp-transpose
-//              reduction; overlaps the next tile's main loop (two TMEM accumulator stages)
-//   warps 4-7  A producers in "gather" mode: one output pixel (A row) per thread, 16-byte
-//              cp.async chunks written straight into the 128B-swizzled K-major layout the
-//              UMMA descriptor expects (zero-fill = padding); in local-attention mode the
-//              BlockExtractor bilinear taps are blended in registers and stored to smem.
-//   warp  8    TMA producer: weights (2D map, always) and, in "TMA-A" mode (stride-1 convs
-//              with Cin % 64 == 0), the activation tile itself as one 4D box per (tap, 64
-//              channels): out-of-bounds box rows are zero-filled by TMA == conv padding.
-//   warp  9    TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit -> mbarriers
+// Persistent, warp-specialised CTA (one per SM, 448 threads):
+//   warps 0-7   epilogue (warp w: TMEM lane quadrant w % 4, 16-column chunks of parity w / 4):
+//               tcgen05.ld (next chunk in flight while the current one is finalised) -> +bias (smem)
+//               (+residual) -> activation -> bf16 -> 32-byte row-segment stores; per-plane
+//               sum / sum-of-squares (instance-norm statistics) by warp-transpose reduction.
+//               Overlaps the next tile's main loop (two TMEM accumulator stages).
+//   warps 8-11  A producers in "gather" mode: one output pixel (A row) per thread, 16-byte
+//               cp.async chunks written straight into the 128B-swizzled K-major layout the
+//               UMMA descriptor expects (zero-fill = padding); in local-attention mode the
+//               BlockExtractor bilinear taps are blended in registers and stored to smem.
+//   warp  12    TMA producer: weights (2D map, always) and, in "TMA-A" mode, the activation tile
+//               itself as one 4D box per (tap, 64 channels) of the tap's input view; out-of-bounds
+//               box rows are zero-filled by TMA == conv padding.  Stride-2 convs and the four
+//               transposed-conv phases are stride-1 problems over strided views (conv_common.cuh),
+//               so they take this path too.
+//   warp  13    TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit -> mbarriers
 //
-// smem ring: STAGES x (A 16 KB + B BN*128 B), 1024-byte aligned for SWIZZLE_128B.
+// smem: ring of STAGES x (A 16 KB + B BN*128 B), 1024-byte aligned for SWIZZLE_128B.
 #include <cuda.h>
 
 #include "conv_common.cuh"
@@ -27,12 +31,14 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int EPI_WARPS = 4, PROD_WARPS = 4;
-constexpr int TMA_WARP = 8, MMA_WARP = 9;
-constexpr int THREADS = 320;
+constexpr int EPI_WARPS = 8, PROD_WARPS = 4;    // epilogue warp w: TMEM lane quadrant w % 4, 16-column chunks of parity w / 4
+constexpr int TMA_WARP = 12, MMA_WARP = 13;
+constexpr int THREADS = 448;
 constexpr int MAX_STAGES = 8;
 constexpr int LOOKAHEAD = 3;           // cp.async groups in flight per producer thread
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int STG_BYTES = 0;
+constexpr int SMEM_TOTAL = 222 * 1024;   // dynamic; + ~3.5 KB static (barriers, stats, bias) <= 227 KB per CTA
+constexpr int RING_BUDGET = SMEM_TOTAL - 1024 - STG_BYTES;
 
 struct UmmaParams {
     ConvParams c;
@@ -42,7 +48,7 @@ struct UmmaParams {
     int k_blocks;    // Kpad / 64
     int stages;
     int tma_a;       // 1: activations by TMA boxes, 0: cp.async / register gather
-    int chunks_per_tap;  // Cin / 8
+    int cpt_shift;   // log2(Cin / 8) when Cin < 64 (chunk -> tap by shift), -1: generic division
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -98,6 +104,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1):
 // start address >> 4 | LBO (unused for swizzled K-major, canonical 1) | SBO = 1024 B (8 rows x 128 B)
@@ -123,7 +130,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16])
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r)
 {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -131,7 +138,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16])
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait::ld with the destination registers as read-write operands, so the compiler cannot hoist their uses
+__device__ __forceinline__ void tmem_ld_wait(uint32_t *r)
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 
 // 16 values per lane x 32 lanes -> column totals: after the call lane L holds the total of
 // column  8*b4 + 4*b3 + 2*b2 + b1  (bits of L), duplicated on lanes L and L^1.
@@ -167,21 +191,24 @@ __device__ __forceinline__ float transpose_reduce16(const float v[16], int lane)
 // ------------------------------------------------------------------------ kernel
 __global__ void __launch_bounds__(THREADS, 1)
 conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
-                 const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1)
+                 const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                 const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3)
 {
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_smem;
     __shared__ float s_stats[2][256];
+    __shared__ __align__(16) float s_bias[256 + 32];
 
     const ConvParams &p = P.c;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int BN = P.BN;
     const int stage_bytes = A_STAGE_BYTES + BN * BK * 2;
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t stg_base = smem_u32(smem);                  // epilogue staging first (1024-aligned)
+    const uint32_t smem_base = stg_base + STG_BYTES;           // then the operand ring
     const int total_tiles = P.m_tiles * P.n_tiles;
-    const int npix = p.OH * p.OW;
+    const int npix = p.GH * p.GW;
 
     if (threadIdx.x == 0) {
         const uint32_t full_count = P.tma_a ? 1u : (uint32_t)(PROD_WARPS * 32 + 1);
@@ -202,10 +229,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
     }
     if (warp == TMA_WARP && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-        if (P.tma_a) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a0) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a1) : "memory");
-        }
+        if (P.tma_a) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a0) : "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -218,6 +242,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
             const int row = threadIdx.x - EPI_WARPS * 32;  // 0..127 : A row == pixel of the tile
             const uint32_t row_off = (uint32_t)row * 128u;
             const uint32_t sw = (uint32_t)(row & 7);
+            const __nv_bfloat16 *src0 = static_cast<const __nv_bfloat16 *>(p.view[0].base);
             uint32_t it = 0;  // running k-block counter across tiles
             int pending = 0;  // k-blocks issued but not yet signalled
             uint32_t sig_it = 0;
@@ -226,80 +251,91 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                 const int n_img = mt / p.tiles_per_image;
                 const int pix = (mt % p.tiles_per_image) * BM + row;
                 const bool valid = pix < npix;
-                const int oy = valid ? pix / p.OW : 0, ox = valid ? pix % p.OW : 0;
+                const int gy = valid ? pix / p.GW : 0, gx = valid ? pix % p.GW : 0;
+                int tap64 = 0, c64 = 0;   // (tap, channel) of the k-block start when Cin % 64 == 0
                 for (int kb = 0; kb < P.k_blocks; ++kb, ++it) {
                     const int s = it % P.stages;
                     mbar_wait(smem_u32(&empty_bar[s]), ((it / P.stages) & 1) ^ 1);
                     const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes + row_off;
                     if (p.mode != HOIG_CONV_LOCAL_ATTN) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int k0 = kb * BK + j * 8;
-                            const void *src = p.src0;
+                        if (P.cpt_shift < 0 && (p.Cin & 63) == 0) {
+                            // all 8 chunks of this k-block share one tap: one bounds test, one base pointer
+                            const __nv_bfloat16 *src = src0;
                             uint32_t bytes = 0;
-                            if (valid && k0 < p.K) {
-                                const int tap = k0 / p.Cin;
-                                int c = k0 - tap * p.Cin;
-                                const int r = tap / p.KW, sx = tap - r * p.KW;
-                                int iy, ix;
-                                bool ok;
-                                if (p.mode == HOIG_CONV) {
-                                    iy = oy * p.stride - p.pad + r; ix = ox * p.stride - p.pad + sx;
-                                    ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-                                } else {
-                                    const int ty = oy + p.pad - r, tx = ox + p.pad - sx;
-                                    ok = ty >= 0 && tx >= 0 && (ty % p.stride) == 0 && (tx % p.stride) == 0;
-                                    iy = ty / p.stride; ix = tx / p.stride;
-                                    ok = ok && iy < p.H && ix < p.W;
-                                }
-                                if (ok) {
-                                    const int64_t pixoff = (int64_t)(n_img * p.H + iy) * p.W + ix;
-                                    if (c >= p.C0) src = static_cast<const __nv_bfloat16 *>(p.src1) + pixoff * p.ld1 + (c - p.C0);
-                                    else           src = static_cast<const __nv_bfloat16 *>(p.src0) + pixoff * p.ld0 + c;
+                            if (valid && tap64 < p.ntaps) {
+                                const bool second = c64 >= p.C0;
+                                const InputView &vw = second ? p.view1 : p.view[p.tap_map[tap64]];
+                                const int iy = gy * p.stride + p.tap_dy[tap64], ix = gx * p.stride + p.tap_dx[tap64];
+                                if (iy >= 0 && iy < vw.H && ix >= 0 && ix < vw.W) {
+                                    src = static_cast<const __nv_bfloat16 *>(vw.base) + view_off(vw, n_img, iy, ix) + (second ? c64 - p.C0 : c64);
                                     bytes = 16;
                                 }
                             }
-                            cp_async_16(a_dst + (((uint32_t)j ^ sw) << 4), src, bytes);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                cp_async_16(a_dst + (((uint32_t)j ^ sw) << 4), src + (bytes ? j * 8 : 0), bytes);
+                            c64 += BK;
+                            if (c64 >= p.Cin) { c64 = 0; ++tap64; }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int chunk = kb * 8 + j;
+                                const __nv_bfloat16 *src = src0;
+                                uint32_t bytes = 0;
+                                int tap, c;
+                                if (P.cpt_shift >= 0) { tap = chunk >> P.cpt_shift; c = (chunk - (tap << P.cpt_shift)) * 8; }
+                                else { tap = (chunk * 8) / p.Cin; c = chunk * 8 - tap * p.Cin; }
+                                if (valid && tap < p.ntaps) {
+                                    const bool second = c >= p.C0;
+                                    const InputView &vw = second ? p.view1 : p.view[p.tap_map[tap]];
+                                    const int iy = gy * p.stride + p.tap_dy[tap], ix = gx * p.stride + p.tap_dx[tap];
+                                    if (iy >= 0 && iy < vw.H && ix >= 0 && ix < vw.W) {
+                                        src = static_cast<const __nv_bfloat16 *>(vw.base) + view_off(vw, n_img, iy, ix) + (second ? c - p.C0 : c);
+                                        bytes = 16;
+                                    }
+                                }
+                                cp_async_16(a_dst + (((uint32_t)j ^ sw) << 4), src, bytes);
+                            }
                         }
                     } else {
-                        // local attention: chunks of [target | source] channels per 5x5 tap
+                        // local attention: chunks of [target | source] channels per k x k tap
                         // (extract_attn.py:24-26); target taps are plain copies (zero flow),
                         // source taps are the BlockExtractor bilinear blend, done in registers.
-                        const int64_t plane = (int64_t)n_img * p.H * p.W;
+                        const InputView &vt = p.view[0];
+                        const InputView &vs = p.view1;
                         int cached_tap = -1;
                         BETap t;
 #pragma unroll 2
                         for (int j = 0; j < 8; ++j) {
                             const int k0 = kb * BK + j * 8;
                             const uint32_t dst_j = a_dst + (((uint32_t)j ^ sw) << 4);
-                            if (!valid || k0 >= p.K) { cp_async_16(dst_j, p.src0, 0); continue; }
+                            if (!valid || k0 >= p.K) { cp_async_16(dst_j, src0, 0); continue; }
                             const int tap = k0 / p.Cin;
                             int c = k0 - tap * p.Cin;
-                            const int r = tap / p.KW, sx = tap - r * p.KW;
+                            const int r = tap / p.KH, sx = tap - r * p.KH;
                             if (c < p.C0) {
-                                const int iy = max(min(oy + r - p.KH / 2, p.H - 1), 0), ix = max(min(ox + sx - p.KW / 2, p.W - 1), 0);
-                                cp_async_16(dst_j, static_cast<const __nv_bfloat16 *>(p.src0) + (plane + (int64_t)iy * p.W + ix) * p.ld0 + c, 16);
+                                const int iy = max(min(gy + r - p.KH / 2, vt.H - 1), 0), ix = max(min(gx + sx - p.KH / 2, vt.W - 1), 0);
+                                cp_async_16(dst_j, static_cast<const __nv_bfloat16 *>(vt.base) + view_off(vt, n_img, iy, ix) + c, 16);
                             } else {
                                 c -= p.C0;
                                 if (tap != cached_tap) {
-                                    const float *fl = p.flow + (plane + (int64_t)oy * p.W + ox) * 2;
-                                    t = be_tap(fl[0], fl[1], oy, ox, r, sx, p.KH, p.H, p.W);
+                                    const float *fl = p.flow + (((int64_t)n_img * p.GH + gy) * p.GW + gx) * 2;
+                                    t = be_tap(fl[0], fl[1], gy, gx, r, sx, p.KH, vs.H, vs.W);
                                     cached_tap = tap;
                                 }
-                                const __nv_bfloat16 *sb = static_cast<const __nv_bfloat16 *>(p.src1) + plane * p.ld1 + c;
+                                const __nv_bfloat16 *sb = static_cast<const __nv_bfloat16 *>(vs.base) + (int64_t)n_img * vs.sn + c;
                                 float acc[8];
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) acc[e] = 0.f;
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
                                     float u[8];
-                                    load8(sb + (int64_t)t.idx[q] * p.ld1, u);
+                                    load8(sb + (int64_t)t.idx[q] * vs.sx, u);
 #pragma unroll
                                     for (int e = 0; e < 8; ++e) acc[e] = __fmaf_rn(t.w[q], u[e], acc[e]);
                                 }
-                                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst_j),
-                                             "r"(pack_bf16x2(acc[0], acc[1])), "r"(pack_bf16x2(acc[2], acc[3])),
-                                             "r"(pack_bf16x2(acc[4], acc[5])), "r"(pack_bf16x2(acc[6], acc[7])) : "memory");
+                                st_shared_v4(dst_j, pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                             pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
                             }
                         }
                     }
@@ -323,13 +359,15 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
     } else if (warp == TMA_WARP) {
         // ======================================================== TMA producer
         if (lane == 0) {
+            const CUtensorMap *maps[4] = {&map_a0, &map_a1, &map_a2, &map_a3};
             uint32_t it = 0;
             const uint32_t tx_bytes = (uint32_t)(BN * BK * 2) + (P.tma_a ? (uint32_t)A_STAGE_BYTES : 0u);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = tile / P.n_tiles, nt = tile % P.n_tiles;
                 const int n_img = mt / p.tiles_per_image;
                 const int pix0 = (mt % p.tiles_per_image) * BM;
-                const int oy0 = pix0 / p.OW, ox0 = pix0 % p.OW;
+                const int gy0 = pix0 / p.GW, gx0 = pix0 % p.GW;
+                int tap = 0, c = 0;
                 for (int kb = 0; kb < P.k_blocks; ++kb, ++it) {
                     const int s = it % P.stages;
                     mbar_wait(smem_u32(&empty_bar[s]), ((it / P.stages) & 1) ^ 1);
@@ -337,12 +375,10 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                     const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
                     mbar_arrive_expect_tx(bar, tx_bytes);
                     if (P.tma_a) {
-                        const int k0 = kb * BK;
-                        const int tap = k0 / p.Cin;
-                        const int c = k0 - tap * p.Cin;
-                        const int r = tap / p.KW, sx = tap - r * p.KW;
-                        if (c >= p.C0) tma_load_4d(a_dst, &map_a1, bar, c - p.C0, ox0 + sx - p.pad, oy0 + r - p.pad, n_img);
-                        else           tma_load_4d(a_dst, &map_a0, bar, c, ox0 + sx - p.pad, oy0 + r - p.pad, n_img);
+                        const int tt = tap < p.ntaps ? tap : p.ntaps - 1;   // K padding blocks: any finite data (weights are zero)
+                        tma_load_4d(a_dst, maps[p.tap_map[tt]], bar, c, gx0 + p.tap_dx[tt], gy0 + p.tap_dy[tt], n_img);
+                        c += BK;
+                        if (c >= p.Cin) { c = 0; ++tap; }
                     }
                     tma_load_2d(a_dst + A_STAGE_BYTES, &map_w, bar, kb * BK, nt * BN);
                 }
@@ -374,84 +410,119 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
         }
     } else {
         // ============================================================ epilogue
-        const int row = warp * 32 + lane;  // TMEM lane == tile row; warp w may touch lanes 32w..32w+31
+        // lane == tile row within the warp's TMEM lane quadrant; the two warps of a quadrant take
+        // alternate 16-column chunks.  Chunk i+1 is in flight (tcgen05.ld) while chunk i is finalised.
+        const int quad = warp & 3, half = warp >> 2;
         const __nv_bfloat16 *res = static_cast<const __nv_bfloat16 *>(p.residual);
         __nv_bfloat16 *dst = static_cast<__nv_bfloat16 *>(p.dst);
+        const bool vec_ok = ((p.ldd & 7) == 0) && (!res || (p.ldr & 7) == 0);
+        const int n_chunks = BN / 16;
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
             const int mt = tile / P.n_tiles, nt = tile % P.n_tiles;
             const int n_img = mt / p.tiles_per_image;
-            const int pix = (mt % p.tiles_per_image) * BM + row;
+            const int pix = (mt % p.tiles_per_image) * BM + quad * 32 + lane;
             const bool valid = pix < npix;
-            const int64_t m = (int64_t)n_img * npix + pix;
+            const int64_t m = valid ? out_pixel(p, n_img, pix) : 0;
+            __nv_bfloat16 *drow = dst + m * p.ldd + (int64_t)nt * BN;
+            const __nv_bfloat16 *rrow = res ? res + m * p.ldr + (int64_t)nt * BN : nullptr;
             const uint32_t acc = tcount & 1;
+            epi_bar();                       // previous tile fully drained: s_bias / s_stats reusable
+            for (int i = threadIdx.x; i < BN; i += EPI_WARPS * 32) {
+                const int n = nt * BN + i;
+                s_bias[i] = (p.bias && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
+            }
             mbar_wait(smem_u32(&tfull_bar[acc]), (tcount >> 1) & 1);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (uint32_t)BN;
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                const int n0 = nt * BN + c0;
-                uint32_t r[16];
-                tmem_ld16(t_row + (uint32_t)c0, r);
-                tmem_ld_wait();
-                if (n0 >= p.Cout) continue;   // warp-uniform
-                float v[16];
+            epi_bar();
+            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)BN;
+            uint32_t ra[16], rb[16];
+            auto finalize = [&](const uint32_t (&r)[16], int ch) {
+                const int c0 = ch * 16;
+                    const int n0 = nt * BN + c0;
+                    if (n0 >= p.Cout) return;     // warp-uniform: padded output channels
+                    float v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-                if (p.bias) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += (n0 + j < p.Cout) ? __ldg(p.bias + n0 + j) : 0.f;
-                }
-                const bool full = n0 + 16 <= p.Cout;
-                if (res && valid) {
-                    if (full) {
-                        float u[8];
-                        load8(res + m * p.ldr + n0, u);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] += u[j];
-                        load8(res + m * p.ldr + n0 + 8, u);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[8 + j] += u[j];
-                    } else {
-                        for (int j = 0; j < 16; ++j)
-                            if (n0 + j < p.Cout) v[j] += __bfloat162float(res[m * p.ldr + n0 + j]);
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 bv = *reinterpret_cast<const float4 *>(&s_bias[c0 + j]);
+                        v[j] = __uint_as_float(r[j]) + bv.x;         v[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
+                        v[j + 2] = __uint_as_float(r[j + 2]) + bv.z; v[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
                     }
-                }
+                    const bool full = n0 + 16 <= p.Cout;
+                    if (res && valid) {
+                        if (full && vec_ok) {
+                            float u[8];
+                            load8(rrow + c0, u);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = round_to<__nv_bfloat16>(apply_act(v[j], p.act));
-                if (valid) {
-                    if (full && ((p.ldd & 7) == 0)) {
-                        store8(dst + m * p.ldd + n0, v);
-                        store8(dst + m * p.ldd + n0 + 8, v + 8);
-                    } else {
-                        for (int j = 0; j < 16; ++j)
-                            if (n0 + j < p.Cout) dst[m * p.ldd + n0 + j] = __float2bfloat16_rn(v[j]);
-                    }
-                }
-                if (p.stats) {
-                    float q[16];
+                            for (int j = 0; j < 8; ++j) v[j] += u[j];
+                            load8(rrow + c0 + 8, u);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) { v[j] = valid ? v[j] : 0.f; q[j] = v[j] * v[j]; }
-                    const float cs = transpose_reduce16(v, lane);
-                    const float cq = transpose_reduce16(q, lane);
-                    if ((lane & 1) == 0) {
-                        const int col = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                        atomicAdd(&s_stats[0][col], cs);
-                        atomicAdd(&s_stats[1][col], cq);
+                            for (int j = 0; j < 8; ++j) v[8 + j] += u[j];
+                        } else {
+                            for (int j = 0; j < 16; ++j)
+                                if (n0 + j < p.Cout) v[j] += __bfloat162float(rrow[c0 + j]);
+                        }
                     }
+                    if (p.act_table) {
+                        for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act_table[min(n0 + j, p.Cout - 1)]);
+                    } else if (p.act == HOIG_ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                    } else if (p.act != HOIG_ACT_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+                    }
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                    if (valid) {
+                        if (full && vec_ok) {
+                            *reinterpret_cast<uint4 *>(drow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            *reinterpret_cast<uint4 *>(drow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        } else {
+                            for (int j = 0; j < 16; ++j)
+                                if (n0 + j < p.Cout) drow[c0 + j] = __float2bfloat16_rn(v[j]);
+                        }
+                    }
+                    if (p.stats) {
+                        float q[16];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {   // statistics of the values as stored (bf16-rounded)
+                            const float lo = valid ? __uint_as_float(pk[j] << 16) : 0.f, hi = valid ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
+                            v[2 * j] = lo; v[2 * j + 1] = hi;
+                            q[2 * j] = lo * lo; q[2 * j + 1] = hi * hi;
+                        }
+                        const float cs = transpose_reduce16(v, lane);
+                        const float cq = transpose_reduce16(q, lane);
+                        if ((lane & 1) == 0) {
+                            const int col = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                            atomicAdd(&s_stats[0][col], cs);
+                            atomicAdd(&s_stats[1][col], cq);
+                        }
+                    }
+            };
+            if (half < n_chunks) tmem_ld16(t_row + (uint32_t)(half * 16), ra);
+            for (int ch = half; ch < n_chunks; ch += 4) {
+                tmem_ld_wait(ra);
+                if (ch + 2 < n_chunks) tmem_ld16(t_row + (uint32_t)((ch + 2) * 16), rb);
+                finalize(ra, ch);
+                if (ch + 2 < n_chunks) {
+                    tmem_ld_wait(rb);
+                    if (ch + 4 < n_chunks) tmem_ld16(t_row + (uint32_t)((ch + 4) * 16), ra);
+                    finalize(rb, ch + 2);
                 }
             }
             // accumulator drained: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             mbar_arrive(smem_u32(&tempty_bar[acc]));
             if (p.stats) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                epi_bar();
                 for (int i = threadIdx.x; i < 2 * BN; i += EPI_WARPS * 32) {
                     const int which = i / BN, col = i % BN;
                     const int n = nt * BN + col;
                     if (n < p.Cout) atomicAdd(&p.stats[((int64_t)n_img * p.Cout + n) * 2 + which], (double)s_stats[which][col]);
                     s_stats[which][col] = 0.f;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
         }
     }
@@ -495,60 +566,52 @@ int make_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t *dim
     return HOIG_OK;
 }
 
-}  // namespace
-
-int g_force_gather = -1;
-
-int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
+int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather)
 {
     UmmaParams P;
-    int st = fill_conv_params(d, BM, &P.c);
-    if (st != HOIG_OK) return st;
+    P.c = cp;
     const ConvParams &p = P.c;
     HOIG_REQUIRE(p.Npad <= 4096, "conv2d: Cout too large");
     P.BN = p.Npad <= 256 ? p.Npad : 256;
     P.n_tiles = ceil_div(p.Npad, P.BN);
     P.m_tiles = p.N * p.tiles_per_image;
     P.k_blocks = p.Kpad / BK;
-    P.chunks_per_tap = p.Cin / 8;
     const int stage_bytes = A_STAGE_BYTES + P.BN * BK * 2;
-    P.stages = (SMEM_BUDGET - 1024) / stage_bytes;
+    P.stages = RING_BUDGET / stage_bytes;
     if (P.stages > MAX_STAGES) P.stages = MAX_STAGES;
     HOIG_REQUIRE(P.stages >= LOOKAHEAD + 1, "conv2d: not enough shared memory stages");
-
-    if (g_force_gather < 0) {
-        const char *e = getenv("HOIG_UMMA_GATHER_ONLY");
-        g_force_gather = (e && e[0] == '1') ? 1 : 0;
+    P.cpt_shift = -1;
+    if (p.Cin < 64) {
+        const int cpt = p.Cin / 8;
+        if ((cpt & (cpt - 1)) == 0) { P.cpt_shift = 0; while ((1 << P.cpt_shift) < cpt) ++P.cpt_shift; }
     }
-    const int64_t npix = (int64_t)p.OH * p.OW;
-    const bool rect = (p.OW % BM == 0) || (BM % p.OW == 0);
-    P.tma_a = (!g_force_gather && p.mode == HOIG_CONV && p.stride == 1 && p.C0 % 64 == 0 && p.C1 % 64 == 0 && rect &&
-               p.OH == p.H && p.OW == p.W && npix % BM == 0)
-                  ? 1 : 0;
 
-    CUtensorMap map_w, map_a0, map_a1;
+    const int64_t npix = (int64_t)p.GH * p.GW;
+    const bool rect = (p.GW % BM == 0) || (BM % p.GW == 0);
+    P.tma_a = (!force_gather && p.mode == HOIG_CONV && p.stride == 1 && p.C1 == 0 && p.C0 % 64 == 0 && rect && npix % BM == 0) ? 1 : 0;
+    if (P.tma_a)   // view strides must be 16-byte multiples for a tensor map
+        for (int v = 0; v < p.nviews; ++v)
+            if ((p.view[v].sx * 2) % 16 || ((uintptr_t)p.view[v].base % 16)) P.tma_a = 0;
+
+    CUtensorMap map_w, map_a[4];
+    int st;
     {
         const cuuint64_t dims[2] = {(cuuint64_t)p.Kpad, (cuuint64_t)p.Npad};
-        const cuuint64_t strides[1] = {(cuuint64_t)p.Kpad * 2};
+        const cuuint64_t strides[1] = {(cuuint64_t)p.ldw * 2};
         const cuuint32_t box[2] = {BK, (cuuint32_t)P.BN};
         st = make_map(&map_w, p.weight, 2, dims, strides, box, "weights");
         if (st != HOIG_OK) return st;
     }
-    map_a0 = map_w; map_a1 = map_w;
+    for (int v = 0; v < 4; ++v) map_a[v] = map_w;
     if (P.tma_a) {
-        const int bw = p.OW < BM ? p.OW : BM;
+        const int bw = p.GW < BM ? p.GW : BM;
         const int bh = BM / bw;
         const cuuint32_t box[4] = {BK, (cuuint32_t)bw, (cuuint32_t)bh, 1};
-        {
-            const cuuint64_t dims[4] = {(cuuint64_t)p.C0, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
-            const cuuint64_t strides[3] = {(cuuint64_t)p.ld0 * 2, (cuuint64_t)p.W * p.ld0 * 2, (cuuint64_t)p.H * p.W * p.ld0 * 2};
-            st = make_map(&map_a0, p.src0, 4, dims, strides, box, "activations0");
-            if (st != HOIG_OK) return st;
-        }
-        if (p.C1 > 0) {
-            const cuuint64_t dims[4] = {(cuuint64_t)p.C1, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
-            const cuuint64_t strides[3] = {(cuuint64_t)p.ld1 * 2, (cuuint64_t)p.W * p.ld1 * 2, (cuuint64_t)p.H * p.W * p.ld1 * 2};
-            st = make_map(&map_a1, p.src1, 4, dims, strides, box, "activations1");
+        for (int v = 0; v < p.nviews; ++v) {
+            const InputView &vw = p.view[v];
+            const cuuint64_t dims[4] = {(cuuint64_t)p.C0, (cuuint64_t)vw.W, (cuuint64_t)vw.H, (cuuint64_t)p.N};
+            const cuuint64_t strides[3] = {(cuuint64_t)vw.sx * 2, (cuuint64_t)vw.sy * 2, (cuuint64_t)vw.sn * 2};
+            st = make_map(&map_a[v], vw.base, 4, dims, strides, box, "activations");
             if (st != HOIG_OK) return st;
         }
     }
@@ -558,14 +621,34 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET) != cudaSuccess)
+        if (cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess)
             return check_launch("conv_umma smem attribute");
     }
     const int total = P.m_tiles * P.n_tiles;
     const int grid = total < num_sms ? total : num_sms;
-    const size_t smem = (size_t)P.stages * stage_bytes + 1024;
-    conv_umma_kernel<<<grid, THREADS, smem, stream>>>(P, map_w, map_a0, map_a1);
+    const size_t smem = (size_t)STG_BYTES + (size_t)P.stages * stage_bytes + 1024;
+    conv_umma_kernel<<<grid, THREADS, smem, stream>>>(P, map_w, map_a[0], map_a[1], map_a[2], map_a[3]);
     return check_launch("conv_umma_kernel");
+}
+
+}  // namespace
+
+int g_force_gather = -1;
+
+int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
+{
+    ConvPlan plan;
+    int st = plan_conv(d, BM, &plan);
+    if (st != HOIG_OK) return st;
+    if (g_force_gather < 0) {
+        const char *e = getenv("HOIG_UMMA_GATHER_ONLY");
+        g_force_gather = (e && e[0] == '1') ? 1 : 0;
+    }
+    for (int i = 0; i < plan.n; ++i) {
+        st = launch_one(plan.launch[i], stream, g_force_gather);
+        if (st != HOIG_OK) return st;
+    }
+    return HOIG_OK;
 }
 
 }  // namespace hoig

@@ -146,44 +146,76 @@ rasterize_kernel(const float *__restrict__ faces, int F, int is, int band_rows, 
             if (k % 3 != 2) wild |= !(fabsf(f[k]) <= kWild);  // catches NaN / inf / huge
 
         float fi[9];
-        int row_lo = r0, row_hi = r1;
         Edges e;
         e.ya[0] = f[1]; e.dx[0] = __fsub_rn(f[3], f[0]); e.xa[0] = f[0]; e.dy[0] = __fsub_rn(f[4], f[1]);
         e.ya[1] = f[4]; e.dx[1] = __fsub_rn(f[6], f[3]); e.xa[1] = f[3]; e.dy[1] = __fsub_rn(f[7], f[4]);
         e.ya[2] = f[7]; e.dx[2] = __fsub_rn(f[0], f[6]); e.xa[2] = f[6]; e.dy[2] = __fsub_rn(f[1], f[7]);
 
+        // Search window.  A pixel that passes the three float edge tests lies within ~3e-5 NDC of each
+        // (computed) edge half-plane, hence within  3e-5 / sin(theta_min / 2)  of the vertex bounding box
+        // (theta_min = smallest corner angle; derivation in DESIGN.md "rasterizer exactness").  Faces with
+        // theta_min >= ~3 deg get a 1-pixel margin, needles down to ~0.06 deg a (1 + 0.03*is)-pixel margin,
+        // anything thinner / larger than 64 NDC / non-finite searches the whole band.  Inside the window the
+        // passing columns of every row are still found EXACTLY by binary search on the reference predicate.
+        int row_lo = r0, row_hi = r1, col_lo = 0, col_hi = is - 1;
         if (!wild) {
-            // rows of this band that can pass edge i: A_i(y) >= min_x B_i(x); B monotone => min at an end.
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const float bmin = fminf(e.B(i, centre[0]), e.B(i, centre[is - 1]));
-                if (!(fmaxf(e.A(i, centre[r0]), e.A(i, centre[r1])) >= bmin)) { row_lo = 1; row_hi = 0; }
+            const float l0 = e.dx[0] * e.dx[0] + e.dy[0] * e.dy[0];
+            const float l1 = e.dx[1] * e.dx[1] + e.dy[1] * e.dy[1];
+            const float l2 = e.dx[2] * e.dx[2] + e.dy[2] * e.dy[2];
+            const float lmax = fmaxf(l0, fmaxf(l1, l2));
+            const float lmid = fmaxf(fminf(l0, l1), fminf(fmaxf(l0, l1), l2));
+            const float cross = e.dx[0] * e.dy[1] - e.dy[0] * e.dx[1];      // twice the signed area
+            const float sin2 = cross * cross;                                 // = sin^2(theta) * l_a * l_b at each corner
+            const float ll = lmax * lmid;
+            const float big = fmaxf(fmaxf(fabsf(f[0]), fabsf(f[3])), fmaxf(fmaxf(fabsf(f[6]), fabsf(f[1])), fmaxf(fabsf(f[4]), fabsf(f[7]))));
+            const float tau0 = fmaxf(0.05f, 1.2e-4f * isf);
+            float margin = -1.f;
+            if (big <= 64.f && ll > 1e-30f && cross > 0.f) {
+                if (sin2 >= tau0 * tau0 * ll) margin = 1.f;
+                else if (sin2 >= 1e-6f * ll) margin = 1.f + ceilf(0.03f * isf);
             }
-            if (row_lo > row_hi) continue;
+            if (margin > 0.f) {
+                const float xmin = fminf(f[0], fminf(f[3], f[6])), xmax = fmaxf(f[0], fmaxf(f[3], f[6]));
+                const float ymin = fminf(f[1], fminf(f[4], f[7])), ymax = fmaxf(f[1], fmaxf(f[4], f[7]));
+                // pixel coordinate of an NDC position: 0.5 * (v * is + is - 1)
+                col_lo = max(0, (int)floorf(0.5f * (xmin * isf + isf - 1.f) - margin));
+                col_hi = min(is - 1, (int)ceilf(0.5f * (xmax * isf + isf - 1.f) + margin));
+                row_lo = max(r0, (int)floorf(0.5f * (ymin * isf + isf - 1.f) - margin));
+                row_hi = min(r1, (int)ceilf(0.5f * (ymax * isf + isf - 1.f) + margin));
+                if (row_lo > row_hi || col_lo > col_hi) continue;
+            } else {
+                // exact band test / row range from the monotone predicate alone (degenerate faces)
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const float bmin = fminf(e.B(i, centre[0]), e.B(i, centre[is - 1]));
-                if (e.dx[i] >= 0.f) {  // A non-decreasing in y: passing rows are a suffix
-                    row_lo = max(row_lo, first_true(r0, r1, [&](int y) { return e.A(i, centre[y]) >= bmin; }));
-                } else {               // A non-increasing: passing rows are a prefix
-                    row_hi = min(row_hi, first_true(r0, r1, [&](int y) { return !(e.A(i, centre[y]) >= bmin); }) - 1);
+                for (int i = 0; i < 3; ++i) {
+                    const float bmin = fminf(e.B(i, centre[0]), e.B(i, centre[is - 1]));
+                    if (!(fmaxf(e.A(i, centre[r0]), e.A(i, centre[r1])) >= bmin)) { row_lo = 1; row_hi = 0; }
                 }
+                if (row_lo > row_hi) continue;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const float bmin = fminf(e.B(i, centre[0]), e.B(i, centre[is - 1]));
+                    if (e.dx[i] >= 0.f) {  // A non-decreasing in y: passing rows are a suffix
+                        row_lo = max(row_lo, first_true(r0, r1, [&](int y) { return e.A(i, centre[y]) >= bmin; }));
+                    } else {               // A non-increasing: passing rows are a prefix
+                        row_hi = min(row_hi, first_true(r0, r1, [&](int y) { return !(e.A(i, centre[y]) >= bmin); }) - 1);
+                    }
+                }
+                if (row_lo > row_hi) continue;
             }
-            if (row_lo > row_hi) continue;
         }
         face_inverse(f, isf, fi);
 
         for (int y = row_lo; y <= row_hi; ++y) {
             const float yp = centre[y];
-            int c_lo = 0, c_hi = is - 1;
+            int c_lo = col_lo, c_hi = col_hi;
             if (!wild) {
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     const float a = e.A(i, yp);
                     if (e.dy[i] >= 0.f) {  // B non-decreasing in x: pass set {B <= a} is a prefix
-                        c_hi = min(c_hi, first_true(0, is - 1, [&](int x) { return a < e.B(i, centre[x]); }) - 1);
+                        c_hi = min(c_hi, first_true(col_lo, col_hi, [&](int x) { return a < e.B(i, centre[x]); }) - 1);
                     } else {               // B non-increasing: pass set is a suffix
-                        c_lo = max(c_lo, first_true(0, is - 1, [&](int x) { return !(a < e.B(i, centre[x])); }));
+                        c_lo = max(c_lo, first_true(col_lo, col_hi, [&](int x) { return !(a < e.B(i, centre[x])); }));
                     }
                 }
             }
@@ -342,9 +374,9 @@ extern "C" int hoig_rasterize_fim_wim(const float *faces, int B, int F, int imag
                                       int flip_y, int32_t *fim, float *wim, float *depth, void *, size_t,
                                       hoigStream_t stream)
 {
-    HOIG_REQUIRE(faces && fim && wim, "rasterize: null pointer");
     HOIG_REQUIRE(B >= 0 && F >= 0 && image_size >= 1 && image_size <= 2048, "rasterize: bad shape B=%d F=%d is=%d", B, F, image_size);
     if (B == 0) return HOIG_OK;
+    HOIG_REQUIRE((faces || F == 0) && fim && wim, "rasterize: null pointer");
     const int is = image_size;
     int band_rows = kMaxBandPixels / is;
     if (band_rows > is) band_rows = is;

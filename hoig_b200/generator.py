@@ -329,6 +329,32 @@ class GeneratorB200(nn.Module):
         y, _ = self._conv(x, name + ".0.weight", cout, 7, act=act)
         return ops.nhwc_to_nchw(y, cout)
 
+    def _heads(self, net, xy):
+        """generator.py:311-315 + :457-461: the four 7x7 regression heads of one side share the [hand | object]
+        decoder buffer, so they run as ONE conv with 8 output channels and a per-channel activation:
+        rows 0-2 img_reg (tanh, hand half), 3 attetion_reg_hand (sigmoid, hand half), 4 attetion_reg_bg
+        (sigmoid, both halves), 5-7 obj_model.img_reg (tanh, object half).  Unused halves carry zero weights."""
+        c0 = self.conv_dim
+        names = [net + ".img_reg.0.weight", net + ".attetion_reg_hand.0.weight", net + ".attetion_reg_bg.0.weight",
+                 "obj_model.img_reg.0.weight"]
+        prm = [self._p(n) for n in names]
+
+        def build():
+            w = torch.zeros(8, 2 * c0, 7, 7, dtype=torch.float32, device=prm[0].device)
+            w[0:3, :c0] = prm[0].detach().float()
+            w[3:4, :c0] = prm[1].detach().float()
+            w[4:5] = prm[2].detach().float()
+            w[5:8, c0:] = prm[3].detach().float()
+            table = torch.tensor([ops.ACT_TANH] * 3 + [ops.ACT_SIGMOID] * 2 + [ops.ACT_TANH] * 3, dtype=torch.int32,
+                                 device=prm[0].device)
+            return pack_conv_weight(w, self.compute_dtype), table
+
+        wp, table = self._cached(net + "#heads", prm, build)
+        n, h, w_, _ = xy.shape
+        y = self._new(n, h, w_, 8)
+        ops.conv2d(xy, wp, y, kh=7, kw=7, stride=1, pad=3, act_table=table)
+        return y
+
     def _warp(self, layer, src, tsf, T, flows):
         """generator.py:480-491 + the residual add of :407/:427/:446; writes into ``tsf`` in place."""
         h = src.shape[1]
@@ -460,10 +486,11 @@ class GeneratorB200(nn.Module):
         self._decode("tsf_model", tx, t_cats, tsf_hand_conds, seg_t, t_xy[..., :c0])
         res = {}
         for tag, net, xy in (("src", "src_model", s_xy), ("tsf", "tsf_model", t_xy)):
-            res[tag + "_hand"] = self._head(net + ".img_reg", xy[..., :c0], 3, ops.ACT_TANH)
-            res[tag + "_mask_hand"] = self._head(net + ".attetion_reg_hand", xy[..., :c0], 1, ops.ACT_SIGMOID)
-            res[tag + "_mask_bg"] = self._head(net + ".attetion_reg_bg", xy, 1, ops.ACT_SIGMOID)
-            res[tag + "_obj"] = self._head("obj_model.img_reg", xy[..., c0:], 3, ops.ACT_TANH)
+            y = self._heads(net, xy)
+            res[tag + "_hand"] = ops.nhwc_to_nchw(y[..., 0:3], 3)
+            res[tag + "_mask_hand"] = ops.nhwc_to_nchw(y[..., 3:4], 1)
+            res[tag + "_mask_bg"] = ops.nhwc_to_nchw(y[..., 4:5], 1)
+            res[tag + "_obj"] = ops.nhwc_to_nchw(y[..., 5:8], 3)
         return (res["src_obj"], res["src_hand"], res["src_mask_bg"], res["src_mask_hand"],
                 res["tsf_obj"], res["tsf_hand"], res["tsf_mask_bg"], res["tsf_mask_hand"])
 

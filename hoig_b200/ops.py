@@ -47,9 +47,9 @@ def _f32c(t: torch.Tensor, name: str) -> int:
     return t.data_ptr()
 
 
-def packed_dims(cout: int, kh: int, kw: int, cin: int):
+def packed_dims(cout: int, kh: int, kw: int, cin: int, mode: int = CONV, stride: int = 1, pad: int = 0):
     r, c = ctypes.c_int(), ctypes.c_int()
-    _lib.load().hoig_conv_packed_dims(cout, kh, kw, cin, ctypes.byref(r), ctypes.byref(c))
+    _lib.load().hoig_conv_packed_dims(mode, cout, kh, kw, cin, stride, pad, ctypes.byref(r), ctypes.byref(c))
     return r.value, c.value
 
 
@@ -139,7 +139,8 @@ def local_attn_reshape(inputs: torch.Tensor, out: torch.Tensor, k: int) -> torch
 def conv2d(x0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, *, kh: int, kw: int, stride: int = 1,
            pad: int = 0, mode: int = CONV, x1: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
            act: int = ACT_NONE, residual: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
-           flow: Optional[torch.Tensor] = None, cout: Optional[int] = None, simt: bool = False) -> torch.Tensor:
+           flow: Optional[torch.Tensor] = None, cout: Optional[int] = None, simt: bool = False,
+           act_table: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Implicit-GEMM convolution; see ``hoigConvDesc``.  ``weight`` is the packed matrix
     from :func:`hoig_b200.packing.pack_conv_weight`; ``out`` is an NHWC view."""
     d = ConvDesc()
@@ -157,7 +158,7 @@ def conv2d(x0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, *, kh: int
     No, OH, OW, Co = out.shape
     d.OH, d.OW, d.Cout = OH, OW, (cout if cout is not None else Co)
     d.KH, d.KW, d.stride, d.pad = kh, kw, stride, pad
-    rows, cols = packed_dims(d.Cout, kh, kw, d.C0 + d.C1)
+    rows, cols = packed_dims(d.Cout, kh, kw, d.C0 + d.C1, mode, stride, pad)
     if tuple(weight.shape) != (rows, cols) or weight.dtype != x0.dtype or not weight.is_contiguous():
         raise ValueError(f"conv2d: packed weight must be {(rows, cols)} {x0.dtype}, got {tuple(weight.shape)} {weight.dtype}")
     if No != N or out.dtype != x0.dtype:
@@ -174,6 +175,12 @@ def conv2d(x0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, *, kh: int
     if stats is not None and (stats.dtype != torch.float64 or stats.numel() != N * d.Cout * 2):
         raise ValueError("conv2d: stats must be float64 [N, Cout, 2]")
     d.flow = _f32c(flow, "flow") if flow is not None else None
+    if act_table is not None:
+        if act_table.dtype != torch.int32 or act_table.numel() != d.Cout or not act_table.is_cuda:
+            raise ValueError("conv2d: act_table must be a CUDA int32 tensor with Cout entries")
+        d.act_table = act_table.data_ptr()
+    else:
+        d.act_table = None
     L = _lib.lib()
     if _lib.recorder.timing:
         _lib.recorder.tag = (f"{('conv', 'convT', 'attn')[mode]} k{kh} s{stride} Cin{d.C0 + d.C1} Cout{d.Cout} "

@@ -112,18 +112,22 @@ typedef struct {
     int KH, KW, stride, pad;
     const void *src0; int64_t ld0;
     const void *src1; int64_t ld1;
-    const void *weight; /* packed [Cout_pad][K_pad], k = (r*KW + s)*(C0+C1) + c; see hoig_conv_packed_dims */
+    const void *weight; /* packed [Cout_pad][cols]; conv / local attention: k = (r*KW + s)*(C0+C1) + c;
+                         * transposed: the four output-parity phases side by side (hoig_conv_packed_dims) */
     const float *bias;  /* [Cout] or NULL */
     int act;            /* hoigAct applied after bias (+ residual) */
     const void *residual; int64_t ldr; /* NHWC (N,OH,OW,Cout) added before `act`, or NULL */
     void *dst; int64_t ldd;            /* NHWC (N,OH,OW,>=Cout) */
     double *stats;      /* NULL or [N][Cout][2]: += per-plane sum / sum of squares of the stored values */
     const float *flow;  /* HOIG_CONV_LOCAL_ATTN only: (N,H,W,2) pixel-unit offsets (x,y) */
+    const int *act_table; /* NULL or [Cout] device array of hoigAct codes overriding `act` per output channel */
 } hoigConvDesc;
 
-/* Rows / columns of the packed weight matrix for a given problem
- * (Cout padded to 16, K padded to 64 elements). */
-int hoig_conv_packed_dims(int Cout, int KH, int KW, int Cin, int *rows, int *cols);
+/* Rows / columns of the packed weight matrix for a given problem: rows = Cout padded to 16;
+ * cols = KH*KW*Cin padded to 64, or, for HOIG_CONV_TRANSPOSED (stride 2), the sum over the four
+ * output-parity phases (a,b) of [taps(a)*taps(b)*Cin padded to 64], phases in order (0,0),(0,1),(1,0),(1,1),
+ * taps of a phase ordered by (r,s) over the kernel rows/cols with (a + pad - r) even. */
+int hoig_conv_packed_dims(int mode, int Cout, int KH, int KW, int Cin, int stride, int pad, int *rows, int *cols);
 /* Implicit-GEMM convolution (nn.Conv2d / nn.ConvTranspose2d k3 s2 p1 op1 /
  * the k5 s5 conv over cat[BlockExtractor(tgt,0), BlockExtractor(src,flow)] of
  * extract_attn.py:24-26 with both extractions fused into the operand gather).

@@ -26,17 +26,38 @@ def unpack_weight(wp, cout, kh, kw, cin_p):
     return w.permute(0, 3, 1, 2).contiguous()  # OIHW over padded input channels
 
 
+def unpack_transposed(wp, cout, kh, kw, cin_p, pad):
+    """Inverse of the four-phase layout of pack_conv_weight(transposed=True): -> (Cout, Cin_p, KH, KW)."""
+    from hoig_b200.packing import transposed_axis_taps
+    ra, sa = transposed_axis_taps(kh, pad), transposed_axis_taps(kw, pad)
+    w = torch.zeros(cout, cin_p, kh, kw)
+    off = 0
+    for a in (0, 1):
+        for b in (0, 1):
+            taps = [(r, s) for r in ra[a] for s in sa[b]]
+            n = len(taps) * cin_p
+            blk = wp.float()[:cout, off:off + n].reshape(cout, len(taps), cin_p)
+            for i, (r, s) in enumerate(taps):
+                w[:, :, r, s] = blk[:, i]
+            off += ceil_to(n, 64)
+    return w
+
+
 def conv2d(x0, weight, out, *, kh, kw, stride=1, pad=0, mode=0, x1=None, bias=None, act=0, residual=None, stats=None,
-           flow=None, cout=None, simt=False):
+           flow=None, cout=None, simt=False, act_table=None):
     x = x0 if x1 is None else torch.cat([x0, x1], 3)
     cin_p = x.shape[3]
     cout = out.shape[3] if cout is None else cout
-    w = unpack_weight(weight, cout, kh, kw, cin_p)
     xn = x.float().permute(0, 3, 1, 2)
+    if mode == real_ops.CONV_TRANSPOSED:
+        w = unpack_transposed(weight, cout, kh, kw, cin_p, pad)
+        y = F.conv_transpose2d(xn, w.permute(1, 0, 2, 3), None, stride=stride, padding=pad, output_padding=1)
+    else:
+        w = unpack_weight(weight, cout, kh, kw, cin_p)
     if mode == real_ops.CONV:
         y = F.conv2d(xn, w, None, stride=stride, padding=pad)
     elif mode == real_ops.CONV_TRANSPOSED:
-        y = F.conv_transpose2d(xn, w.permute(1, 0, 2, 3), None, stride=stride, padding=pad, output_padding=1)
+        pass
     else:
         c = x0.shape[3]
         tgt, src = xn[:, :c], xn[:, c:]
@@ -49,7 +70,11 @@ def conv2d(x0, weight, out, *, kh, kw, stride=1, pad=0, mode=0, x1=None, bias=No
     y = y.permute(0, 2, 3, 1)
     if residual is not None:
         y = y + residual[..., :cout].float()
-    y = _q(ACT[act](y), out)
+    if act_table is not None:
+        y = torch.stack([ACT[int(a)](y[..., i]) for i, a in enumerate(act_table.tolist())], -1)
+    else:
+        y = ACT[act](y)
+    y = _q(y, out)
     out[..., :cout] = y
     if stats is not None:
         yf = y.double()

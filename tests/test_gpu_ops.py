@@ -21,7 +21,9 @@ def _load_ref(name):
     path = os.path.join(REF_DIR, name + ".so")
     if not os.path.exists(path):
         return None
-    spec = importlib.util.spec_from_file_location(name, path)
+    # the reference's rasterizer hard-codes its pybind module name (rasterize_cuda.cpp:194)
+    init = "rasterize" if name == "ref_rasterize_cuda" else name
+    spec = importlib.util.spec_from_file_location(init, path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
@@ -146,6 +148,10 @@ CONV_CASES = [
     ("3x3_s1_w64", 1, 64, 64, 128, 3, 1, "conv", dict(bias=True, act=1)),
     ("3x3_s1_w256_many_tiles", 3, 256, 64, 64, 3, 1, "conv", dict(stats=True)),
     ("3x3_s2", 2, 32, 64, 128, 3, 2, "conv", dict(stats=True)),
+    ("3x3_s2_c32_gather_views", 2, 16, 32, 64, 3, 2, "conv", dict(stats=True, bias=True)),
+    ("3x3_s2_c256", 1, 64, 256, 512, 3, 2, "conv", dict(stats=True)),
+    ("7x7_heads_merged_act_table", 1, 32, 128, 8, 7, 1, "conv", dict(act_table=[3, 3, 3, 4, 4, 3, 3, 3])),
+    ("convT_3x3_s2_c512", 1, 32, 512, 256, 3, 2, "convT", dict(stats=True)),
     ("7x7_stem_c8", 2, 32, 8, 64, 7, 1, "conv", dict(stats=True)),
     ("3x3_seg_c16_relu", 2, 16, 16, 128, 3, 1, "conv", dict(bias=True, act=1)),
     ("7x7_head_c64_n3_tanh", 1, 32, 64, 3, 7, 1, "conv", dict(act=3)),
@@ -184,12 +190,15 @@ def _run_conv(case, dtype, simt=False):
     Cst = ceil_to(Cout, 8)
     res = _rand(g, N, OH, OH, Cst).to(dtype) if ex.get("residual") else None
     kw = dict(kh=k, kw=k, stride=stride, pad=pad_, mode=m, act=ex.get("act", 0), cout=Cout)
+    table = torch.tensor(ex["act_table"], dtype=torch.int32) if ex.get("act_table") else None
     st_ref = torch.zeros(N * Cout * 2, dtype=torch.float64) if ex.get("stats") else None
-    ref = emu_ops.conv2d(x0, wp, torch.zeros(N, OH, OH, Cst, dtype=dtype), x1=x1, bias=bias, residual=res, stats=st_ref, flow=flow, **kw)
+    ref = emu_ops.conv2d(x0, wp, torch.zeros(N, OH, OH, Cst, dtype=dtype), x1=x1, bias=bias, residual=res, stats=st_ref, flow=flow,
+                         act_table=table, **kw)
     st = torch.zeros(N * Cout * 2, dtype=torch.float64, device="cuda") if ex.get("stats") else None
     cu = lambda t: None if t is None else t.cuda()
     out = torch.zeros(N, OH, OH, Cst, dtype=dtype, device="cuda")
-    ops.conv2d(cu(x0), wp.cuda(), out, x1=cu(x1), bias=cu(bias), residual=cu(res), stats=st, flow=cu(flow), simt=simt, **kw)
+    ops.conv2d(cu(x0), wp.cuda(), out, x1=cu(x1), bias=cu(bias), residual=cu(res), stats=st, flow=cu(flow), simt=simt,
+               act_table=cu(table), **kw)
     torch.cuda.synchronize()
     return out, ref, st, st_ref
 

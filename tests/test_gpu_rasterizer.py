@@ -22,7 +22,9 @@ def _load_ref(name):
     path = os.path.join(REF_DIR, name + ".so")
     if not os.path.exists(path):
         return None
-    spec = importlib.util.spec_from_file_location(name, path)
+    # the reference's rasterizer hard-codes its pybind module name (rasterize_cuda.cpp:194)
+    init = "rasterize" if name == "ref_rasterize_cuda" else name
+    spec = importlib.util.spec_from_file_location(init, path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
