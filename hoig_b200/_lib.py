@@ -36,6 +36,7 @@ class ConvDesc(Structure):
         ("stats", c_void_p),
         ("flow", c_void_p),
         ("act_table", c_void_p),
+        ("pad_w", c_int),
     ]
 
 
@@ -68,10 +69,15 @@ _SIGNATURES = {
                                     c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "hoig_resize_flow": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hoig_attn_finish": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
-                                 c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+                                 c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_void_p]),
+    "hoig_attn_unfold": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+                                 c_int, c_int, c_void_p]),
     "hoig_grid_sample": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int,
                                  c_int, c_int, c_void_p]),
     "hoig_composite": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p]),
+    "hoig_hunfold_nchw": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "hoig_hfold_nchw": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                POINTER(c_void_p), POINTER(c_int), POINTER(c_int), c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -57,7 +57,8 @@ int plan_conv(const hoigConvDesc *d, int bm, ConvPlan *plan)
     HOIG_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->OH > 0 && d->OW > 0 && d->Cout > 0, "conv2d: bad shape");
     HOIG_REQUIRE(d->C0 > 0 && d->C0 % 8 == 0 && d->C1 >= 0 && d->C1 % 8 == 0, "conv2d: C0/C1 must be multiples of 8 (got %d,%d)", d->C0, d->C1);
     HOIG_REQUIRE(d->C1 == 0 || d->src1, "conv2d: C1 > 0 needs src1");
-    HOIG_REQUIRE(d->KH > 0 && d->KW > 0 && d->KH * d->KW <= kMaxTaps && d->stride > 0 && d->pad >= 0, "conv2d: bad kernel geometry");
+    HOIG_REQUIRE(d->KH > 0 && d->KW > 0 && d->KH * d->KW <= kMaxTaps && d->stride > 0 && d->pad >= 0 && d->pad_w >= 0,
+                 "conv2d: bad kernel geometry");
     HOIG_REQUIRE(d->ld0 >= d->C0 && d->ld0 % 8 == 0 && (d->C1 == 0 || (d->ld1 >= d->C1 && d->ld1 % 8 == 0)),
                  "conv2d: source pixel stride must be a multiple of 8 and >= channels");
     HOIG_REQUIRE(d->ldd >= d->Cout, "conv2d: ldd < Cout");
@@ -84,7 +85,7 @@ int plan_conv(const hoigConvDesc *d, int bm, ConvPlan *plan)
     base.os = 1; base.OHf = d->OH; base.OWf = d->OW;
 
     if (d->mode == HOIG_CONV) {
-        HOIG_REQUIRE(d->OH == (d->H + 2 * d->pad - d->KH) / d->stride + 1 && d->OW == (d->W + 2 * d->pad - d->KW) / d->stride + 1,
+        HOIG_REQUIRE(d->OH == (d->H + 2 * d->pad - d->KH) / d->stride + 1 && d->OW == (d->W + 2 * d->pad_w - d->KW) / d->stride + 1,
                      "conv2d: output size does not match geometry");
         ConvParams &p = plan->launch[0];
         p = base;
@@ -106,7 +107,7 @@ int plan_conv(const hoigConvDesc *d, int bm, ConvPlan *plan)
         }
         for (int r = 0; r < d->KH; ++r)
             for (int s = 0; s < d->KW; ++s) {
-                const int t = r * d->KW + s, qy = r - d->pad, qx = s - d->pad;
+                const int t = r * d->KW + s, qy = r - d->pad, qx = s - d->pad_w;
                 if (phases) {
                     const int a = mod2(qy), b = mod2(qx);
                     p.tap_dy[t] = (int8_t)((qy - a) / 2); p.tap_dx[t] = (int8_t)((qx - b) / 2); p.tap_map[t] = (int8_t)(a * 2 + b);

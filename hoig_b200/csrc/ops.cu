@@ -179,7 +179,8 @@ template <typename T, int KK>
 __global__ void __launch_bounds__(128)
 attn_finish_kernel(const T *__restrict__ hidden, int64_t ldh, int Chid, const float *__restrict__ w2,
                    const float *__restrict__ b2, const T *__restrict__ src, int64_t lds, const float *__restrict__ flow,
-                   const T *__restrict__ tgt, int64_t ldt, T *__restrict__ dst, int64_t ldd, int64_t npix_total, int h, int C)
+                   const T *__restrict__ tgt, int64_t ldt, T *__restrict__ dst, int64_t ldd, int64_t npix_total, int h, int C,
+                   const T *__restrict__ unfold, int64_t ldu)
 {
     constexpr int K = (KK == 25) ? 5 : 3;
     __shared__ float s_attn[4][KK];
@@ -228,13 +229,17 @@ attn_finish_kernel(const T *__restrict__ hidden, int64_t ldh, int Chid, const fl
             float smp[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) smp[j] = 0.f;
+            if (unfold) {   // taps already extracted by attn_unfold: [tap][tgt C | src C] per pixel
+                load8(unfold + pix * ldu + (int64_t)t * 2 * C + C + cc * 8, smp);
+            } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float u[8];
-                load8(src + (plane + s_idx[warp][t][q]) * lds + cc * 8, u);
-                const float wq = s_w[warp][t][q];
+                for (int q = 0; q < 4; ++q) {
+                    float u[8];
+                    load8(src + (plane + s_idx[warp][t][q]) * lds + cc * 8, u);
+                    const float wq = s_w[warp][t][q];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) smp[j] = __fmaf_rn(wq, u[j], smp[j]);
+                    for (int j = 0; j < 8; ++j) smp[j] = __fmaf_rn(wq, u[j], smp[j]);
+                }
             }
             const float a = s_attn[warp][t];
 #pragma unroll
@@ -330,6 +335,108 @@ __global__ void local_attn_reshape_kernel(const float *__restrict__ in, float *_
     const int Wo = k * W, Ho = k * H;
     const int x = (int)(i % Wo), y = (int)((i / Wo) % Ho), b = (int)(i / ((int64_t)Wo * Ho));
     out[i] = in[(((int64_t)b * k * k + (y % k) * k + x % k) * H + y / k) * W + x / k];
+}
+
+// extract_attn.py:24-25 materialised for the tensor-core path: U[pix][t*2C + c] = BlockExtractor(tgt, 0) tap t
+// for c < C and BlockExtractor(src, flow) tap t for c >= C (block_extractor_kernel.cu:52-84, same float op
+// order as the fused gather), so the k x k stride-k conv over cat[block_target, block_source] becomes a plain
+// GEMM over K = k*k*2C that TMA can feed.  One CTA = 4 pixels; tap tables are built once per pixel in smem.
+template <typename T, int KK>
+__global__ void __launch_bounds__(256)
+attn_unfold_kernel(const T *__restrict__ src, int64_t lds, const T *__restrict__ tgt, int64_t ldt, const float *__restrict__ flow,
+                   T *__restrict__ out, int64_t ldo, int64_t npix_total, int h, int C)
+{
+    constexpr int K = (KK == 25) ? 5 : 3;
+    constexpr int P = 4;
+    __shared__ int s_idx[P][KK][4];
+    __shared__ float s_w[P][KK][4];
+    __shared__ int s_tidx[P][KK];
+    const int64_t pix0 = (int64_t)blockIdx.x * P;
+    for (int i = threadIdx.x; i < P * KK; i += blockDim.x) {
+        const int pp = i / KK, t = i % KK;
+        const int64_t pix = pix0 + pp;
+        if (pix < npix_total) {
+            const int x = (int)(pix % h), y = (int)((pix / h) % h);
+            const BETap tp = be_tap(flow[pix * 2], flow[pix * 2 + 1], y, x, t / K, t % K, K, h, h);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { s_idx[pp][t][q] = tp.idx[q]; s_w[pp][t][q] = tp.w[q]; }
+            const int iy = max(min(y + t / K - K / 2, h - 1), 0), ix = max(min(x + t % K - K / 2, h - 1), 0);
+            s_tidx[pp][t] = iy * h + ix;
+        }
+    }
+    __syncthreads();
+    const int chunks = C / 8;
+    for (int i = threadIdx.x; i < P * chunks; i += blockDim.x) {
+        const int pp = i / chunks, cc = i % chunks;
+        const int64_t pix = pix0 + pp;
+        if (pix >= npix_total) continue;
+        const int64_t plane = (pix / ((int64_t)h * h)) * h * h;
+        T *o = out + pix * ldo + cc * 8;
+        for (int t = 0; t < KK; ++t) {
+            float v[8];
+            load8(tgt + (plane + s_tidx[pp][t]) * ldt + cc * 8, v);
+            store8(o + (int64_t)t * 2 * C, v);
+            float smp[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) smp[j] = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float u[8];
+                load8(src + (plane + s_idx[pp][t][q]) * lds + cc * 8, u);
+                const float wq = s_w[pp][t][q];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) smp[j] = __fmaf_rn(wq, u[j], smp[j]);
+            }
+            store8(o + (int64_t)t * 2 * C + C, smp);
+        }
+    }
+}
+
+// x7[b,y,x, s*C + c] = x[b,c,y,x+s-k/2]  (zero outside the row / beyond k*C), from the NCHW f32 input
+template <typename T>
+__global__ void hunfold_kernel(const float *__restrict__ src, int B, int C, int H, int W, int k, T *__restrict__ dst, int64_t ldd, int Cpad)
+{
+    const int chunks = Cpad / 8;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * H * W * chunks) return;
+    const int ch = (int)(i % chunks);
+    const int64_t bp = i / chunks;
+    const int x = (int)(bp % W), y = (int)((bp / W) % H), b = (int)(bp / ((int64_t)W * H));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int kc = ch * 8 + j;
+        const int s = kc / C, c = kc - s * C;
+        const int xx = x + s - k / 2;
+        v[j] = (s < k && xx >= 0 && xx < W) ? src[(((int64_t)b * C + c) * H + y) * W + xx] : 0.f;
+    }
+    store8(dst + bp * ldd + ch * 8, v);
+}
+
+struct FoldSegs {
+    float *out[4];
+    int c0[4], n[4], nseg;
+};
+// y[b,g,y,x] = act_g( sum_s Z[b,y,x+s-k/2, s*G + g] ); one thread per (pixel, g)
+template <typename T>
+__global__ void hfold_kernel(const T *__restrict__ z, int64_t ldz, int B, int H, int W, int G, int k, const int *__restrict__ act_table,
+                             FoldSegs segs)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * G * H * W) return;
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const int g = (int)((i / ((int64_t)W * H)) % G), b = (int)(i / ((int64_t)W * H * G));
+    float acc = 0.f;
+    for (int s = 0; s < k; ++s) {
+        const int xx = x + s - k / 2;
+        if (xx < 0 || xx >= W) continue;
+        acc += DT<T>::ld(z + (((int64_t)b * H + y) * W + xx) * ldz + s * G + g);
+    }
+    acc = apply_act(acc, act_table ? act_table[g] : HOIG_ACT_NONE);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (q < segs.nseg && g >= segs.c0[q] && g < segs.c0[q] + segs.n[q])
+            segs.out[q][(((int64_t)b * segs.n[q] + (g - segs.c0[q])) * H + y) * W + x] = acc;
 }
 
 template <typename F> int dispatch(int dtype, F f)
@@ -437,9 +544,10 @@ extern "C" int hoig_resize_flow(const float *T, int B, int Hi, int Wi, int h, in
 
 extern "C" int hoig_attn_finish(const void *hidden, int64_t ldh, int Chid, const float *w2, const float *b2, const void *src,
                                 int64_t lds, const float *flow, const void *tgt, int64_t ldt, void *dst, int64_t ldd, int dtype,
-                                int N, int h, int C, int k, hoigStream_t stream)
+                                int N, int h, int C, int k, const void *unfold, int64_t ldu, hoigStream_t stream)
 {
     HOIG_REQUIRE(hidden && w2 && b2 && src && flow && tgt && dst, "attn_finish: null pointer");
+    HOIG_REQUIRE(!unfold || (ldu >= (int64_t)2 * k * k * C && ldu % 8 == 0), "attn_finish: unfold buffer needs 2*k*k*C channels");
     HOIG_REQUIRE(k == 5 || k == 3, "attn_finish: kernel size %d not supported (3 or 5)", k);
     HOIG_REQUIRE(C % 8 == 0 && lds % 8 == 0 && ldt % 8 == 0 && ldd % 8 == 0, "attn_finish: channels / strides must be multiples of 8");
     const int64_t npix = (int64_t)N * h * h;
@@ -448,10 +556,12 @@ extern "C" int hoig_attn_finish(const void *hidden, int64_t ldh, int Chid, const
         using T = std::remove_pointer_t<decltype(tag)>;
         if (k == 5)
             attn_finish_kernel<T, 25><<<ceil_div(npix, 4), 128, 0, as_stream(stream)>>>(
-                (const T *)hidden, ldh, Chid, w2, b2, (const T *)src, lds, flow, (const T *)tgt, ldt, (T *)dst, ldd, npix, h, C);
+                (const T *)hidden, ldh, Chid, w2, b2, (const T *)src, lds, flow, (const T *)tgt, ldt, (T *)dst, ldd, npix, h, C,
+                (const T *)unfold, ldu);
         else
             attn_finish_kernel<T, 9><<<ceil_div(npix, 4), 128, 0, as_stream(stream)>>>(
-                (const T *)hidden, ldh, Chid, w2, b2, (const T *)src, lds, flow, (const T *)tgt, ldt, (T *)dst, ldd, npix, h, C);
+                (const T *)hidden, ldh, Chid, w2, b2, (const T *)src, lds, flow, (const T *)tgt, ldt, (T *)dst, ldd, npix, h, C,
+                (const T *)unfold, ldu);
         return check_launch("attn_finish_kernel");
     });
 }
@@ -497,4 +607,59 @@ extern "C" int hoig_local_attn_reshape_f32(const float *in, float *out, int B, i
     if (n == 0) return HOIG_OK;
     local_attn_reshape_kernel<<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>(in, out, n, k, H, W);
     return check_launch("local_attn_reshape_kernel");
+}
+
+extern "C" int hoig_attn_unfold(const void *src, int64_t lds, const void *tgt, int64_t ldt, const float *flow, void *out,
+                                int64_t ldo, int dtype, int N, int h, int C, int k, hoigStream_t stream)
+{
+    HOIG_REQUIRE(src && tgt && flow && out, "attn_unfold: null pointer");
+    HOIG_REQUIRE(k == 5 || k == 3, "attn_unfold: kernel size %d not supported (3 or 5)", k);
+    HOIG_REQUIRE(C % 8 == 0 && lds % 8 == 0 && ldt % 8 == 0 && ldo % 8 == 0 && ldo >= (int64_t)2 * k * k * C,
+                 "attn_unfold: channels / strides must be multiples of 8 and ldo >= 2*k*k*C");
+    const int64_t npix = (int64_t)N * h * h;
+    if (npix == 0) return HOIG_OK;
+    return dispatch(dtype, [&](auto *tag) {
+        using T = std::remove_pointer_t<decltype(tag)>;
+        if (k == 5)
+            attn_unfold_kernel<T, 25><<<ceil_div(npix, 4), 256, 0, as_stream(stream)>>>((const T *)src, lds, (const T *)tgt, ldt, flow,
+                                                                                       (T *)out, ldo, npix, h, C);
+        else
+            attn_unfold_kernel<T, 9><<<ceil_div(npix, 4), 256, 0, as_stream(stream)>>>((const T *)src, lds, (const T *)tgt, ldt, flow,
+                                                                                      (T *)out, ldo, npix, h, C);
+        return check_launch("attn_unfold_kernel");
+    });
+}
+
+extern "C" int hoig_hunfold_nchw(const float *src, int B, int C, int H, int W, int k, void *dst, int64_t ldd, int Cpad, int dtype,
+                                 hoigStream_t stream)
+{
+    HOIG_REQUIRE(src && dst && k >= 1 && (k & 1) && Cpad % 8 == 0 && Cpad >= k * C && ldd >= Cpad && ldd % 8 == 0, "hunfold: bad argument");
+    const int64_t n = (int64_t)B * H * W * (Cpad / 8);
+    if (n == 0) return HOIG_OK;
+    return dispatch(dtype, [&](auto *tag) {
+        using T = std::remove_pointer_t<decltype(tag)>;
+        hunfold_kernel<T><<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>(src, B, C, H, W, k, (T *)dst, ldd, Cpad);
+        return check_launch("hunfold_kernel");
+    });
+}
+
+extern "C" int hoig_hfold_nchw(const void *z, int64_t ldz, int dtype, int B, int H, int W, int G, int k, const int *act_table,
+                               int nseg, float *const *outs, const int *seg_c0, const int *seg_n, hoigStream_t stream)
+{
+    HOIG_REQUIRE(z && outs && seg_c0 && seg_n && nseg >= 1 && nseg <= 4 && k >= 1 && (k & 1) && ldz >= (int64_t)k * G, "hfold: bad argument");
+    FoldSegs segs;
+    segs.nseg = nseg;
+    for (int q = 0; q < 4; ++q) {
+        segs.out[q] = q < nseg ? outs[q] : nullptr;
+        segs.c0[q] = q < nseg ? seg_c0[q] : 0;
+        segs.n[q] = q < nseg ? seg_n[q] : 0;
+        HOIG_REQUIRE(q >= nseg || outs[q], "hfold: null output");
+    }
+    const int64_t n = (int64_t)B * G * H * W;
+    if (n == 0) return HOIG_OK;
+    return dispatch(dtype, [&](auto *tag) {
+        using T = std::remove_pointer_t<decltype(tag)>;
+        hfold_kernel<T><<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>((const T *)z, ldz, B, H, W, G, k, act_table, segs);
+        return check_launch("hfold_kernel");
+    });
 }

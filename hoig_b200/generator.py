@@ -329,6 +329,51 @@ class GeneratorB200(nn.Module):
         y, _ = self._conv(x, name + ".0.weight", cout, 7, act=act)
         return ops.nhwc_to_nchw(y, cout)
 
+    def _stem(self, wname, prefix_norm, parts, out=None):
+        """7x7 stem conv (no bias) + InstanceNorm(affine) + ReLU (generator.py:99-102, 151-155) on NCHW f32 inputs.
+        The 7 horizontal taps are unfolded into channels while converting the layout (hunfold), so the conv
+        itself is a 7x1 implicit GEMM with K = 7 * 64 fed by TMA."""
+        x = parts[0] if len(parts) == 1 else torch.cat(list(parts), 1)
+        x = x.float().contiguous()
+        b, c, h, w = x.shape
+        cpad = ceil_to(7 * c, 64)
+        x7 = ops.hunfold_nchw(x, self._new(b, h, w, cpad), 7)
+        prm = self._p(wname)
+        cout = prm.shape[0]
+
+        def build():
+            w7 = torch.zeros(cout, cpad, 7, 1, dtype=torch.float32, device=prm.device)
+            # W7[co, s*C + c, r, 0] = W[co, c, r, s]
+            w7[:, :7 * c, :, 0] = prm.detach().float().permute(0, 3, 1, 2).reshape(cout, 7 * c, 7)
+            return pack_conv_weight(w7, self.compute_dtype)
+
+        wp = self._cached(wname + "#stem7", [prm], build)
+        raw = self._new(b, h, w, cout)
+        stats = self._arena.take(b, cout)
+        ops.conv2d(x7, wp, raw, kh=7, kw=1, stride=1, pad=3, pad_w=0, stats=stats)
+        dst = raw if out is None else out
+        ops.instnorm_apply(raw, stats, dst, gamma=self._f32(prefix_norm + "weight"), beta=self._f32(prefix_norm + "bias"), relu=True)
+        return dst
+
+    def _fold7(self, key, weights, x, acts, segments):
+        """7x7 conv with G = few output channels (generator.py:125, 223-241): a 7x1 conv produces the 7 horizontal
+        partial sums Z[.., s*G + g]; hfold adds the 7 shifted columns, applies the per-channel activation and
+        writes NCHW f32.  ``weights`` is a callable returning the (G, C, 7, 7) fp32 weight."""
+        prm, make = weights
+        g = len(acts)
+
+        def build():
+            wm = make()                                                   # (G, C, 7, 7)
+            wz = wm.permute(3, 0, 1, 2).reshape(7 * g, wm.shape[1], 7, 1)  # row s*G + g  <-  W[g, :, r, s]
+            table = torch.tensor(acts, dtype=torch.int32, device=wm.device)
+            return pack_conv_weight(wz, self.compute_dtype), table
+
+        wp, table = self._cached(key, prm, build)
+        n, h, w_, _ = x.shape
+        z = self._new(n, h, w_, ceil_to(7 * g, 8))
+        ops.conv2d(x, wp, z, kh=7, kw=1, stride=1, pad=3, pad_w=0, cout=7 * g)
+        return ops.hfold_nchw(z, g, 7, segments, table)
+
     def _heads(self, net, xy):
         """generator.py:311-315 + :457-461: the four 7x7 regression heads of one side share the [hand | object]
         decoder buffer, so they run as ONE conv with 8 output channels and a per-channel activation:
@@ -338,22 +383,17 @@ class GeneratorB200(nn.Module):
         names = [net + ".img_reg.0.weight", net + ".attetion_reg_hand.0.weight", net + ".attetion_reg_bg.0.weight",
                  "obj_model.img_reg.0.weight"]
         prm = [self._p(n) for n in names]
+        acts = [ops.ACT_TANH] * 3 + [ops.ACT_SIGMOID] * 2 + [ops.ACT_TANH] * 3
 
-        def build():
+        def merged():
             w = torch.zeros(8, 2 * c0, 7, 7, dtype=torch.float32, device=prm[0].device)
             w[0:3, :c0] = prm[0].detach().float()
             w[3:4, :c0] = prm[1].detach().float()
             w[4:5] = prm[2].detach().float()
             w[5:8, c0:] = prm[3].detach().float()
-            table = torch.tensor([ops.ACT_TANH] * 3 + [ops.ACT_SIGMOID] * 2 + [ops.ACT_TANH] * 3, dtype=torch.int32,
-                                 device=prm[0].device)
-            return pack_conv_weight(w, self.compute_dtype), table
+            return w
 
-        wp, table = self._cached(net + "#heads", prm, build)
-        n, h, w_, _ = xy.shape
-        y = self._new(n, h, w_, 8)
-        ops.conv2d(xy, wp, y, kh=7, kw=7, stride=1, pad=3, act_table=table)
-        return y
+        return self._fold7(net + "#heads", (prm, merged), xy, acts, [(0, 3), (3, 1), (4, 1), (5, 3)])
 
     def _warp(self, layer, src, tsf, T, flows):
         """generator.py:480-491 + the residual add of :407/:427/:446; writes into ``tsf`` in place."""
@@ -367,10 +407,18 @@ class GeneratorB200(nn.Module):
         p = f"attn_{layer}.fully_connect_layer."
         n, _, _, c = src.shape
         hidden = self._new(n, h, h, ATTN_HIDDEN)
-        ops.conv2d(tsf, self._w(p + "0.weight"), hidden, kh=ATTN_K, kw=ATTN_K, stride=ATTN_K, pad=0, mode=ops.CONV_LOCAL_ATTN,
-                   x1=src, bias=self._f32(p + "0.bias"), act=ops.ACT_LEAKY, flow=flows[key])
         w2 = self._cached(p + "2#w2", [self._p(p + "2.weight")],
                           lambda: self._p(p + "2.weight").detach().float().reshape(ATTN_K * ATTN_K, ATTN_HIDDEN).contiguous())
+        if self.compute_dtype == torch.bfloat16:
+            # tensor-core path: extract the 2 x 25 taps once (bandwidth-bound), then the k5s5 conv is a plain
+            # TMA-fed GEMM over K = 25*2C and attn_finish re-reads the source taps instead of re-sampling them
+            unf = ops.attn_unfold(src, tsf, flows[key], self._new(n, h, h, 2 * ATTN_K * ATTN_K * c), ATTN_K)
+            ops.conv2d(unf, self._w(p + "0.weight"), hidden, kh=1, kw=1, stride=1, pad=0, bias=self._f32(p + "0.bias"),
+                       act=ops.ACT_LEAKY)
+            return ops.attn_finish(hidden, w2, self._f32(p + "2.bias"), src, flows[key], tsf, tsf, ATTN_K, unfold=unf)
+        # fp32 parity path: both BlockExtractor gathers fused into the conv's operand loader
+        ops.conv2d(tsf, self._w(p + "0.weight"), hidden, kh=ATTN_K, kw=ATTN_K, stride=ATTN_K, pad=0, mode=ops.CONV_LOCAL_ATTN,
+                   x1=src, bias=self._f32(p + "0.bias"), act=ops.ACT_LEAKY, flow=flows[key])
         return ops.attn_finish(hidden, w2, self._f32(p + "2.bias"), src, flows[key], tsf, tsf, ATTN_K)
 
     def _to_nhwc(self, parts: Sequence[torch.Tensor]) -> torch.Tensor:
@@ -379,10 +427,10 @@ class GeneratorB200(nn.Module):
         b, c, h, w = x.shape
         return ops.nchw_to_nhwc(x, self._new(b, h, w, ceil_to(c, 8)))
 
-    def _bg(self, x_nhwc):
+    def _bg(self, parts):
         """ResNetGenerator.forward, generator.py:93-135."""
         p, i, c = "bg_model.model.", 0, self.conv_dim
-        h = self._conv_in_relu(x_nhwc, f"{p}{i}.", f"{p}{i + 1}.", c, 7); i += 3
+        h = self._stem(f"{p}{i}.weight", f"{p}{i + 1}.", parts); i += 3
         for _ in range(self.n_down):
             c *= 2
             h = self._conv_in_relu(h, f"{p}{i}.", f"{p}{i + 1}.", c, 3, stride=2); i += 3
@@ -391,16 +439,16 @@ class GeneratorB200(nn.Module):
         for _ in range(self.n_down):
             c //= 2
             h = self._conv_in_relu(h, f"{p}{i}.", f"{p}{i + 1}.", c, 3, transposed=True); i += 3
-        y, _ = self._conv(h, f"{p}{i}.weight", 3, 7, act=ops.ACT_TANH)
-        return ops.nhwc_to_nchw(y, 3)
+        prm = self._p(f"{p}{i}.weight")
+        return self._fold7(f"{p}{i}#fold7", ([prm], lambda: prm.detach().float()), h, [ops.ACT_TANH] * 3, [(0, 3)])[0]
 
-    def _unet_features(self, net, x_nhwc, seg, seg_cache, final_out):
+    def _unet_features(self, net, x_nchw, seg, seg_cache, final_out):
         """ResUnetGenerator.forward (generator.py:260-281) up to the decoder output (obj_model)."""
-        n, H, W, _ = x_nhwc.shape
+        n, _, H, W = x_nchw.shape
         c = self.conv_dim
         cats = []
         cat0 = self._new(n, H, W, 2 * c)
-        h = self._conv_in_relu(x_nhwc, f"{net}.encoders.0.0.", f"{net}.encoders.0.1.", c, 7, out=cat0[..., :c])
+        h = self._stem(f"{net}.encoders.0.0.weight", f"{net}.encoders.0.1.", [x_nchw], out=cat0[..., :c])
         cats.append(cat0)
         for i in range(1, self.n_down + 1):
             c *= 2
@@ -434,8 +482,8 @@ class GeneratorB200(nn.Module):
             src_bg.append(src_armask)
         if tsf_armask is not None:
             tsf_bg.append(tsf_armask)
-        src_img_bg = self._bg(self._to_nhwc(src_bg))
-        tsf_img_bg = self._bg(self._to_nhwc(tsf_bg))
+        src_img_bg = self._bg(src_bg)
+        tsf_img_bg = self._bg(tsf_bg)
         outs = self._infer_front(src_obj_inputs, tsf_obj_inputs, src_hand_inputs, tsf_hand_inputs, T.float().contiguous(),
                                  src_obj_conds, src_hand_conds, tsf_obj_conds, tsf_hand_conds)
         self._arena = None
@@ -449,16 +497,14 @@ class GeneratorB200(nn.Module):
         flows: dict = {}
         conds = [c.float().contiguous() if c is not None else None for c in (src_hand_conds, tsf_hand_conds, src_obj_conds, tsf_obj_conds)]
         src_hand_conds, tsf_hand_conds, src_obj_conds, tsf_obj_conds = conds
-        xs = self._to_nhwc([src_hand_inputs])
-        xt = self._to_nhwc([tsf_hand_inputs])
-        n, H, W, _ = xs.shape
+        n, _, H, W = src_hand_inputs.shape
 
         def cat_buf(level):
             return self._new(n, H >> level, W >> level, 2 * c0 * 2 ** level)
 
         s_cats, t_cats = [cat_buf(0)], [cat_buf(0)]
-        sx = self._conv_in_relu(xs, "src_model.encoders.0.0.", "src_model.encoders.0.1.", c0, 7, out=s_cats[0][..., :c0])
-        tx = self._conv_in_relu(xt, "tsf_model.encoders.0.0.", "tsf_model.encoders.0.1.", c0, 7, out=t_cats[0][..., :c0])
+        sx = self._stem("src_model.encoders.0.0.weight", "src_model.encoders.0.1.", [src_hand_inputs], out=s_cats[0][..., :c0])
+        tx = self._stem("tsf_model.encoders.0.0.weight", "tsf_model.encoders.0.1.", [tsf_hand_inputs], out=t_cats[0][..., :c0])
         c = c0
         for i in range(1, nd + 1):
             c *= 2
@@ -480,17 +526,13 @@ class GeneratorB200(nn.Module):
         # attetion_reg_bg's cat[x, y] input is a plain view
         s_xy, t_xy = self._new(n, H, W, 2 * c0), self._new(n, H, W, 2 * c0)
         seg_so, seg_to = {}, {}
-        self._unet_features("obj_model", self._to_nhwc([src_obj_inputs]), src_obj_conds, seg_so, s_xy[..., c0:])
-        self._unet_features("obj_model", self._to_nhwc([tsf_obj_inputs]), tsf_obj_conds, seg_to, t_xy[..., c0:])
+        self._unet_features("obj_model", src_obj_inputs, src_obj_conds, seg_so, s_xy[..., c0:])
+        self._unet_features("obj_model", tsf_obj_inputs, tsf_obj_conds, seg_to, t_xy[..., c0:])
         self._decode("src_model", sx, s_cats, src_hand_conds, seg_s, s_xy[..., :c0])
         self._decode("tsf_model", tx, t_cats, tsf_hand_conds, seg_t, t_xy[..., :c0])
         res = {}
         for tag, net, xy in (("src", "src_model", s_xy), ("tsf", "tsf_model", t_xy)):
-            y = self._heads(net, xy)
-            res[tag + "_hand"] = ops.nhwc_to_nchw(y[..., 0:3], 3)
-            res[tag + "_mask_hand"] = ops.nhwc_to_nchw(y[..., 3:4], 1)
-            res[tag + "_mask_bg"] = ops.nhwc_to_nchw(y[..., 4:5], 1)
-            res[tag + "_obj"] = ops.nhwc_to_nchw(y[..., 5:8], 3)
+            res[tag + "_hand"], res[tag + "_mask_hand"], res[tag + "_mask_bg"], res[tag + "_obj"] = self._heads(net, xy)
         return (res["src_obj"], res["src_hand"], res["src_mask_bg"], res["src_mask_hand"],
                 res["tsf_obj"], res["tsf_hand"], res["tsf_mask_bg"], res["tsf_mask_hand"])
 

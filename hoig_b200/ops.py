@@ -137,7 +137,7 @@ def local_attn_reshape(inputs: torch.Tensor, out: torch.Tensor, k: int) -> torch
 
 # ------------------------------------------------------------------ stage G
 def conv2d(x0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, *, kh: int, kw: int, stride: int = 1,
-           pad: int = 0, mode: int = CONV, x1: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+           pad: int = 0, pad_w: Optional[int] = None, mode: int = CONV, x1: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
            act: int = ACT_NONE, residual: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
            flow: Optional[torch.Tensor] = None, cout: Optional[int] = None, simt: bool = False,
            act_table: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -158,6 +158,7 @@ def conv2d(x0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, *, kh: int
     No, OH, OW, Co = out.shape
     d.OH, d.OW, d.Cout = OH, OW, (cout if cout is not None else Co)
     d.KH, d.KW, d.stride, d.pad = kh, kw, stride, pad
+    d.pad_w = pad if pad_w is None else pad_w
     rows, cols = packed_dims(d.Cout, kh, kw, d.C0 + d.C1, mode, stride, pad)
     if tuple(weight.shape) != (rows, cols) or weight.dtype != x0.dtype or not weight.is_contiguous():
         raise ValueError(f"conv2d: packed weight must be {(rows, cols)} {x0.dtype}, got {tuple(weight.shape)} {weight.dtype}")
@@ -246,15 +247,27 @@ def resize_flow(T: torch.Tensor, h: int, subtract_identity: bool = True) -> torc
 
 
 def attn_finish(hidden: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, src: torch.Tensor, flow: torch.Tensor,
-                tgt: torch.Tensor, out: torch.Tensor, k: int) -> torch.Tensor:
+                tgt: torch.Tensor, out: torch.Tensor, k: int, unfold: Optional[torch.Tensor] = None) -> torch.Tensor:
     N, h, _, C = src.shape
     hp, ldh = _nhwc(hidden, "hidden")
     sp, lds = _nhwc(src, "src")
     tp, ldt = _nhwc(tgt, "tgt")
     op, ldo = _nhwc(out, "out")
+    up, ldu = _nhwc(unfold, "unfold") if unfold is not None else (None, 0)
     _lib.check(_lib.lib().hoig_attn_finish(hp, ldh, hidden.shape[3], _f32c(w2, "w2"), _f32c(b2, "b2"), sp, lds,
-                                           _f32c(flow, "flow"), tp, ldt, op, ldo, _dt(src), N, h, C, k, _stream()),
+                                           _f32c(flow, "flow"), tp, ldt, op, ldo, _dt(src), N, h, C, k, up, ldu, _stream()),
                "attn_finish")
+    return out
+
+
+def attn_unfold(src: torch.Tensor, tgt: torch.Tensor, flow: torch.Tensor, out: torch.Tensor, k: int) -> torch.Tensor:
+    """out (N,h,h,2*k*k*C): per tap t the channels [BlockExtractor(tgt,0) tap | BlockExtractor(src,flow) tap]."""
+    N, h, _, C = src.shape
+    sp, lds = _nhwc(src, "src")
+    tp, ldt = _nhwc(tgt, "tgt")
+    op, ldo = _nhwc(out, "out")
+    _lib.check(_lib.lib().hoig_attn_unfold(sp, lds, tp, ldt, _f32c(flow, "flow"), op, ldo, _dt(src), N, h, C, k, _stream()),
+               "attn_unfold")
     return out
 
 
@@ -266,6 +279,30 @@ def grid_sample(x: torch.Tensor, grid: torch.Tensor, out: torch.Tensor, tgt: Opt
     _lib.check(_lib.lib().hoig_grid_sample(xp, ldx, _f32c(grid, "grid"), tp, ldt, op, ldo, _dt(x), N, h, C, _stream()),
                "grid_sample")
     return out
+
+
+def hunfold_nchw(x: torch.Tensor, out: torch.Tensor, k: int) -> torch.Tensor:
+    """NCHW f32 (B,C,H,W) -> NHWC (B,H,W,Cpad) with channel s*C + c = x[b,c,y,x+s-k//2] (zero padded)."""
+    B, C, H, W = x.shape
+    ptr, ld = _nhwc(out, "out")
+    _lib.check(_lib.lib().hoig_hunfold_nchw(_f32c(x, "x"), B, C, H, W, k, ptr, ld, out.shape[3], _dt(out), _stream()),
+               "hunfold_nchw")
+    return out
+
+
+def hfold_nchw(z: torch.Tensor, groups: int, k: int, segments, act_table: Optional[torch.Tensor] = None):
+    """Z (B,H,W,>=k*G) -> list of NCHW f32 tensors, one per (c0, n) segment of the G folded channels."""
+    B, H, W, _ = z.shape
+    zp, ldz = _nhwc(z, "z")
+    outs = [torch.empty(B, n, H, W, dtype=torch.float32, device=z.device) for _, n in segments]
+    nseg = len(segments)
+    arr_p = (ctypes.c_void_p * nseg)(*[o.data_ptr() for o in outs])
+    arr_c0 = (ctypes.c_int * nseg)(*[c0 for c0, _ in segments])
+    arr_n = (ctypes.c_int * nseg)(*[n for _, n in segments])
+    _lib.check(_lib.lib().hoig_hfold_nchw(zp, ldz, _dt(z), B, H, W, groups, k,
+                                          act_table.data_ptr() if act_table is not None else None, nseg, arr_p, arr_c0,
+                                          arr_n, _stream()), "hfold_nchw")
+    return outs
 
 
 def composite(img_bg, obj, hand, mask_bg, mask_hand) -> torch.Tensor:

@@ -109,7 +109,7 @@ typedef struct {
     int N, H, W;        /* input batch / spatial size */
     int C0, C1;         /* channels taken from src0 / src1 (C1 = 0: single source); multiples of 8 */
     int OH, OW, Cout;   /* output size; Cout = logical output channels */
-    int KH, KW, stride, pad;
+    int KH, KW, stride, pad;  /* pad = vertical padding; horizontal padding is pad_w (last field) */
     const void *src0; int64_t ld0;
     const void *src1; int64_t ld1;
     const void *weight; /* packed [Cout_pad][cols]; conv / local attention: k = (r*KW + s)*(C0+C1) + c;
@@ -121,6 +121,7 @@ typedef struct {
     double *stats;      /* NULL or [N][Cout][2]: += per-plane sum / sum of squares of the stored values */
     const float *flow;  /* HOIG_CONV_LOCAL_ATTN only: (N,H,W,2) pixel-unit offsets (x,y) */
     const int *act_table; /* NULL or [Cout] device array of hoigAct codes overriding `act` per output channel */
+    int pad_w;          /* horizontal padding (set equal to pad for square kernels) */
 } hoigConvDesc;
 
 /* Rows / columns of the packed weight matrix for a given problem: rows = Cout padded to 16;
@@ -169,11 +170,29 @@ int hoig_resize_flow(const float *T, int B, int Hi, int Wi, int h, int subtract_
  * hidden (N,h,h,Chid) dtype, w2 [k*k][Chid] f32, b2 [k*k] f32; src/tgt/dst NHWC (N,h,h,C). */
 int hoig_attn_finish(const void *hidden, int64_t ldh, int Chid, const float *w2, const float *b2,
                      const void *src, int64_t lds, const float *flow, const void *tgt, int64_t ldt,
-                     void *dst, int64_t ldd, int dtype, int N, int h, int C, int k, hoigStream_t stream);
+                     void *dst, int64_t ldd, int dtype, int N, int h, int C, int k,
+                     const void *unfold, int64_t ldu, hoigStream_t stream);
+/* extract_attn.py:24-25 for the tensor-core path: out (N,h,h,2*k*k*C), channel t*2C + c = BlockExtractor(tgt,0)
+ * tap t (c < C) | BlockExtractor(src,flow) tap t (c >= C); the k5s5 conv over cat[block_target, block_source]
+ * is then hoig_conv2d with a 1x1 kernel over this tensor, and hoig_attn_finish can read the source taps from
+ * it (`unfold`) instead of re-sampling. */
+int hoig_attn_unfold(const void *src, int64_t lds, const void *tgt, int64_t ldt, const float *flow, void *out,
+                     int64_t ldo, int dtype, int N, int h, int C, int k, hoigStream_t stream);
 /* generator.py:475-478 stn: F.grid_sample(x, grid) bilinear / zeros / align_corners=False;
  * x, dst NHWC (N,h,h,C); grid (N,h,h,2) f32; dst = tgt + sample when tgt != NULL. */
 int hoig_grid_sample(const void *x, int64_t ldx, const float *grid, const void *tgt, int64_t ldt,
                      void *dst, int64_t ldd, int dtype, int N, int h, int C, hoigStream_t stream);
+/* 7x7 convs with few input or output channels (generator.py:99,125,151,223-241) are computed as a 7x1
+ * "vertical taps" implicit GEMM plus a horizontal (un)fold, which cuts the operand traffic 7x:
+ *  - stems:  hoig_hunfold_nchw builds x7[b,y,x, s*C + c] = x[b,c,y,x+s-k/2] (zero outside, channels padded to Cpad)
+ *            straight from the NCHW f32 network input; the stem is then a kx1 conv over x7;
+ *  - heads:  a kx1 conv produces Z[b,y,x, s*G + g] for the G head outputs and hoig_hfold_nchw sums
+ *            y[b,g,y,x] = act_g( sum_s Z[b,y,x+s-k/2, s*G + g] ) into NCHW f32 (exact re-association of the sum).
+ * hoig_hfold_nchw writes up to 4 output tensors: segment i takes channels [seg_c0[i], seg_c0[i]+seg_n[i]). */
+int hoig_hunfold_nchw(const float *src, int B, int C, int H, int W, int k, void *dst, int64_t ldd, int Cpad, int dtype,
+                      hoigStream_t stream);
+int hoig_hfold_nchw(const void *z, int64_t ldz, int dtype, int B, int H, int W, int G, int k, const int *act_table,
+                    int nseg, float *const *outs, const int *seg_c0, const int *seg_n, hoigStream_t stream);
 /* models/trainer.py:400-401: img = m_bg*bg + (1-m_bg)*(obj*m_hand + hand*(1-m_hand)); NCHW f32, 3 channels. */
 int hoig_composite(const float *img_bg, const float *obj, const float *hand, const float *mask_bg,
                    const float *mask_hand, float *out, int B, int HW, hoigStream_t stream);

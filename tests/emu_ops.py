@@ -43,7 +43,7 @@ def unpack_transposed(wp, cout, kh, kw, cin_p, pad):
     return w
 
 
-def conv2d(x0, weight, out, *, kh, kw, stride=1, pad=0, mode=0, x1=None, bias=None, act=0, residual=None, stats=None,
+def conv2d(x0, weight, out, *, kh, kw, stride=1, pad=0, pad_w=None, mode=0, x1=None, bias=None, act=0, residual=None, stats=None,
            flow=None, cout=None, simt=False, act_table=None):
     x = x0 if x1 is None else torch.cat([x0, x1], 3)
     cin_p = x.shape[3]
@@ -55,7 +55,7 @@ def conv2d(x0, weight, out, *, kh, kw, stride=1, pad=0, mode=0, x1=None, bias=No
     else:
         w = unpack_weight(weight, cout, kh, kw, cin_p)
     if mode == real_ops.CONV:
-        y = F.conv2d(xn, w, None, stride=stride, padding=pad)
+        y = F.conv2d(xn, w, None, stride=stride, padding=(pad, pad if pad_w is None else pad_w))
     elif mode == real_ops.CONV_TRANSPOSED:
         pass
     else:
@@ -130,10 +130,29 @@ def resize_flow(T, h, subtract_identity=True):
     return t.contiguous()
 
 
-def attn_finish(hidden, w2, b2, src, flow, tgt, out, k):
+def attn_unfold(src, tgt, flow, out, k):
+    n, h, _, c = src.shape
+    fl = flow.permute(0, 3, 1, 2)
+    bs = gr.block_extract(src.float().permute(0, 3, 1, 2), fl, k)                       # (N,C,kh,kh)
+    bt = gr.block_extract(tgt.float().permute(0, 3, 1, 2), torch.zeros_like(fl), k)
+
+    def taps(b):   # -> (N,h,h,k*k,C): tap t = (ky,kx) of pixel (y,x) sits at block position (k*y+ky, k*x+kx)
+        return b.reshape(n, c, h, k, h, k).permute(0, 2, 4, 3, 5, 1).reshape(n, h, h, k * k, c)
+
+    u = torch.cat([taps(bt), taps(bs)], 4).reshape(n, h, h, k * k * 2 * c)
+    out.copy_(u.to(out.dtype))
+    return out
+
+
+def attn_finish(hidden, w2, b2, src, flow, tgt, out, k, unfold=None):
     n, h, _, c = src.shape
     logits = hidden.float() @ w2.t() + b2                      # (N,h,h,k*k)
     a = F.softmax(logits, 3).permute(0, 3, 1, 2)
+    if unfold is not None:
+        bsu = unfold.float().reshape(n, h, h, k * k, 2 * c)[..., c:]                   # (N,h,h,kk,C)
+        res = (a.permute(0, 2, 3, 1)[..., None] * bsu).sum(3) / (k * k)
+        out.copy_((tgt.float() + res).to(out.dtype))
+        return out
     bs = gr.block_extract(src.float().permute(0, 3, 1, 2), flow.permute(0, 3, 1, 2), k)
     res = F.avg_pool2d(gr.local_attn_reshape(a, k) * bs, k, k).permute(0, 2, 3, 1)
     out.copy_((tgt.float() + res).to(out.dtype))
@@ -147,6 +166,26 @@ def grid_sample(x, grid, out, tgt=None):
         y = y + tgt.float()
     out.copy_(y.to(out.dtype))
     return out
+
+
+def hunfold_nchw(x, out, k):
+    b, c, h, w = x.shape
+    xp = F.pad(x, (k // 2, k // 2))
+    cols = torch.stack([xp[..., s:s + w] for s in range(k)], 1).reshape(b, k * c, h, w)   # channel s*C + c
+    out.zero_()
+    out[..., : k * c] = cols.permute(0, 2, 3, 1).to(out.dtype)
+    return out
+
+
+def hfold_nchw(z, groups, k, segments, act_table=None):
+    b, h, w, _ = z.shape
+    zz = z.float()[..., : k * groups].reshape(b, h, w, k, groups)
+    zp = F.pad(zz, (0, 0, 0, 0, k // 2, k // 2))                 # pad W
+    y = sum(zp[:, :, s:s + w, s] for s in range(k))               # y[x] = sum_s Z[x + s - k//2, s]
+    if act_table is not None:
+        y = torch.stack([ACT[int(a)](y[..., i]) for i, a in enumerate(act_table.tolist())], -1)
+    y = y.permute(0, 3, 1, 2)
+    return [y[:, c0:c0 + n].contiguous() for c0, n in segments]
 
 
 def composite(img_bg, obj, hand, mask_bg, mask_hand):
@@ -165,7 +204,7 @@ def install(monkeypatch):
         if k.isupper():
             setattr(emu, k, getattr(real_ops, k))
     for name in ("conv2d", "nchw_to_nhwc", "nhwc_to_nchw", "seg_resize", "plane_stats", "instnorm_apply", "resize_flow",
-                 "attn_finish", "grid_sample", "composite"):
+                 "attn_finish", "attn_unfold", "grid_sample", "composite", "hunfold_nchw", "hfold_nchw"):
         setattr(emu, name, globals()[name])
     monkeypatch.setattr(G, "ops", emu)
     return emu

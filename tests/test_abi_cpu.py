@@ -48,7 +48,7 @@ def test_argument_validation_without_gpu(lib):
     assert lib.hoig_conv2d(None, None) == -1
     assert lib.hoig_rasterize_fim_wim(None, 1, 1, 64, 0.1, 100.0, 1, None, None, None, None, 0, None) == -1
     # hidden, ldh, Chid, w2, b2, src, lds, flow, tgt, ldt, dst, ldd, dtype, N, h, C, k, stream
-    assert lib.hoig_attn_finish(None, 0, 128, None, None, None, 0, None, None, 0, None, 0, 1, 1, 8, 8, 5, None) == -1
+    assert lib.hoig_attn_finish(None, 0, 128, None, None, None, 0, None, None, 0, None, 0, 1, 1, 8, 8, 5, None, 0, None) == -1
     r, c = ctypes.c_int(), ctypes.c_int()
     lib.hoig_conv_packed_dims(0, 3, 7, 7, 64, 1, 3, ctypes.byref(r), ctypes.byref(c))
     assert (r.value, c.value) == (16, 3136)

@@ -139,6 +139,36 @@ def test_resize_flow_and_warp_ops():
     assert (out.cpu() - emu_ops.composite(*imgs)).abs().max().item() <= 1e-6
 
 
+def test_fold_and_unfold_ops():
+    g = torch.Generator().manual_seed(5)
+    x = _rand(g, 2, 8, 16, 24)
+    for dtype in (torch.float32, torch.bfloat16):
+        a = ops.hunfold_nchw(x.cuda(), torch.empty(2, 16, 24, 64, dtype=dtype, device="cuda"), 7)
+        b = emu_ops.hunfold_nchw(x, torch.empty(2, 16, 24, 64, dtype=dtype), 7)
+        assert torch.equal(a.cpu(), b)
+        z = _rand(g, 2, 16, 24, 56).to(dtype)
+        table = torch.tensor([3, 3, 3, 4, 4, 3, 3, 3], dtype=torch.int32)
+        segs = [(0, 3), (3, 1), (4, 1), (5, 3)]
+        outs = ops.hfold_nchw(z.cuda(), 8, 7, segs, table.cuda())
+        refs = emu_ops.hfold_nchw(z, 8, 7, segs, table)
+        for o, r in zip(outs, refs):
+            assert o.shape == r.shape and (o.cpu() - r).abs().max().item() <= 2e-6
+        C, h = 32, 16
+        src, tgt = _rand(g, 2, h, h, C).to(dtype), _rand(g, 2, h, h, C).to(dtype)
+        flow = _rand(g, 2, h, h, 2, scale=3.0)
+        u = ops.attn_unfold(src.cuda(), tgt.cuda(), flow.cuda(), torch.empty(2, h, h, 50 * C, dtype=dtype, device="cuda"), 5)
+        ur = emu_ops.attn_unfold(src, tgt, flow, torch.empty(2, h, h, 50 * C, dtype=dtype), 5)
+        tol = 2e-6 if dtype == torch.float32 else 1.6e-2
+        assert (u.cpu().float() - ur.float()).abs().max().item() <= tol
+        hidden = _rand(g, 2, h, h, 128).to(dtype)
+        w2, b2 = _rand(g, 25, 128, scale=0.2), _rand(g, 25)
+        o = ops.attn_finish(hidden.cuda(), w2.cuda(), b2.cuda(), src.cuda(), flow.cuda(), tgt.cuda(),
+                            torch.empty(2, h, h, C, dtype=dtype, device="cuda"), 5, unfold=u)
+        r = emu_ops.attn_finish(hidden, w2, b2, src, flow, tgt, torch.empty(2, h, h, C, dtype=dtype), 5, unfold=ur)
+        ok, _ = _report(f"attn_finish(unfold) {dtype}", o, r, 2e-5 if dtype == torch.float32 else 3e-2, 3e-2)
+        assert ok
+
+
 # --------------------------------------------------------------------------- convolution
 CONV_CASES = [
     # name, N, H, Cin, Cout, k, stride, mode, extras
@@ -157,6 +187,9 @@ CONV_CASES = [
     ("7x7_head_c64_n3_tanh", 1, 32, 64, 3, 7, 1, "conv", dict(act=3)),
     ("7x7_head_c128_n1_sigmoid", 1, 32, 128, 1, 7, 1, "conv", dict(act=4)),
     ("1x1", 2, 16, 64, 32, 1, 1, "conv", dict(bias=True)),
+    ("1x1_k3200_attn_gemm", 1, 16, 3200, 128, 1, 1, "conv", dict(bias=True, act=2)),
+    ("7x1_stem_c64", 2, 32, 64, 64, 7, 1, "conv", dict(stats=True, kw=1)),
+    ("7x1_heads_c128_n56", 1, 32, 128, 56, 7, 1, "conv", dict(kw=1)),
     ("3x3_tiny_8x8", 2, 8, 32, 32, 3, 1, "conv", dict(stats=True)),
     ("convT_3x3_s2", 2, 16, 128, 64, 3, 2, "convT", dict(stats=True)),
     ("convT_3x3_s2_small", 1, 8, 32, 16, 3, 2, "convT", dict(stats=True)),
@@ -170,6 +203,8 @@ def _run_conv(case, dtype, simt=False):
     name, N, H, Cin, Cout, k, stride, mode, ex = case
     g = torch.Generator().manual_seed(hash(name) % 1000)
     pad = k // 2
+    kw_ = ex.get("kw", k)
+    padw = kw_ // 2
     if mode == "attn":
         tgt, src = _rand(g, N, H, H, Cin).to(dtype), _rand(g, N, H, H, Cin).to(dtype)
         flow = _rand(g, N, H, H, 2, scale=3.0)
@@ -183,13 +218,15 @@ def _run_conv(case, dtype, simt=False):
         # exercise the channel-slice view (ld > C) on the input
         buf = _rand(g, N, H, H, Cin + 8).to(dtype)
         x0, x1, flow = buf[..., :Cin], None, None
-        w = _rand(g, Cout, Cin, k, k, scale=0.05)
+        w = _rand(g, Cout, Cin, k, kw_, scale=0.05)
         OH, m, pad_ = (H + 2 * pad - k) // stride + 1, ops.CONV, pad
     wp = pack_conv_weight(w, dtype, transposed=(mode == "convT"))
     bias = _rand(g, Cout) if ex.get("bias") else None
     Cst = ceil_to(Cout, 8)
     res = _rand(g, N, OH, OH, Cst).to(dtype) if ex.get("residual") else None
-    kw = dict(kh=k, kw=k, stride=stride, pad=pad_, mode=m, act=ex.get("act", 0), cout=Cout)
+    kw = dict(kh=k, kw=kw_ if mode == "conv" else k, stride=stride, pad=pad_, mode=m, act=ex.get("act", 0), cout=Cout)
+    if mode == "conv":
+        kw["pad_w"] = padw
     table = torch.tensor(ex["act_table"], dtype=torch.int32) if ex.get("act_table") else None
     st_ref = torch.zeros(N * Cout * 2, dtype=torch.float64) if ex.get("stats") else None
     ref = emu_ops.conv2d(x0, wp, torch.zeros(N, OH, OH, Cst, dtype=dtype), x1=x1, bias=bias, residual=res, stats=st_ref, flow=flow,
