@@ -135,7 +135,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
 
-    from hoig_b200 import _lib, synth
+    from hoig_b200 import _lib, dist_utils, synth
     from hoig_b200.generator import composite, create
 
     B = args.batch
@@ -144,7 +144,7 @@ def run_ours(args):
     g = create("generator_spade_attn", dtype=dtype, **CFG)
     g.init_weights()
     g = g.cuda().eval()
-    host = {k: v.pin_memory() for k, v in synth.generator_inputs(B, seed=100 + rank, size=256).items()}
+    host = {k: v.pin_memory() for k, v in synth.generator_inputs(B, seed=dist_utils.shard_seed(100, rank), size=256).items()}
     dev = {k: v.cuda(non_blocking=True) for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
     out_host = torch.empty(B, 3, 256, 256, dtype=torch.float32).pin_memory()
@@ -194,10 +194,7 @@ def run_ours(args):
     ms_e2e = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+    ms, ms_e2e = dist_utils.reduce_max([ms, ms_e2e], "cuda")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -205,7 +202,7 @@ def run_ours(args):
 
     sustained, burst, hbm, peak_src = _peaks()
     n_img = B * world * args.steps
-    value = n_img / (ms / 1e3)
+    value = dist_utils.throughput(B, world, args.steps, ms)
     conv_n, conv_ms = per_kernel.get("hoig_conv2d", (0, 0.0))
     conv_flops_per_launch = GFLOP_PER_IMAGE * 1e9 * B * args.steps / max(conv_n, 1)
     achieved = conv_flops_per_launch / (conv_ms / max(conv_n, 1) / 1e3) / 1e12 if conv_ms > 0 else 0.0

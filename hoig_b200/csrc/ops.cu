@@ -98,7 +98,7 @@ __global__ void plane_stats_kernel(const T *__restrict__ x, int64_t ldx, int HW,
 
 // grid (slabs, N).  mean / rstd of the C planes of image n are rebuilt in smem per CTA.
 template <typename T>
-__global__ void instnorm_apply_kernel(const T *__restrict__ x, int64_t ldx, const double *__restrict__ stats,
+__global__ void __launch_bounds__(256, 4) instnorm_apply_kernel(const T *__restrict__ x, int64_t ldx, const double *__restrict__ stats,
                                       const float *__restrict__ gamma, const float *__restrict__ beta,
                                       const T *__restrict__ gb, int64_t ldgb, const T *__restrict__ res, int64_t ldr,
                                       int relu, T *__restrict__ dst, int64_t ldd, int HW, int C, int pix_per_block, float eps)
@@ -120,31 +120,46 @@ __global__ void instnorm_apply_kernel(const T *__restrict__ x, int64_t ldx, cons
     __syncthreads();
     const int chunks = C / 8;
     const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
-    for (int i = threadIdx.x; i < (p1 - p0) * chunks; i += blockDim.x) {
-        const int cc = i % chunks, p = p0 + i / chunks;
-        const int64_t row = (int64_t)n * HW + p;
-        float v[8];
-        load8(x + row * ldx + cc * 8, v);
+    const int total = (p1 - p0) * chunks;
+    constexpr int U = 2;   // independent 16-byte loads in flight per thread
+    for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * U) {
+        float v[U][8], r[U][8];
+        int cc[U];
+        int64_t row[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j] - meanv[cc * 8 + j], scale[cc * 8 + j], shift[cc * 8 + j]);
-        if (gb) {  // spade.py:36  normalized * (1 + gamma) + beta
-            float g[8], b[8];
-            load8(gb + row * ldgb + cc * 8, g);
-            load8(gb + row * ldgb + C + cc * 8, b);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], 1.f + g[j], b[j]);
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * blockDim.x;
+            const int ii = i < total ? i : i0;
+            cc[u] = ii % chunks;
+            row[u] = (int64_t)n * HW + p0 + ii / chunks;
+            load8(x + row[u] * ldx + cc[u] * 8, v[u]);
         }
         if (res) {
-            float r[8];
-            load8(res + row * ldr + cc * 8, r);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += r[j];
+            for (int u = 0; u < U; ++u) load8(res + row[u] * ldr + cc[u] * 8, r[u]);
         }
-        if (relu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        for (int u = 0; u < U; ++u) {
+            const int c8 = cc[u] * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[u][j] = fmaf(v[u][j] - meanv[c8 + j], scale[c8 + j], shift[c8 + j]);
+            if (gb) {  // spade.py:36  normalized * (1 + gamma) + beta
+                float g[8], b[8];
+                load8(gb + row[u] * ldgb + c8, g);
+                load8(gb + row[u] * ldgb + C + c8, b);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[u][j] = fmaf(v[u][j], 1.f + g[j], b[j]);
+            }
+            if (res) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[u][j] += r[u][j];
+            }
+            if (relu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[u][j] = fmaxf(v[u][j], 0.f);
+            }
+            if (i0 + u * (int)blockDim.x < total) store8(dst + row[u] * ldd + c8, v[u]);
         }
-        store8(dst + row * ldd + cc * 8, v);
     }
 }
 
@@ -396,21 +411,22 @@ attn_unfold_kernel(const T *__restrict__ src, int64_t lds, const T *__restrict__
 template <typename T>
 __global__ void hunfold_kernel(const float *__restrict__ src, int B, int C, int H, int W, int k, T *__restrict__ dst, int64_t ldd, int Cpad)
 {
-    const int chunks = Cpad / 8;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)B * H * W * chunks) return;
-    const int ch = (int)(i % chunks);
-    const int64_t bp = i / chunks;
+    // one thread per pixel: loads are coalesced along x (consecutive lanes = consecutive pixels of a row)
+    const int64_t bp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (bp >= (int64_t)B * H * W) return;
     const int x = (int)(bp % W), y = (int)((bp / W) % H), b = (int)(bp / ((int64_t)W * H));
-    float v[8];
+    const float *row = src + ((int64_t)b * C * H + y) * W;
+    for (int ch = 0; ch < Cpad / 8; ++ch) {
+        float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int kc = ch * 8 + j;
-        const int s = kc / C, c = kc - s * C;
-        const int xx = x + s - k / 2;
-        v[j] = (s < k && xx >= 0 && xx < W) ? src[(((int64_t)b * C + c) * H + y) * W + xx] : 0.f;
+        for (int j = 0; j < 8; ++j) {
+            const int kc = ch * 8 + j;
+            const int s = kc / C, c = kc - s * C;
+            const int xx = x + s - k / 2;
+            v[j] = (s < k && xx >= 0 && xx < W) ? __ldg(row + (int64_t)c * H * W + xx) : 0.f;
+        }
+        store8(dst + bp * ldd + ch * 8, v);
     }
-    store8(dst + bp * ldd + ch * 8, v);
 }
 
 struct FoldSegs {
@@ -492,8 +508,8 @@ extern "C" int hoig_seg_resize_nearest(const float *seg, int B, int C, int Hi, i
 
 static int slab_pixels(int HW, int N)
 {
-    // aim for >= 4 CTAs per SM over the (slab, image) grid
-    int slabs = (148 * 4 + N - 1) / N;
+    // aim for >= 8 CTAs per SM over the (slab, image) grid
+    int slabs = (148 * 8 + N - 1) / N;
     if (slabs < 1) slabs = 1;
     int pp = (HW + slabs - 1) / slabs;
     if (pp < 64) pp = 64;
@@ -634,7 +650,7 @@ extern "C" int hoig_hunfold_nchw(const float *src, int B, int C, int H, int W, i
                                  hoigStream_t stream)
 {
     HOIG_REQUIRE(src && dst && k >= 1 && (k & 1) && Cpad % 8 == 0 && Cpad >= k * C && ldd >= Cpad && ldd % 8 == 0, "hunfold: bad argument");
-    const int64_t n = (int64_t)B * H * W * (Cpad / 8);
+    const int64_t n = (int64_t)B * H * W;
     if (n == 0) return HOIG_OK;
     return dispatch(dtype, [&](auto *tag) {
         using T = std::remove_pointer_t<decltype(tag)>;
