@@ -60,6 +60,7 @@ _SIGNATURES = {
     "hoig_conv2d": (c_int, [POINTER(ConvDesc), c_void_p]),
     "hoig_conv2d_simt": (c_int, [POINTER(ConvDesc), c_void_p]),
     "hoig_set_umma_gather_only": (None, [c_int]),
+    "hoig_set_rasterizer_band_pixels": (None, [c_int]),
     "hoig_nchw_to_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "hoig_nhwc_to_nchw": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hoig_seg_resize_nearest": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_int,
@@ -141,7 +142,7 @@ class LaunchRecorder:
 
 recorder = LaunchRecorder()
 _NO_LAUNCH = {"hoig_version", "hoig_last_error", "hoig_check_device", "hoig_conv_packed_dims",
-              "hoig_rasterize_workspace_bytes", "hoig_set_umma_gather_only"}
+              "hoig_rasterize_workspace_bytes", "hoig_set_umma_gather_only", "hoig_set_rasterizer_band_pixels"}
 
 
 class _Proxy:

@@ -120,46 +120,76 @@ __global__ void __launch_bounds__(256, 4) instnorm_apply_kernel(const T *__restr
     __syncthreads();
     const int chunks = C / 8;
     const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
-    const int total = (p1 - p0) * chunks;
-    constexpr int U = 2;   // independent 16-byte loads in flight per thread
-    for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * U) {
-        float v[U][8], r[U][8];
-        int cc[U];
-        int64_t row[U];
+    if (blockDim.x % chunks == 0) {
+        // fast path: a thread keeps ONE 8-channel chunk for all its pixels, so the per-channel constants live in
+        // registers and the loop has no index division and no shared-memory traffic
+        const int lanes = blockDim.x / chunks;
+        const int c8 = (threadIdx.x % chunks) * 8, pl = threadIdx.x / chunks;
+        float mu[8], sc[8], sh[8];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * blockDim.x;
-            const int ii = i < total ? i : i0;
-            cc[u] = ii % chunks;
-            row[u] = (int64_t)n * HW + p0 + ii / chunks;
-            load8(x + row[u] * ldx + cc[u] * 8, v[u]);
+        for (int j = 0; j < 8; ++j) { mu[j] = meanv[c8 + j]; sc[j] = scale[c8 + j]; sh[j] = shift[c8 + j]; }
+        constexpr int U = 2;
+        for (int pb = p0 + pl; pb < p1; pb += lanes * U) {
+            float v[U][8];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int p = min(pb + u * lanes, p1 - 1);
+                load8(x + ((int64_t)n * HW + p) * ldx + c8, v[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int p = pb + u * lanes;
+                if (p >= p1) break;
+                const int64_t row = (int64_t)n * HW + p;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[u][j] = fmaf(v[u][j] - mu[j], sc[j], sh[j]);
+                if (gb) {  // spade.py:36  normalized * (1 + gamma) + beta
+                    float g[8], b[8];
+                    load8(gb + row * ldgb + c8, g);
+                    load8(gb + row * ldgb + C + c8, b);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[u][j] = fmaf(v[u][j], 1.f + g[j], b[j]);
+                }
+                if (res) {
+                    float r[8];
+                    load8(res + row * ldr + c8, r);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[u][j] += r[j];
+                }
+                if (relu) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[u][j] = fmaxf(v[u][j], 0.f);
+                }
+                store8(dst + row * ldd + c8, v[u]);
+            }
+        }
+        return;
+    }
+    for (int i = threadIdx.x; i < (p1 - p0) * chunks; i += blockDim.x) {
+        const int cc = i % chunks, p = p0 + i / chunks;
+        const int64_t row = (int64_t)n * HW + p;
+        float v[8];
+        load8(x + row * ldx + cc * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j] - meanv[cc * 8 + j], scale[cc * 8 + j], shift[cc * 8 + j]);
+        if (gb) {
+            float g[8], b[8];
+            load8(gb + row * ldgb + cc * 8, g);
+            load8(gb + row * ldgb + C + cc * 8, b);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], 1.f + g[j], b[j]);
         }
         if (res) {
+            float r[8];
+            load8(res + row * ldr + cc * 8, r);
 #pragma unroll
-            for (int u = 0; u < U; ++u) load8(res + row[u] * ldr + cc[u] * 8, r[u]);
+            for (int j = 0; j < 8; ++j) v[j] += r[j];
         }
+        if (relu) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int c8 = cc[u] * 8;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[u][j] = fmaf(v[u][j] - meanv[c8 + j], scale[c8 + j], shift[c8 + j]);
-            if (gb) {  // spade.py:36  normalized * (1 + gamma) + beta
-                float g[8], b[8];
-                load8(gb + row[u] * ldgb + c8, g);
-                load8(gb + row[u] * ldgb + C + c8, b);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[u][j] = fmaf(v[u][j], 1.f + g[j], b[j]);
-            }
-            if (res) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[u][j] += r[u][j];
-            }
-            if (relu) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[u][j] = fmaxf(v[u][j], 0.f);
-            }
-            if (i0 + u * (int)blockDim.x < total) store8(dst + row[u] * ldd + c8, v[u]);
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
         }
+        store8(dst + row * ldd + cc * 8, v);
     }
 }
 
@@ -508,11 +538,11 @@ extern "C" int hoig_seg_resize_nearest(const float *seg, int B, int C, int Hi, i
 
 static int slab_pixels(int HW, int N)
 {
-    // aim for >= 8 CTAs per SM over the (slab, image) grid
-    int slabs = (148 * 8 + N - 1) / N;
+    // aim for >= 16 CTAs per SM over the (slab, image) grid (4 resident): >= 4 waves keeps the tail small
+    int slabs = (148 * 16 + N - 1) / N;
     if (slabs < 1) slabs = 1;
     int pp = (HW + slabs - 1) / slabs;
-    if (pp < 64) pp = 64;
+    if (pp < 32) pp = 32;
     return pp;
 }
 

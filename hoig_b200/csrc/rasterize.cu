@@ -112,14 +112,157 @@ struct Edges {
     __device__ __forceinline__ float B(int i, float xp) const { return __fmul_rn(__fsub_rn(xp, xa[i]), dy[i]); }
 };
 
-// One CTA per (mesh, band).  Dynamic smem: keys[band_rows*is] (u64) | centre[is] (f32).
-__global__ void __launch_bounds__(kRastThreads, 1)
+struct Window {
+    int row_lo, row_hi, col_lo, col_hi;
+    int tier;   // 0: bounded window (regular / needle), 1: exact monotone search over the band, 2: wild (verbatim tests), -1: skip
+};
+
+__device__ __forceinline__ void make_edges(const float f[9], Edges &e)
+{
+    e.ya[0] = f[1]; e.dx[0] = __fsub_rn(f[3], f[0]); e.xa[0] = f[0]; e.dy[0] = __fsub_rn(f[4], f[1]);
+    e.ya[1] = f[4]; e.dx[1] = __fsub_rn(f[6], f[3]); e.xa[1] = f[3]; e.dy[1] = __fsub_rn(f[7], f[4]);
+    e.ya[2] = f[7]; e.dx[2] = __fsub_rn(f[0], f[6]); e.xa[2] = f[6]; e.dy[2] = __fsub_rn(f[1], f[7]);
+}
+
+// Search window of a front-facing face inside the band [r0, r1].  A pixel that passes the three float edge
+// tests lies within ~3e-5 NDC of each (computed) edge half-plane, hence within  3e-5 / sin(theta_min / 2)  of the
+// vertex bounding box (theta_min = smallest corner angle; derivation in DESIGN.md 3.2).  Faces with
+// theta_min >= ~3 deg get a 1-pixel margin, needles down to ~0.06 deg a (1 + 0.03*is)-pixel margin, anything
+// thinner / larger than 64 NDC searches the whole band with the exact monotone predicate, non-finite or huge
+// coordinates run the reference tests verbatim on every band pixel.
+__device__ __forceinline__ Window classify(const float f[9], const Edges &e, const float *centre, int is, float isf, int r0, int r1)
+{
+    Window w;
+    w.row_lo = r0; w.row_hi = r1; w.col_lo = 0; w.col_hi = is - 1; w.tier = 2;
+    bool wild = false;
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+        if (k % 3 != 2) wild |= !(fabsf(f[k]) <= kWild);  // catches NaN / inf / huge
+    if (wild) return w;
+    const float l0 = e.dx[0] * e.dx[0] + e.dy[0] * e.dy[0];
+    const float l1 = e.dx[1] * e.dx[1] + e.dy[1] * e.dy[1];
+    const float l2 = e.dx[2] * e.dx[2] + e.dy[2] * e.dy[2];
+    const float lmax = fmaxf(l0, fmaxf(l1, l2));
+    const float lmid = fmaxf(fminf(l0, l1), fminf(fmaxf(l0, l1), l2));
+    const float cross = e.dx[0] * e.dy[1] - e.dy[0] * e.dx[1];      // twice the signed area
+    const float sin2 = cross * cross;                                 // = sin^2(theta_min) * lmax * lmid
+    const float ll = lmax * lmid;
+    const float big = fmaxf(fmaxf(fabsf(f[0]), fabsf(f[3])), fmaxf(fmaxf(fabsf(f[6]), fabsf(f[1])), fmaxf(fabsf(f[4]), fabsf(f[7]))));
+    const float tau0 = fmaxf(0.05f, 1.2e-4f * isf);
+    float margin = -1.f;
+    if (big <= 64.f && ll > 1e-30f && cross > 0.f) {
+        if (sin2 >= tau0 * tau0 * ll) margin = 1.f;
+        else if (sin2 >= 1e-6f * ll) margin = 1.f + ceilf(0.03f * isf);
+    }
+    if (margin > 0.f) {
+        const float xmin = fminf(f[0], fminf(f[3], f[6])), xmax = fmaxf(f[0], fmaxf(f[3], f[6]));
+        const float ymin = fminf(f[1], fminf(f[4], f[7])), ymax = fmaxf(f[1], fmaxf(f[4], f[7]));
+        // pixel coordinate of an NDC position: 0.5 * (v * is + is - 1)
+        w.col_lo = max(0, (int)floorf(0.5f * (xmin * isf + isf - 1.f) - margin));
+        w.col_hi = min(is - 1, (int)ceilf(0.5f * (xmax * isf + isf - 1.f) + margin));
+        w.row_lo = max(r0, (int)floorf(0.5f * (ymin * isf + isf - 1.f) - margin));
+        w.row_hi = min(r1, (int)ceilf(0.5f * (ymax * isf + isf - 1.f) + margin));
+        w.tier = (w.row_lo > w.row_hi || w.col_lo > w.col_hi) ? -1 : 0;
+        return w;
+    }
+    // exact band test from the monotone predicate alone (degenerate faces)
+    w.tier = 1;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float bmin = fminf(e.B(i, centre[0]), e.B(i, centre[is - 1]));
+        if (!(fmaxf(e.A(i, centre[r0]), e.A(i, centre[r1])) >= bmin)) w.tier = -1;
+    }
+    return w;
+}
+
+// Scatter one face into the band's key buffer.  Inside the window the passing pixels are decided by the
+// reference's own float predicate (short windows: evaluated directly; wide ones: per-row binary search on it).
+__device__ __forceinline__ void scatter_face(const float f[9], const Edges &e, Window w, int fn, const float *centre,
+                                             unsigned long long *keys, int is, float isf, int r0, int r1, float near_, float far_)
+{
+    if (w.tier == 1) {   // exact row range by binary search on the monotone row predicate
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float bmin = fminf(e.B(i, centre[0]), e.B(i, centre[is - 1]));
+            if (e.dx[i] >= 0.f) w.row_lo = max(w.row_lo, first_true(r0, r1, [&](int y) { return e.A(i, centre[y]) >= bmin; }));
+            else                w.row_hi = min(w.row_hi, first_true(r0, r1, [&](int y) { return !(e.A(i, centre[y]) >= bmin); }) - 1);
+        }
+        if (w.row_lo > w.row_hi) return;
+    }
+    float fi[9];
+    face_inverse(f, isf, fi);
+    const bool direct = w.tier == 2 || (w.col_hi - w.col_lo) < 8;
+    for (int y = w.row_lo; y <= w.row_hi; ++y) {
+        const float yp = centre[y];
+        const float a0 = e.A(0, yp), a1 = e.A(1, yp), a2 = e.A(2, yp);
+        int c_lo = w.col_lo, c_hi = w.col_hi;
+        if (!direct) {
+            const float a[3] = {a0, a1, a2};
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                if (e.dy[i] >= 0.f)  // B non-decreasing in x: pass set {B <= a} is a prefix
+                    c_hi = min(c_hi, first_true(w.col_lo, w.col_hi, [&](int x) { return a[i] < e.B(i, centre[x]); }) - 1);
+                else                 // B non-increasing: pass set is a suffix
+                    c_lo = max(c_lo, first_true(w.col_lo, w.col_hi, [&](int x) { return !(a[i] < e.B(i, centre[x])); }));
+            }
+        }
+        for (int x = c_lo; x <= c_hi; ++x) {
+            if (direct) {  // rasterize_cuda_kernel.cu:132-135 verbatim (NaN compares false => passes)
+                const float xp = centre[x];
+                if ((a0 < e.B(0, xp)) || (a1 < e.B(1, xp)) || (a2 < e.B(2, xp))) continue;
+            }
+            float wgt[3], zp;
+            if (!shade(f, fi, (float)x, (float)y, near_, far_, wgt, zp)) continue;
+            const unsigned long long key = ((unsigned long long)ordered_bits(zp) << 32) | (uint32_t)fn;
+            atomicMin(&keys[(size_t)(y - r0) * is + x], key);
+        }
+    }
+}
+
+constexpr int kListCap = 6144;   // compacted in-band faces per CTA (overflow is processed in place)
+
+// Pre-pass (used when a workspace is supplied): every face is culled and classified ONCE per mesh and a packed
+// (band << 24 | face) entry is appended to the mesh's bin for each band its window touches, so the raster CTAs
+// no longer re-visit all F faces per band.  bins: per mesh [count | entries[cap]].
+__global__ void __launch_bounds__(256)
+rast_bin_kernel(const float *__restrict__ faces, int F, int is, int band_rows, int n_bands, uint32_t *__restrict__ bins, int cap)
+{
+    __shared__ float centre_s[2048];
+    for (int i = threadIdx.x; i < is; i += blockDim.x) centre_s[i] = (float)((2. * i + 1 - is) / is);
+    __syncthreads();
+    const int mesh = blockIdx.y;
+    const int fn = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fn >= F) return;
+    const float *fp = faces + ((size_t)mesh * F + fn) * 9;
+    float f[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) f[k] = __ldg(fp + k);
+    if (back_facing(f)) return;
+    Edges e;
+    make_edges(f, e);
+    const Window w = classify(f, e, centre_s, is, (float)is, 0, is - 1);
+    if (w.tier < 0) return;
+    uint32_t *bin = bins + (size_t)mesh * (cap + 1);
+    const int b0 = w.row_lo / band_rows, b1 = w.row_hi / band_rows;   // tiers 1/2 span every band; the raster CTA re-tests exactly
+    for (int b = b0; b <= b1; ++b) {
+        const uint32_t slot = atomicAdd(bin, 1u);
+        if (slot < (uint32_t)cap) bin[1 + slot] = ((uint32_t)b << 24) | (uint32_t)fn;
+    }
+}
+
+// One CTA per (mesh, band).  Dynamic smem: keys[band_rows*is] (u64) | centre[is] (f32) | list[kListCap] (i32).
+// Phase A culls / classifies every face and compacts the in-band survivors into a shared list so that phase B
+// runs with (nearly) full warps; phase C decodes the keys.
+__global__ void __launch_bounds__(kRastThreads)
 rasterize_kernel(const float *__restrict__ faces, int F, int is, int band_rows, int n_bands, float near_, float far_,
-                 int flip_y, int32_t *__restrict__ fim, float *__restrict__ wim, float *__restrict__ depth)
+                 int flip_y, int32_t *__restrict__ fim, float *__restrict__ wim, float *__restrict__ depth,
+                 const uint32_t *__restrict__ bins, int cap)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
     float *centre = reinterpret_cast<float *>(keys + (size_t)band_rows * is);
+    int *list = reinterpret_cast<int *>(centre + is);
+    __shared__ int list_n;
 
     const int mesh = blockIdx.x / n_bands;
     const int band = blockIdx.x % n_bands;
@@ -131,109 +274,82 @@ rasterize_kernel(const float *__restrict__ faces, int F, int is, int band_rows, 
     for (int i = threadIdx.x; i < npix; i += blockDim.x) keys[i] = kEmptyKey;
     // rasterize_cuda_kernel.cu:113-114: pixel centre in f64, rounded once
     for (int i = threadIdx.x; i < is; i += blockDim.x) centre[i] = (float)((2. * i + 1 - is) / is);
+    if (threadIdx.x == 0) list_n = 0;
     __syncthreads();
 
     const float *mf = faces + (size_t)mesh * F * 9;
-    for (int fn = threadIdx.x; fn < F; fn += blockDim.x) {
-        float f[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) f[k] = __ldg(mf + (size_t)fn * 9 + k);
-        if (back_facing(f)) continue;
-
-        bool wild = false;
-#pragma unroll
-        for (int k = 0; k < 9; ++k)
-            if (k % 3 != 2) wild |= !(fabsf(f[k]) <= kWild);  // catches NaN / inf / huge
-
-        float fi[9];
-        Edges e;
-        e.ya[0] = f[1]; e.dx[0] = __fsub_rn(f[3], f[0]); e.xa[0] = f[0]; e.dy[0] = __fsub_rn(f[4], f[1]);
-        e.ya[1] = f[4]; e.dx[1] = __fsub_rn(f[6], f[3]); e.xa[1] = f[3]; e.dy[1] = __fsub_rn(f[7], f[4]);
-        e.ya[2] = f[7]; e.dx[2] = __fsub_rn(f[0], f[6]); e.xa[2] = f[6]; e.dy[2] = __fsub_rn(f[1], f[7]);
-
-        // Search window.  A pixel that passes the three float edge tests lies within ~3e-5 NDC of each
-        // (computed) edge half-plane, hence within  3e-5 / sin(theta_min / 2)  of the vertex bounding box
-        // (theta_min = smallest corner angle; derivation in DESIGN.md "rasterizer exactness").  Faces with
-        // theta_min >= ~3 deg get a 1-pixel margin, needles down to ~0.06 deg a (1 + 0.03*is)-pixel margin,
-        // anything thinner / larger than 64 NDC / non-finite searches the whole band.  Inside the window the
-        // passing columns of every row are still found EXACTLY by binary search on the reference predicate.
-        int row_lo = r0, row_hi = r1, col_lo = 0, col_hi = is - 1;
-        if (!wild) {
-            const float l0 = e.dx[0] * e.dx[0] + e.dy[0] * e.dy[0];
-            const float l1 = e.dx[1] * e.dx[1] + e.dy[1] * e.dy[1];
-            const float l2 = e.dx[2] * e.dx[2] + e.dy[2] * e.dy[2];
-            const float lmax = fmaxf(l0, fmaxf(l1, l2));
-            const float lmid = fmaxf(fminf(l0, l1), fminf(fmaxf(l0, l1), l2));
-            const float cross = e.dx[0] * e.dy[1] - e.dy[0] * e.dx[1];      // twice the signed area
-            const float sin2 = cross * cross;                                 // = sin^2(theta) * l_a * l_b at each corner
-            const float ll = lmax * lmid;
-            const float big = fmaxf(fmaxf(fabsf(f[0]), fabsf(f[3])), fmaxf(fmaxf(fabsf(f[6]), fabsf(f[1])), fmaxf(fabsf(f[4]), fabsf(f[7]))));
-            const float tau0 = fmaxf(0.05f, 1.2e-4f * isf);
-            float margin = -1.f;
-            if (big <= 64.f && ll > 1e-30f && cross > 0.f) {
-                if (sin2 >= tau0 * tau0 * ll) margin = 1.f;
-                else if (sin2 >= 1e-6f * ll) margin = 1.f + ceilf(0.03f * isf);
+    // Loops below are written warp-synchronously (no `continue`, __syncwarp at the end of every trip): with
+    // independent thread scheduling an early `continue` lets lanes run ahead into their next face and the warp
+    // never reconverges (measured: 4 of 32 lanes active per issued instruction).
+    // ---- phase A: compact this band's faces -- from the mesh's bin when the pre-pass ran (and did not overflow) ...
+    const uint32_t *bin = bins ? bins + (size_t)mesh * (cap + 1) : nullptr;
+    const uint32_t n_bin = bin ? bin[0] : 0u;
+    const bool use_bin = bin && n_bin <= (uint32_t)cap;
+    if (use_bin) {
+        for (uint32_t base = 0; base < n_bin; base += blockDim.x) {
+            const uint32_t i = base + threadIdx.x;
+            const uint32_t ent = i < n_bin ? __ldg(bin + 1 + i) : 0xffffffffu;
+            int fn = -1;
+            if (i < n_bin && (int)(ent >> 24) == band) {
+                fn = (int)(ent & 0xffffffu);
+                const int slot = atomicAdd(&list_n, 1);
+                if (slot < kListCap) { list[slot] = fn; fn = -1; }
             }
-            if (margin > 0.f) {
-                const float xmin = fminf(f[0], fminf(f[3], f[6])), xmax = fmaxf(f[0], fmaxf(f[3], f[6]));
-                const float ymin = fminf(f[1], fminf(f[4], f[7])), ymax = fmaxf(f[1], fmaxf(f[4], f[7]));
-                // pixel coordinate of an NDC position: 0.5 * (v * is + is - 1)
-                col_lo = max(0, (int)floorf(0.5f * (xmin * isf + isf - 1.f) - margin));
-                col_hi = min(is - 1, (int)ceilf(0.5f * (xmax * isf + isf - 1.f) + margin));
-                row_lo = max(r0, (int)floorf(0.5f * (ymin * isf + isf - 1.f) - margin));
-                row_hi = min(r1, (int)ceilf(0.5f * (ymax * isf + isf - 1.f) + margin));
-                if (row_lo > row_hi || col_lo > col_hi) continue;
-            } else {
-                // exact band test / row range from the monotone predicate alone (degenerate faces)
+            if (fn >= 0) {   // list full: do it now
+                float f[9];
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const float bmin = fminf(e.B(i, centre[0]), e.B(i, centre[is - 1]));
-                    if (!(fmaxf(e.A(i, centre[r0]), e.A(i, centre[r1])) >= bmin)) { row_lo = 1; row_hi = 0; }
-                }
-                if (row_lo > row_hi) continue;
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const float bmin = fminf(e.B(i, centre[0]), e.B(i, centre[is - 1]));
-                    if (e.dx[i] >= 0.f) {  // A non-decreasing in y: passing rows are a suffix
-                        row_lo = max(row_lo, first_true(r0, r1, [&](int y) { return e.A(i, centre[y]) >= bmin; }));
-                    } else {               // A non-increasing: passing rows are a prefix
-                        row_hi = min(row_hi, first_true(r0, r1, [&](int y) { return !(e.A(i, centre[y]) >= bmin); }) - 1);
-                    }
-                }
-                if (row_lo > row_hi) continue;
+                for (int k = 0; k < 9; ++k) f[k] = __ldg(mf + (size_t)fn * 9 + k);
+                Edges e;
+                make_edges(f, e);
+                const Window w = classify(f, e, centre, is, isf, r0, r1);
+                if (w.tier >= 0) scatter_face(f, e, w, fn, centre, keys, is, isf, r0, r1, near_, far_);
             }
+            __syncwarp();
         }
-        face_inverse(f, isf, fi);
-
-        for (int y = row_lo; y <= row_hi; ++y) {
-            const float yp = centre[y];
-            int c_lo = col_lo, c_hi = col_hi;
-            if (!wild) {
+    } else {
+        // ... or by culling / classifying every face of the mesh here
+        for (int base = 0; base < F; base += blockDim.x) {
+            const int fn = base + threadIdx.x;
+            float f[9];
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const float a = e.A(i, yp);
-                    if (e.dy[i] >= 0.f) {  // B non-decreasing in x: pass set {B <= a} is a prefix
-                        c_hi = min(c_hi, first_true(col_lo, col_hi, [&](int x) { return a < e.B(i, centre[x]); }) - 1);
-                    } else {               // B non-increasing: pass set is a suffix
-                        c_lo = max(c_lo, first_true(col_lo, col_hi, [&](int x) { return !(a < e.B(i, centre[x])); }));
-                    }
-                }
+            for (int k = 0; k < 9; ++k) f[k] = fn < F ? __ldg(mf + (size_t)fn * 9 + k) : 0.f;
+            Window w;
+            w.tier = -1;
+            Edges e;
+            if (fn < F && !back_facing(f)) {
+                make_edges(f, e);
+                w = classify(f, e, centre, is, isf, r0, r1);
             }
-            for (int x = c_lo; x <= c_hi; ++x) {
-                if (wild) {  // rasterize_cuda_kernel.cu:132-135 verbatim (NaN compares false => passes)
-                    const float xp = centre[x];
-                    if ((e.A(0, yp) < e.B(0, xp)) || (e.A(1, yp) < e.B(1, xp)) || (e.A(2, yp) < e.B(2, xp))) continue;
-                }
-                float w[3], zp;
-                if (!shade(f, fi, (float)x, (float)y, near_, far_, w, zp)) continue;
-                const unsigned long long key = ((unsigned long long)ordered_bits(zp) << 32) | (uint32_t)fn;
-                atomicMin(&keys[(size_t)(y - r0) * is + x], key);
+            bool overflow = false;
+            if (w.tier >= 0) {
+                const int slot = atomicAdd(&list_n, 1);
+                if (slot < kListCap) list[slot] = fn;
+                else overflow = true;
             }
+            if (overflow) scatter_face(f, e, w, fn, centre, keys, is, isf, r0, r1, near_, far_);
+            __syncwarp();
         }
     }
     __syncthreads();
+    // ---- phase B: scatter the compacted faces
+    const int n_list = min(list_n, kListCap);
+    for (int base = 0; base < n_list; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        if (i < n_list) {
+            const int fn = list[i];
+            float f[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) f[k] = __ldg(mf + (size_t)fn * 9 + k);
+            Edges e;
+            make_edges(f, e);
+            const Window w = classify(f, e, centre, is, isf, r0, r1);
+            if (w.tier >= 0) scatter_face(f, e, w, fn, centre, keys, is, isf, r0, r1, near_, far_);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
 
-    // resolve: keys -> fim / wim / depth  (rasterize_cuda_kernel.cu:174-179, rasterize.py:50-52,335-338)
+    // ---- phase C: keys -> fim / wim / depth  (rasterize_cuda_kernel.cu:174-179, rasterize.py:50-52,335-338)
     for (int i = threadIdx.x; i < npix; i += blockDim.x) {
         const int y = r0 + i / is, x = i % is;
         const unsigned long long key = keys[i];
@@ -368,29 +484,47 @@ __global__ void erode_kernel(const float *__restrict__ in, float *__restrict__ o
 
 using namespace hoig;
 
-extern "C" size_t hoig_rasterize_workspace_bytes(int, int, int) { return 0; }  // z-buffer lives in shared memory
+static int g_band_pixels = 8192;   // 32 rows at 256 px: two CTAs per SM measured best (profiles/)
+// Tuning hook: pixels per band (<= 16384, the 128 KB key buffer); smaller bands -> more CTAs per SM, more face re-visits.
+extern "C" void hoig_set_rasterizer_band_pixels(int n) { g_band_pixels = n < 256 ? 256 : (n > kMaxBandPixels ? kMaxBandPixels : n); }
+
+static inline int bin_cap(int F) { return 2 * F + 1024; }
+// Optional workspace for the binning pre-pass: per mesh a counter and 2F+1024 packed (band, face) entries.
+// Without it (NULL / too small) every band CTA scans all faces itself.
+extern "C" size_t hoig_rasterize_workspace_bytes(int B, int F, int) { return (size_t)B * (bin_cap(F) + 1) * sizeof(uint32_t); }  // z-buffer lives in shared memory
 
 extern "C" int hoig_rasterize_fim_wim(const float *faces, int B, int F, int image_size, float near_, float far_,
-                                      int flip_y, int32_t *fim, float *wim, float *depth, void *, size_t,
+                                      int flip_y, int32_t *fim, float *wim, float *depth, void *workspace, size_t workspace_bytes,
                                       hoigStream_t stream)
 {
     HOIG_REQUIRE(B >= 0 && F >= 0 && image_size >= 1 && image_size <= 2048, "rasterize: bad shape B=%d F=%d is=%d", B, F, image_size);
     if (B == 0) return HOIG_OK;
     HOIG_REQUIRE((faces || F == 0) && fim && wim, "rasterize: null pointer");
     const int is = image_size;
-    int band_rows = kMaxBandPixels / is;
+    int band_rows = g_band_pixels / is;
     if (band_rows > is) band_rows = is;
     HOIG_REQUIRE(band_rows >= 1, "rasterize: image too wide");
     const int n_bands = ceil_div(is, band_rows);
-    const size_t smem = (size_t)band_rows * is * sizeof(unsigned long long) + (size_t)is * sizeof(float);
+    const size_t smem = (size_t)band_rows * is * sizeof(unsigned long long) + (size_t)is * sizeof(float) + (size_t)kListCap * sizeof(int);
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(rasterize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
             return check_launch("rasterize smem attribute");
         attr_set = true;
     }
+    uint32_t *bins = nullptr;
+    const int cap = bin_cap(F);
+    if (workspace && workspace_bytes >= hoig_rasterize_workspace_bytes(B, F, is) && F > 0 && F < (1 << 24) && n_bands <= 256 && B <= 65535) {
+        bins = static_cast<uint32_t *>(workspace);
+        // zero the per-mesh counters (strided): one 2-D memset
+        if (cudaMemset2DAsync(bins, (size_t)(cap + 1) * sizeof(uint32_t), 0, sizeof(uint32_t), (size_t)B, as_stream(stream)) != cudaSuccess)
+            return check_launch("rasterize bin memset");
+        rast_bin_kernel<<<dim3((unsigned)ceil_div(F, 256), (unsigned)B), 256, 0, as_stream(stream)>>>(faces, F, is, band_rows, n_bands, bins, cap);
+        const int rc = check_launch("rast_bin_kernel");
+        if (rc != HOIG_OK) return rc;
+    }
     rasterize_kernel<<<(unsigned)((int64_t)B * n_bands), kRastThreads, smem, as_stream(stream)>>>(
-        faces, F, is, band_rows, n_bands, near_, far_, flip_y, fim, wim, depth);
+        faces, F, is, band_rows, n_bands, near_, far_, flip_y, fim, wim, depth, bins, cap);
     return check_launch("rasterize_kernel");
 }
 

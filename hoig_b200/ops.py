@@ -55,7 +55,7 @@ def packed_dims(cout: int, kh: int, kw: int, cin: int, mode: int = CONV, stride:
 
 # ------------------------------------------------------------------ stage R
 def rasterize(faces: torch.Tensor, image_size: int = 256, near: float = 0.1, far: float = 100.0,
-              flip_y: bool = True, return_depth: bool = False):
+              flip_y: bool = True, return_depth: bool = False, use_workspace: bool = True):
     """faces (B,F,3,3) f32 -> fim (B,is,is) int32, wim (B,is,is,3) f32[, depth (B,is,is)]."""
     B, F = faces.shape[:2]
     fp = _f32c(faces, "faces")
@@ -63,8 +63,11 @@ def rasterize(faces: torch.Tensor, image_size: int = 256, near: float = 0.1, far
     wim = torch.empty(B, image_size, image_size, 3, dtype=torch.float32, device=faces.device)
     depth = torch.empty(B, image_size, image_size, dtype=torch.float32, device=faces.device) if return_depth else None
     L = _lib.lib()
+    ws_bytes = L.hoig_rasterize_workspace_bytes(B, F, image_size) if use_workspace else 0
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=faces.device) if ws_bytes else None
     _lib.check(L.hoig_rasterize_fim_wim(fp, B, F, image_size, near, far, int(flip_y), fim.data_ptr(), wim.data_ptr(),
-                                        depth.data_ptr() if depth is not None else None, None, 0, _stream()),
+                                        depth.data_ptr() if depth is not None else None,
+                                        ws.data_ptr() if ws is not None else None, ws_bytes, _stream()),
                "rasterize_fim_wim")
     return (fim, wim, depth) if return_depth else (fim, wim)
 
@@ -230,6 +233,8 @@ def instnorm_apply(x: torch.Tensor, stats: torch.Tensor, out: torch.Tensor, *, g
     op, ldo = _nhwc(out, "out")
     gp, ldg = _nhwc(gb, "gb") if gb is not None else (None, 0)
     rp, ldr = _nhwc(residual, "residual") if residual is not None else (None, 0)
+    if _lib.recorder.timing:
+        _lib.recorder.tag = f"C{C} {H}x{W} N{N} gb={int(gb is not None)} res={int(residual is not None)} ld={ldx}->{ldo}"
     _lib.check(_lib.lib().hoig_instnorm_apply(xp, ldx, stats.data_ptr(),
                                               _f32c(gamma, "gamma") if gamma is not None else None,
                                               _f32c(beta, "beta") if beta is not None else None,

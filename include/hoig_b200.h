@@ -139,6 +139,8 @@ int hoig_conv2d(const hoigConvDesc *desc, hoigStream_t stream);
  * forces the bf16 kernel's A operand through the cp.async gather path instead of TMA boxes. */
 int hoig_conv2d_simt(const hoigConvDesc *desc, hoigStream_t stream);
 void hoig_set_umma_gather_only(int on);
+/* Tuning hook: pixels per rasterizer band (256..16384; the band's 64-bit key buffer lives in shared memory). */
+void hoig_set_rasterizer_band_pixels(int n);
 
 /* NCHW f32 (B,C,H,W) -> NHWC dtype with `Cpad` channels (extra channels zero). */
 int hoig_nchw_to_nhwc(const float *src, int B, int C, int H, int W, void *dst, int64_t ldd, int Cpad,

@@ -12,6 +12,9 @@ from hoig_b200 import ops, synth  # noqa: E402
 from hoig_b200.renderer import EYE_Z  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+if len(sys.argv) > 2:
+    from hoig_b200 import _lib
+    _lib.load().hoig_set_rasterizer_band_pixels(int(sys.argv[2]))
 CH = 256  # distinct pose pairs generated on host, tiled to N on device
 sc = synth.make_scene(CH // 2, seed=0, obj_faces=12238)
 nv = sc.n_verts

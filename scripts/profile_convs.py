@@ -29,7 +29,13 @@ acc = 0.0
 for (name, tag), (n, ms) in rows[:60]:
     acc += ms
     extra = ""
-    if tag:
+    if tag and name == "hoig_instnorm_apply":
+        import re
+        m = re.match(r"C(\d+) (\d+)x(\d+) N(\d+) gb=(\d) res=(\d)", tag)
+        c, h, w, nn, gbf, rs = map(int, m.groups())
+        by = nn * h * w * c * 2 * (2 + 2 * gbf + rs)
+        extra = f" {by * n / ms / 1e6:8.1f} GB/s"
+    elif tag:
         import re
         m = re.match(r"(\w+) k(\d+) s(\d+) Cin(\d+) Cout(\d+) (\d+)x(\d+)->(\d+)x(\d+) N(\d+)", tag)
         mode, k, s, cin, cout, h, w, oh, ow, nn = m.group(1), *map(int, m.groups()[1:])

@@ -56,6 +56,9 @@ def _compare(faces_cpu, is_, tag):
     fim_o, wim_o, dep_o = oracle.rasterize(faces_cpu.numpy(), is_)
     fim, wim, dep = ops.rasterize(faces_cpu.cuda(), is_, return_depth=True)
     torch.cuda.synchronize()
+    # the binning pre-pass (workspace) and the scan-all-faces path must agree bit for bit
+    f2, w2, d2 = ops.rasterize(faces_cpu.cuda(), is_, return_depth=True, use_workspace=False)
+    assert torch.equal(f2, fim) and torch.equal(w2, wim) and torch.equal(d2, dep)
     fim, wim, dep = fim.cpu().numpy(), wim.cpu().numpy(), dep.cpu().numpy()
     nbad = int((fim != fim_o).sum())
     print(f"[{tag}] covered={int((fim_o >= 0).sum())} fim mismatches={nbad} "
