@@ -12,9 +12,11 @@
 //   nn.Conv2d              taps (r - pad, s - pad); stride-2 convs read the four parity
 //                          sub-images of the input as four strided views with offsets in {-1,0},
 //                          which makes them stride-1 (TMA-box friendly) problems;
-//   nn.ConvTranspose2d     four launches, one per output parity (a,b): a stride-1 conv over the
-//                          INPUT grid with 1/2/2/4 taps whose result lands at (2*gy+a, 2*gx+b)
-//                          -- no zero-insertion, 4x fewer MACs than the gather formulation;
+//   nn.ConvTranspose2d     ONE stride-1 conv over the INPUT grid with the 2x2 taps (dy,dx) in {0,1}^2 and
+//                          N = 4*Cout columns, one block per output parity (a,b); block (a,b) lands at
+//                          (2*gy+a, 2*gx+b).  Taps a parity does not use carry zero weights (9 of 16
+//                          blocks are live): no zero-insertion, 2.25x fewer MACs than the gather
+//                          formulation and a wide-N tile for the tensor core;
 //   local attention        5x5 taps of BlockExtractor(tgt,0) | BlockExtractor(src,flow)
 //                          (extract_attn.py:24-26 + block_extractor_kernel.cu:52-84).
 #pragma once
@@ -50,6 +52,8 @@ struct ConvParams {
     const void *residual; int64_t ldr;
     void *dst; int64_t ldd;
     int OHf, OWf, os, ooy, oox;   // output pixel = (gy*os + ooy, gx*os + oox) in an OHf x OWf image
+    int phase_cout;               // > 0 (transposed conv): GEMM column n = phase*phase_cout + channel, phase (a,b) = (n/pc >> 1, & 1)
+                                  //      lands at pixel (gy*2 + a, gx*2 + b); Cout then counts all 4 phases
     double *stats;
     const float *flow;
     int KH;                 // local attention: kernel size (5)

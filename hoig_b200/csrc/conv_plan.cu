@@ -11,13 +11,6 @@ static inline int mod2(int q) { return ((q % 2) + 2) % 2; }
 
 // taps of transposed-conv output parity `a` along one axis: kernel index r' contributes
 // iff (a + pad - r') is even; the input offset is (a + pad - r') / 2.
-static int transposed_axis_taps(int a, int k, int pad, int idx[8], int off[8])
-{
-    int n = 0;
-    for (int r = 0; r < k; ++r)
-        if (mod2(a + pad - r) == 0) { idx[n] = r; off[n] = (a + pad - r) / 2; ++n; }
-    return n;
-}
 
 void packed_layout(int mode, int Cout, int KH, int KW, int Cin, int stride, int pad, int *rows, int *cols, int col_off[4],
                    int col_len[4])
@@ -29,17 +22,11 @@ void packed_layout(int mode, int Cout, int KH, int KW, int Cin, int stride, int 
         *cols = col_len[0];
         return;
     }
-    (void)stride;
-    int off = 0;
-    for (int a = 0; a < 2; ++a)
-        for (int b = 0; b < 2; ++b) {
-            int ri[8], ro[8], si[8], so[8];
-            const int nr = transposed_axis_taps(a, KH, pad, ri, ro), ns = transposed_axis_taps(b, KW, pad, si, so);
-            col_off[a * 2 + b] = off;
-            col_len[a * 2 + b] = ceil_to(nr * ns * Cin, 64);
-            off += col_len[a * 2 + b];
-        }
-    *cols = off;
+    (void)stride; (void)pad;
+    // transposed (stride 2): one GEMM, rows = 4 parity blocks of Cout, cols = 2x2 input taps x Cin
+    *rows = ceil_to(4 * Cout, 16);
+    col_len[0] = ceil_to(4 * Cin, 64);
+    *cols = col_len[0];
 }
 
 static InputView full_view(const void *base, int H, int W, int64_t ld)
@@ -62,6 +49,8 @@ int plan_conv(const hoigConvDesc *d, int bm, ConvPlan *plan)
     HOIG_REQUIRE(d->ld0 >= d->C0 && d->ld0 % 8 == 0 && (d->C1 == 0 || (d->ld1 >= d->C1 && d->ld1 % 8 == 0)),
                  "conv2d: source pixel stride must be a multiple of 8 and >= channels");
     HOIG_REQUIRE(d->ldd >= d->Cout, "conv2d: ldd < Cout");
+    HOIG_REQUIRE(d->mode != HOIG_CONV_TRANSPOSED || (d->KH == 3 && d->KW == 3 && d->pad == 1),
+                 "conv2d(transposed): only the k3 s2 p1 op1 geometry of generator.py:118,201 is supported");
     HOIG_REQUIRE(!d->residual || d->ldr >= d->Cout, "conv2d: ldr < Cout");
     HOIG_REQUIRE(((uintptr_t)d->src0 % 16) == 0 && (!d->src1 || ((uintptr_t)d->src1 % 16) == 0) && ((uintptr_t)d->weight % 16) == 0,
                  "conv2d: sources and weights must be 16-byte aligned");
@@ -119,23 +108,17 @@ int plan_conv(const hoigConvDesc *d, int bm, ConvPlan *plan)
     } else if (d->mode == HOIG_CONV_TRANSPOSED) {
         HOIG_REQUIRE(d->stride == 2 && d->OH == 2 * d->H && d->OW == 2 * d->W && d->C1 == 0,
                      "conv2d(transposed): only stride 2 with output = 2x input (k3 p1 op1 style) is supported");
-        plan->n = 4;
-        for (int a = 0; a < 2; ++a)
-            for (int b = 0; b < 2; ++b) {
-                ConvParams &p = plan->launch[a * 2 + b];
-                p = base;
-                p.GH = d->H; p.GW = d->W;
-                p.os = 2; p.ooy = a; p.oox = b;
-                int ri[8], ro[8], si[8], so[8];
-                const int nr = transposed_axis_taps(a, d->KH, d->pad, ri, ro), ns = transposed_axis_taps(b, d->KW, d->pad, si, so);
-                p.ntaps = nr * ns;
-                for (int i = 0; i < nr; ++i)
-                    for (int j = 0; j < ns; ++j) {
-                        p.tap_dy[i * ns + j] = (int8_t)ro[i]; p.tap_dx[i * ns + j] = (int8_t)so[j]; p.tap_map[i * ns + j] = 0;
-                    }
-                p.K = p.ntaps * Cin; p.Kpad = col_len[a * 2 + b];
-                p.weight = static_cast<const char *>(d->weight) + (int64_t)col_off[a * 2 + b] * esz;
-            }
+        HOIG_REQUIRE(d->Cout % 16 == 0, "conv2d(transposed): Cout must be a multiple of 16");
+        ConvParams &p = plan->launch[0];
+        p = base;
+        plan->n = 1;
+        p.GH = d->H; p.GW = d->W;
+        p.os = 2; p.ooy = 0; p.oox = 0;
+        p.phase_cout = d->Cout;
+        p.Cout = 4 * d->Cout;
+        p.ntaps = 4;
+        for (int t = 0; t < 4; ++t) { p.tap_dy[t] = (int8_t)(t >> 1); p.tap_dx[t] = (int8_t)(t & 1); p.tap_map[t] = 0; }
+        p.K = 4 * Cin; p.Kpad = col_len[0]; p.weight = d->weight;
     } else {
         HOIG_REQUIRE(d->flow && d->src1 && d->C0 == d->C1 && d->OH == d->H && d->OW == d->W && d->KH == d->KW,
                      "conv2d(local_attn): needs flow, src1, C0 == C1, OH == H");

@@ -88,11 +88,18 @@ conv_simt_kernel(const ConvParams p)
     for (int i = 0; i < 4; ++i) {
         const int pix = pix0 + ty * 4 + i;
         if (pix >= npix) continue;
-        const int64_t m = out_pixel(p, n_img, pix);
+        const int64_t m0 = out_pixel(p, n_img, pix);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx * 4 + j;
-            if (n >= p.Cout) continue;
+            const int ng = n0 + tx * 4 + j;      // GEMM column
+            if (ng >= p.Cout) continue;
+            int n = ng;                           // output channel
+            int64_t m = m0;
+            if (p.phase_cout) {                   // transposed conv: column = phase * Cout + channel
+                const int ph = ng / p.phase_cout;
+                n = ng - ph * p.phase_cout;
+                m = m0 + (int64_t)(ph >> 1) * p.OWf + (ph & 1);
+            }
             float val = acc[i][j];
             if (p.bias) val += p.bias[n];
             if (p.residual) val += DT<T>::ld(static_cast<const T *>(p.residual) + m * p.ldr + n);
@@ -117,7 +124,8 @@ conv_simt_kernel(const ConvParams p)
                 float s = 0.f;
 #pragma unroll
                 for (int r = 0; r < 16; ++r) s += red[which][r][col];
-                atomicAdd(&p.stats[((int64_t)n_img * p.Cout + n) * 2 + which], (double)s);
+                const int pc = p.phase_cout;
+                atomicAdd(&p.stats[((int64_t)n_img * (pc ? pc : p.Cout) + (pc ? n % pc : n)) * 2 + which], (double)s);
             }
         }
     }

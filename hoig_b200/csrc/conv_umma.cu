@@ -37,7 +37,7 @@ constexpr int THREADS = 448;
 constexpr int MAX_STAGES = 8;
 constexpr int LOOKAHEAD = 3;           // cp.async groups in flight per producer thread
 constexpr int STG_BYTES = 0;
-constexpr int SMEM_TOTAL = 222 * 1024;   // dynamic; + ~3.5 KB static (barriers, stats, bias) <= 227 KB per CTA
+constexpr int SMEM_TOTAL = 214 * 1024;   // dynamic; + ~10 KB static (barriers, stats, bias) <= 227 KB per CTA
 constexpr int RING_BUDGET = SMEM_TOTAL - 1024 - STG_BYTES;
 
 struct UmmaParams {
@@ -49,6 +49,7 @@ struct UmmaParams {
     int stages;
     int tma_a;       // 1: activations by TMA boxes, 0: cp.async / register gather
     int cpt_shift;   // log2(Cin / 8) when Cin < 64 (chunk -> tap by shift), -1: generic division
+    int prefetch_tiles;  // TMA-A: L2-prefetch the activation boxes this many tile rounds ahead (0 = off)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -95,6 +96,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// L2 prefetch of a box (no smem destination, no barrier): hides HBM latency that the smem ring alone cannot
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *map, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src, uint32_t src_bytes)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -104,7 +111,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1):
 // start address >> 4 | LBO (unused for swizzled K-major, canonical 1) | SBO = 1024 B (8 rows x 128 B)
@@ -197,7 +204,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float s_stats[2][256];
+    __shared__ float s_stats[4][2][256];   // per TMEM lane quadrant: plain += by its owning warps, no shared atomics
     __shared__ __align__(16) float s_bias[256 + 32];
 
     const ConvParams &p = P.c;
@@ -218,11 +225,11 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&tfull_bar[a]), 1);
-            mbar_init(smem_u32(&tempty_bar[a]), EPI_WARPS * 32);
+            mbar_init(smem_u32(&tempty_bar[a]), (uint32_t)((P.tma_a ? EPI_WARPS + PROD_WARPS : EPI_WARPS) * 32));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < 256) { s_stats[0][threadIdx.x] = 0.f; s_stats[1][threadIdx.x] = 0.f; }
+    for (int i = threadIdx.x; i < 4 * 2 * 256; i += blockDim.x) (&s_stats[0][0][0])[i] = 0.f;
     if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_smem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -236,9 +243,10 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
+    // In TMA-A mode the four producer warps have nothing to gather and join the epilogue as a third group.
+    if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS && !P.tma_a) {
         // =============================================== A producers (gather mode)
-        if (!P.tma_a) {
+        {
             const int row = threadIdx.x - EPI_WARPS * 32;  // 0..127 : A row == pixel of the tile
             const uint32_t row_off = (uint32_t)row * 128u;
             const uint32_t sw = (uint32_t)(row & 7);
@@ -367,6 +375,19 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                 const int n_img = mt / p.tiles_per_image;
                 const int pix0 = (mt % p.tiles_per_image) * BM;
                 const int gy0 = pix0 / p.GW, gx0 = pix0 % p.GW;
+                if (P.prefetch_tiles && nt == 0) {
+                    // The ring holds ~190 KB per SM; at HBM latency that caps a streaming conv at ~50 GB/s per SM.
+                    // Pull the activation boxes of the tile this CTA will reach `prefetch_tiles` rounds from now into L2.
+                    const int ft = tile + P.prefetch_tiles * (int)gridDim.x;
+                    if (ft < total_tiles) {
+                        const int fmt = ft / P.n_tiles;
+                        const int fn = fmt / p.tiles_per_image, fpix = (fmt % p.tiles_per_image) * BM;
+                        const int fy = fpix / p.GW, fx = fpix % p.GW;
+                        for (int t = 0; t < p.ntaps; ++t)
+                            for (int cc = 0; cc < p.Cin; cc += BK)
+                                tma_prefetch_4d(maps[p.tap_map[t]], cc, fx + p.tap_dx[t], fy + p.tap_dy[t], fn);
+                    }
+                }
                 int tap = 0, c = 0;
                 for (int kb = 0; kb < P.k_blocks; ++kb, ++it) {
                     const int s = it % P.stages;
@@ -412,7 +433,9 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
         // ============================================================ epilogue
         // lane == tile row within the warp's TMEM lane quadrant; the two warps of a quadrant take
         // alternate 16-column chunks.  Chunk i+1 is in flight (tcgen05.ld) while chunk i is finalised.
-        const int quad = warp & 3, half = warp >> 2;
+        const int quad = warp & 3, half = warp >> 2;               // half = chunk group of this warp
+        const int ngrp = P.tma_a ? 3 : 2;                          // groups share the chunks round-robin
+        const int epi_threads = ngrp * 128;
         const __nv_bfloat16 *res = static_cast<const __nv_bfloat16 *>(p.residual);
         __nv_bfloat16 *dst = static_cast<__nv_bfloat16 *>(p.dst);
         const bool vec_ok = ((p.ldd & 7) == 0) && (!res || (p.ldr & 7) == 0);
@@ -424,23 +447,31 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
             const int pix = (mt % p.tiles_per_image) * BM + quad * 32 + lane;
             const bool valid = pix < npix;
             const int64_t m = valid ? out_pixel(p, n_img, pix) : 0;
-            __nv_bfloat16 *drow = dst + m * p.ldd + (int64_t)nt * BN;
-            const __nv_bfloat16 *rrow = res ? res + m * p.ldr + (int64_t)nt * BN : nullptr;
+            const int pc = p.phase_cout;     // > 0: transposed conv, column n = phase * pc + channel
             const uint32_t acc = tcount & 1;
-            epi_bar();                       // previous tile fully drained: s_bias / s_stats reusable
-            for (int i = threadIdx.x; i < BN; i += EPI_WARPS * 32) {
+            epi_bar(epi_threads);                       // previous tile fully drained: s_bias / s_stats reusable
+            for (int i = threadIdx.x; i < BN; i += epi_threads) {
                 const int n = nt * BN + i;
-                s_bias[i] = (p.bias && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
+                s_bias[i] = (p.bias && n < p.Cout) ? __ldg(p.bias + (pc ? n % pc : n)) : 0.f;
             }
             mbar_wait(smem_u32(&tfull_bar[acc]), (tcount >> 1) & 1);
             tc_fence_after();
-            epi_bar();
+            epi_bar(epi_threads);
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)BN;
             uint32_t ra[16], rb[16];
             auto finalize = [&](const uint32_t (&r)[16], int ch) {
                 const int c0 = ch * 16;
                     const int n0 = nt * BN + c0;
                     if (n0 >= p.Cout) return;     // warp-uniform: padded output channels
+                    int ncol = n0;
+                    int64_t mm = m;
+                    if (pc) {   // output parity (a,b) = phase: pixel (2gy+a, 2gx+b), channel n0 - phase*pc
+                        const int ph = n0 / pc;
+                        ncol = n0 - ph * pc;
+                        mm = m + (int64_t)(ph >> 1) * p.OWf + (ph & 1);
+                    }
+                    __nv_bfloat16 *drow = dst + mm * p.ldd + ncol - c0;
+                    const __nv_bfloat16 *rrow = res ? res + mm * p.ldr + ncol - c0 : nullptr;
                     float v[16];
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
@@ -496,32 +527,34 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                         const float cq = transpose_reduce16(q, lane);
                         if ((lane & 1) == 0) {
                             const int col = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                            atomicAdd(&s_stats[0][col], cs);
-                            atomicAdd(&s_stats[1][col], cq);
+                            s_stats[quad][0][col] += cs;   // (quad, column) is touched by this warp only
+                            s_stats[quad][1][col] += cq;
                         }
                     }
             };
             if (half < n_chunks) tmem_ld16(t_row + (uint32_t)(half * 16), ra);
-            for (int ch = half; ch < n_chunks; ch += 4) {
+            for (int ch = half; ch < n_chunks; ch += 2 * ngrp) {
                 tmem_ld_wait(ra);
-                if (ch + 2 < n_chunks) tmem_ld16(t_row + (uint32_t)((ch + 2) * 16), rb);
+                if (ch + ngrp < n_chunks) tmem_ld16(t_row + (uint32_t)((ch + ngrp) * 16), rb);
                 finalize(ra, ch);
-                if (ch + 2 < n_chunks) {
+                if (ch + ngrp < n_chunks) {
                     tmem_ld_wait(rb);
-                    if (ch + 4 < n_chunks) tmem_ld16(t_row + (uint32_t)((ch + 4) * 16), ra);
-                    finalize(rb, ch + 2);
+                    if (ch + 2 * ngrp < n_chunks) tmem_ld16(t_row + (uint32_t)((ch + 2 * ngrp) * 16), ra);
+                    finalize(rb, ch + ngrp);
                 }
             }
             // accumulator drained: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             mbar_arrive(smem_u32(&tempty_bar[acc]));
             if (p.stats) {
-                epi_bar();
-                for (int i = threadIdx.x; i < 2 * BN; i += EPI_WARPS * 32) {
+                epi_bar(epi_threads);
+                for (int i = threadIdx.x; i < 2 * BN; i += epi_threads) {
                     const int which = i / BN, col = i % BN;
                     const int n = nt * BN + col;
-                    if (n < p.Cout) atomicAdd(&p.stats[((int64_t)n_img * p.Cout + n) * 2 + which], (double)s_stats[which][col]);
-                    s_stats[which][col] = 0.f;
+                    const float tot = s_stats[0][which][col] + s_stats[1][which][col] + s_stats[2][which][col] + s_stats[3][which][col];
+                    if (n < p.Cout)
+                        atomicAdd(&p.stats[((int64_t)n_img * (pc ? pc : p.Cout) + (pc ? n % pc : n)) * 2 + which], (double)tot);
+                    s_stats[0][which][col] = 0.f; s_stats[1][which][col] = 0.f; s_stats[2][which][col] = 0.f; s_stats[3][which][col] = 0.f;
                 }
             }
         }
@@ -566,6 +599,8 @@ int make_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t *dim
     return HOIG_OK;
 }
 
+int g_prefetch_tiles = 0;   // measured: L2 prefetch of future tiles HURTS (the streaming convs are L2->SM bandwidth bound, not latency bound)
+
 int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather)
 {
     UmmaParams P;
@@ -592,6 +627,10 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather)
     if (P.tma_a)   // view strides must be 16-byte multiples for a tensor map
         for (int v = 0; v < p.nviews; ++v)
             if ((p.view[v].sx * 2) % 16 || ((uintptr_t)p.view[v].base % 16)) P.tma_a = 0;
+
+    // streaming inputs (larger than a fraction of L2) need HBM latency hidden beyond the smem ring
+    const double in_bytes = (double)p.N * p.view[0].sn * 2.0;
+    P.prefetch_tiles = (P.tma_a && g_prefetch_tiles > 0 && in_bytes > 48e6) ? g_prefetch_tiles : 0;
 
     CUtensorMap map_w, map_a[4];
     int st;
@@ -643,6 +682,8 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
     if (g_force_gather < 0) {
         const char *e = getenv("HOIG_UMMA_GATHER_ONLY");
         g_force_gather = (e && e[0] == '1') ? 1 : 0;
+        const char *pf = getenv("HOIG_UMMA_PREFETCH_TILES");
+        if (pf) g_prefetch_tiles = atoi(pf);
     }
     for (int i = 0; i < plan.n; ++i) {
         st = launch_one(plan.launch[i], stream, g_force_gather);

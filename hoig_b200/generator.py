@@ -25,6 +25,7 @@ Schedule (reference line numbers in comments):
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -161,6 +162,8 @@ class GeneratorB200(nn.Module):
         if dtype not in (torch.bfloat16, torch.float32):
             raise ValueError("GeneratorB200: dtype must be torch.bfloat16 (tensor-core path) or torch.float32 (parity path)")
         self.compute_dtype = dtype
+        # K (= taps x input channels) from which InstanceNorm statistics are accumulated in the conv epilogue
+        self.stats_epilogue_min_k = int(os.environ.get("HOIG_STATS_EPILOGUE_MIN_K", "0"))
         self._layout = parameter_layout(bg_dim, img_dim, obj_dim, img_cond_dim, obj_cond_dim, conv_dim, repeat_num,
                                         self.n_down, self.spade_layers, self.attn_layers)
         for top in ("bg_model", "obj_model", "src_model", "tsf_model"):
@@ -242,8 +245,14 @@ class GeneratorB200(nn.Module):
         if out is None:
             out = self._new(n, oh, ow, ceil_to(cout, 8))
         stats = self._arena.take(n, cout) if want_stats else None
+        # statistics ride in the conv epilogue when the tile's MMA time hides it (long K); for short-K convs the
+        # epilogue is the critical path, so a separate bandwidth pass over the (L2-warm) output is cheaper
+        k_len = k * k * x.shape[3] if not transposed else 4 * x.shape[3]
+        fused = stats is not None and k_len >= self.stats_epilogue_min_k
         ops.conv2d(x, self._w(wname, transposed), out, kh=k, kw=k, stride=2 if transposed else stride, pad=pad, mode=mode,
-                   bias=self._f32(bias) if bias else None, act=act, residual=residual, stats=stats, cout=cout)
+                   bias=self._f32(bias) if bias else None, act=act, residual=residual, stats=stats if fused else None, cout=cout)
+        if stats is not None and not fused:
+            ops.plane_stats(out[..., :cout] if out.shape[3] != cout else out, stats)
         return out, stats
 
     def _conv_in_relu(self, x, prefix_conv, prefix_norm, cout, k, *, stride=1, transposed=False, out=None, relu=True,
@@ -350,7 +359,10 @@ class GeneratorB200(nn.Module):
         wp = self._cached(wname + "#stem7", [prm], build)
         raw = self._new(b, h, w, cout)
         stats = self._arena.take(b, cout)
-        ops.conv2d(x7, wp, raw, kh=7, kw=1, stride=1, pad=3, pad_w=0, stats=stats)
+        fused = 7 * cpad >= self.stats_epilogue_min_k
+        ops.conv2d(x7, wp, raw, kh=7, kw=1, stride=1, pad=3, pad_w=0, stats=stats if fused else None)
+        if not fused:
+            ops.plane_stats(raw, stats)
         dst = raw if out is None else out
         ops.instnorm_apply(raw, stats, dst, gamma=self._f32(prefix_norm + "weight"), beta=self._f32(prefix_norm + "bias"), relu=True)
         return dst

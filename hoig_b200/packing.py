@@ -5,9 +5,8 @@ consume a K-major matrix ``Wp[Cout_pad16][cols]``:
 
 * ``nn.Conv2d`` (and the local-attention k5s5 conv): ``k = (r*KW + s)*Cin_pad + c``, padded to 64 columns
   (``Cin_pad`` = Cin rounded up to 8, matching the zero-padded NHWC activations);
-* ``nn.ConvTranspose2d`` (stride 2): the four output-parity phases (a,b) side by side, each
-  ``[taps(a) x taps(b) x Cin_pad]`` padded to 64 columns, where kernel row ``r`` belongs to parity ``a`` iff
-  ``(a + pad - r)`` is even (it then reads input row ``gy + (a + pad - r)/2``) -- see ``csrc/conv_plan.cu``.
+* ``nn.ConvTranspose2d`` (k3 s2 p1 op1): ``[4*Cout][4*Cin_pad]`` -- row block (a,b) = output parity, column
+  block (dy,dx) = input tap of the 2x2 neighbourhood; blocks a parity does not use are zero (``csrc/conv_plan.cu``).
 
 Packed copies are derived caches.
 """
@@ -20,34 +19,31 @@ def ceil_to(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
-def transposed_axis_taps(k: int, pad: int):
-    """Per output parity a in (0,1): kernel indices r with (a + pad - r) even, in increasing order."""
-    return [[r for r in range(k) if (a + pad - r) % 2 == 0] for a in (0, 1)]
-
-
 def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, transposed: bool = False, pad: int = 1) -> torch.Tensor:
-    """``nn.Conv2d.weight`` (Cout,Cin,KH,KW) or ``nn.ConvTranspose2d.weight`` (Cin,Cout,KH,KW) -> packed matrix."""
+    """``nn.Conv2d.weight`` (Cout,Cin,KH,KW) or ``nn.ConvTranspose2d.weight`` (Cin,Cout,3,3; stride 2) -> packed matrix."""
     w = w.detach().float()
-    if transposed:
-        w = w.permute(1, 0, 2, 3)
-    cout, cin, kh, kw = w.shape
-    cin_p = ceil_to(cin, 8)
-    rows = ceil_to(cout, 16)
-    t = torch.zeros(cout, kh, kw, cin_p, dtype=torch.float32, device=w.device)
-    t[..., :cin] = w.permute(0, 2, 3, 1)
     if not transposed:
-        groups = [[(r, s) for r in range(kh) for s in range(kw)]]
-    else:
-        ra, sa = transposed_axis_taps(kh, pad), transposed_axis_taps(kw, pad)
-        groups = [[(r, s) for r in ra[a] for s in sa[b]] for a in (0, 1) for b in (0, 1)]
-    blocks = []
-    for taps in groups:
-        n = len(taps) * cin_p
-        blk = torch.zeros(rows, ceil_to(n, 64), dtype=torch.float32, device=w.device)
-        if taps:
-            blk[:cout, :n] = torch.stack([t[:, r, s] for r, s in taps], 1).reshape(cout, n)
-        blocks.append(blk)
-    return torch.cat(blocks, 1).to(dtype).contiguous()
+        cout, cin, kh, kw = w.shape
+        cin_p = ceil_to(cin, 8)
+        t = torch.zeros(cout, kh, kw, cin_p, dtype=torch.float32, device=w.device)
+        t[..., :cin] = w.permute(0, 2, 3, 1)
+        out = torch.zeros(ceil_to(cout, 16), ceil_to(kh * kw * cin_p, 64), dtype=torch.float32, device=w.device)
+        out[:cout, : kh * kw * cin_p] = t.reshape(cout, -1)
+        return out.to(dtype).contiguous()
+    # transposed conv as ONE GEMM over the 2x2 input taps (dy,dx): row block (a,b) = output parity, and
+    # out[2gy+a, 2gx+b] += in[gy+dy, gx+dx] * W[:, :, a+pad-2dy, b+pad-2dx]  whenever that kernel index exists
+    cin, cout, kh, kw = w.shape
+    cin_p = ceil_to(cin, 8)
+    out = torch.zeros(ceil_to(4 * cout, 16), ceil_to(4 * cin_p, 64), dtype=torch.float32, device=w.device)
+    for a in (0, 1):
+        for b in (0, 1):
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    r, s_ = a + pad - 2 * dy, b + pad - 2 * dx
+                    if 0 <= r < kh and 0 <= s_ < kw:
+                        ph, t = a * 2 + b, dy * 2 + dx
+                        out[ph * cout:(ph + 1) * cout, t * cin_p:t * cin_p + cin] = w[:, :, r, s_].t()
+    return out.to(dtype).contiguous()
 
 
 def pack_spade_gamma_beta(wg, bg, wb, bb, dtype):

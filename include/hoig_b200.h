@@ -112,8 +112,8 @@ typedef struct {
     int KH, KW, stride, pad;  /* pad = vertical padding; horizontal padding is pad_w (last field) */
     const void *src0; int64_t ld0;
     const void *src1; int64_t ld1;
-    const void *weight; /* packed [Cout_pad][cols]; conv / local attention: k = (r*KW + s)*(C0+C1) + c;
-                         * transposed: the four output-parity phases side by side (hoig_conv_packed_dims) */
+    const void *weight; /* packed [rows][cols]; conv / local attention: k = (r*KW + s)*(C0+C1) + c;
+                         * transposed: parity-block x tap-block matrix (hoig_conv_packed_dims) */
     const float *bias;  /* [Cout] or NULL */
     int act;            /* hoigAct applied after bias (+ residual) */
     const void *residual; int64_t ldr; /* NHWC (N,OH,OW,Cout) added before `act`, or NULL */
@@ -124,10 +124,10 @@ typedef struct {
     int pad_w;          /* horizontal padding (set equal to pad for square kernels) */
 } hoigConvDesc;
 
-/* Rows / columns of the packed weight matrix for a given problem: rows = Cout padded to 16;
- * cols = KH*KW*Cin padded to 64, or, for HOIG_CONV_TRANSPOSED (stride 2), the sum over the four
- * output-parity phases (a,b) of [taps(a)*taps(b)*Cin padded to 64], phases in order (0,0),(0,1),(1,0),(1,1),
- * taps of a phase ordered by (r,s) over the kernel rows/cols with (a + pad - r) even. */
+/* Rows / columns of the packed weight matrix for a given problem.  Conv / local attention: rows = Cout padded
+ * to 16, cols = KH*KW*Cin padded to 64.  HOIG_CONV_TRANSPOSED (k3 s2 p1 op1): rows = 4*Cout (one block per output
+ * parity (a,b), block index a*2+b), cols = 4*Cin padded to 64 (one block per input tap (dy,dx) of the 2x2
+ * neighbourhood, index dy*2+dx); block [(a,b)][(dy,dx)] = W[:, :, a+pad-2dy, b+pad-2dx]^T or zero. */
 int hoig_conv_packed_dims(int mode, int Cout, int KH, int KW, int Cin, int stride, int pad, int *rows, int *cols);
 /* Implicit-GEMM convolution (nn.Conv2d / nn.ConvTranspose2d k3 s2 p1 op1 /
  * the k5 s5 conv over cat[BlockExtractor(tgt,0), BlockExtractor(src,flow)] of

@@ -27,19 +27,16 @@ def unpack_weight(wp, cout, kh, kw, cin_p):
 
 
 def unpack_transposed(wp, cout, kh, kw, cin_p, pad):
-    """Inverse of the four-phase layout of pack_conv_weight(transposed=True): -> (Cout, Cin_p, KH, KW)."""
-    from hoig_b200.packing import transposed_axis_taps
-    ra, sa = transposed_axis_taps(kh, pad), transposed_axis_taps(kw, pad)
+    """Inverse of pack_conv_weight(transposed=True): [4*Cout][4*Cin_p] parity/tap blocks -> (Cout, Cin_p, KH, KW)."""
     w = torch.zeros(cout, cin_p, kh, kw)
-    off = 0
     for a in (0, 1):
         for b in (0, 1):
-            taps = [(r, s) for r in ra[a] for s in sa[b]]
-            n = len(taps) * cin_p
-            blk = wp.float()[:cout, off:off + n].reshape(cout, len(taps), cin_p)
-            for i, (r, s) in enumerate(taps):
-                w[:, :, r, s] = blk[:, i]
-            off += ceil_to(n, 64)
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    r, s_ = a + pad - 2 * dy, b + pad - 2 * dx
+                    if 0 <= r < kh and 0 <= s_ < kw:
+                        ph, t = a * 2 + b, dy * 2 + dx
+                        w[:, :, r, s_] = wp.float()[ph * cout:(ph + 1) * cout, t * cin_p:(t + 1) * cin_p]
     return w
 
 

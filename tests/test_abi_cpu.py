@@ -54,10 +54,10 @@ def test_argument_validation_without_gpu(lib):
     assert (r.value, c.value) == (16, 3136)
     lib.hoig_conv_packed_dims(2, 128, 5, 5, 1024, 5, 0, ctypes.byref(r), ctypes.byref(c))
     assert (r.value, c.value) == (128, 25600)
-    lib.hoig_conv_packed_dims(1, 64, 3, 3, 128, 2, 1, ctypes.byref(r), ctypes.byref(c))     # 1+2+2+4 taps x 128 ch
-    assert (r.value, c.value) == (64, 9 * 128)
-    lib.hoig_conv_packed_dims(1, 16, 3, 3, 32, 2, 1, ctypes.byref(r), ctypes.byref(c))      # each phase padded to 64 columns
-    assert (r.value, c.value) == (16, 64 + 64 + 64 + 128)
+    lib.hoig_conv_packed_dims(1, 64, 3, 3, 128, 2, 1, ctypes.byref(r), ctypes.byref(c))     # 4 parity blocks x 4 input taps
+    assert (r.value, c.value) == (256, 512)
+    lib.hoig_conv_packed_dims(1, 16, 3, 3, 8, 2, 1, ctypes.byref(r), ctypes.byref(c))
+    assert (r.value, c.value) == (64, 64)
 
 
 def test_ops_fail_loudly_without_a_gpu():
@@ -96,8 +96,9 @@ def test_packing_layout():
     assert p[0, 3] == 0 and p[2:].abs().sum() == 0
     wt = torch.arange(3 * 2 * 3 * 3, dtype=torch.float32).reshape(3, 2, 3, 3)   # ConvTranspose2d (Cin,Cout,kh,kw)
     pt = pack_conv_weight(wt, torch.float32, transposed=True)
-    assert pt.shape == (16, 4 * 64)
-    assert pt[1, 0 * 64 + 2] == wt[2, 1, 1, 1]            # phase (0,0): the centre tap only
-    assert pt[1, 3 * 64 + (1 * 2 + 0) * 8 + 2] == wt[2, 1, 2, 0]   # phase (1,1): taps (0,0),(0,2),(2,0),(2,2)
+    assert pt.shape == (16, 64)                            # 4 parities x Cout=2 rows (pad 16), 4 taps x Cin_pad=8 cols (pad 64)
+    assert pt[0 * 2 + 1, 0 * 8 + 2] == wt[2, 1, 1, 1]      # parity (0,0) uses only tap (0,0) with the centre weight
+    assert pt[0 * 2 + 1, 8:].abs().sum() == 0
+    assert pt[3 * 2 + 1, (1 * 2 + 0) * 8 + 2] == wt[2, 1, 0, 2]   # parity (1,1), tap (dy,dx)=(1,0): kernel index (0,2)
     from tests.emu_ops import unpack_transposed
     assert torch.equal(unpack_transposed(pt, 2, 3, 3, 8, 1)[:, :3], wt.permute(1, 0, 2, 3))

@@ -82,4 +82,5 @@ def test_umma_matches_simt_bf16_bitwise_mostly():
     b, _, _, _ = _run_conv(case, torch.bfloat16, simt=True)
     diff = (a.float() - b.float()).abs()
     print("umma vs simt: maxabs", diff.max().item(), "fraction differing", (diff > 0).float().mean().item())
-    assert diff.max().item() <= 3e-2
+    # fp32 accumulation order differs (tile-K vs 16-wide K steps): at most one bf16 ulp (2^-8 relative) apart
+    assert (diff <= 2.0 ** -7 * b.float().abs() + 1e-3).all()
