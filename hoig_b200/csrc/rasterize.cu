@@ -126,9 +126,9 @@ __device__ __forceinline__ void make_edges(const float f[9], Edges &e)
 
 // Search window of a front-facing face inside the band [r0, r1].  A pixel that passes the three float edge
 // tests lies within ~3e-5 NDC of each (computed) edge half-plane, hence within  3e-5 / sin(theta_min / 2)  of the
-// vertex bounding box (theta_min = smallest corner angle; derivation in DESIGN.md 3.2).  Faces with
-// theta_min >= ~3 deg get a 1-pixel margin, needles down to ~0.06 deg a (1 + 0.03*is)-pixel margin, anything
-// thinner / larger than 64 NDC searches the whole band with the exact monotone predicate, non-finite or huge
+// vertex bounding box (theta_min = smallest corner angle; derivation in DESIGN.md 3.2).  The margin is computed
+// per face from sin(theta_min) (0.8 px for well-shaped faces, growing for needles); faces thinner than ~0.03 deg
+// or larger than 64 NDC search the whole band with the exact monotone predicate, non-finite or huge
 // coordinates run the reference tests verbatim on every band pixel.
 __device__ __forceinline__ Window classify(const float f[9], const Edges &e, const float *centre, int is, float isf, int r0, int r1)
 {
@@ -148,11 +148,13 @@ __device__ __forceinline__ Window classify(const float f[9], const Edges &e, con
     const float sin2 = cross * cross;                                 // = sin^2(theta_min) * lmax * lmid
     const float ll = lmax * lmid;
     const float big = fmaxf(fmaxf(fabsf(f[0]), fabsf(f[3])), fmaxf(fmaxf(fabsf(f[6]), fabsf(f[1])), fmaxf(fabsf(f[4]), fabsf(f[7]))));
-    const float tau0 = fmaxf(0.05f, 1.2e-4f * isf);
+    // margin (pixels) = 0.5 + 2 x the bound  3e-5 * is / sin(theta_min)  on how far the float pass region can
+    // extend beyond the vertex bounding box; faces thinner than ~0.03 deg fall through to the
+    // exact whole-band search
     float margin = -1.f;
     if (big <= 64.f && ll > 1e-30f && cross > 0.f) {
-        if (sin2 >= tau0 * tau0 * ll) margin = 1.f;
-        else if (sin2 >= 1e-6f * ll) margin = 1.f + ceilf(0.03f * isf);
+        const float m = 0.5f + 6e-5f * isf * sqrtf(ll / sin2);
+        if (m <= 0.5f + 0.06f * isf) margin = m;
     }
     if (margin > 0.f) {
         const float xmin = fminf(f[0], fminf(f[3], f[6])), xmax = fmaxf(f[0], fmaxf(f[3], f[6]));
@@ -219,7 +221,40 @@ __device__ __forceinline__ void scatter_face(const float f[9], const Edges &e, W
     }
 }
 
+// Warp-cooperative scatter of one "heavy" face (needle / degenerate / wild: large search window): the window's
+// pixels are spread over the 32 lanes and each lane runs the reference's edge tests verbatim on its pixels.
+__device__ __forceinline__ void scatter_face_warp(const float f[9], const Edges &e, Window w, int fn, const float *centre,
+                                                  unsigned long long *keys, int is, float isf, int r0, int r1, float near_, float far_,
+                                                  int lane)
+{
+    if (w.tier == 1) {   // exact row range by binary search on the monotone row predicate (uniform across lanes)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float bmin = fminf(e.B(i, centre[0]), e.B(i, centre[is - 1]));
+            if (e.dx[i] >= 0.f) w.row_lo = max(w.row_lo, first_true(r0, r1, [&](int y) { return e.A(i, centre[y]) >= bmin; }));
+            else                w.row_hi = min(w.row_hi, first_true(r0, r1, [&](int y) { return !(e.A(i, centre[y]) >= bmin); }) - 1);
+        }
+        if (w.row_lo > w.row_hi) return;
+    }
+    float fi[9];
+    face_inverse(f, isf, fi);
+    const int cols = w.col_hi - w.col_lo + 1;
+    const int npx = (w.row_hi - w.row_lo + 1) * cols;
+    for (int q = lane; q < npx; q += 32) {
+        const int y = w.row_lo + q / cols, x = w.col_lo + q % cols;
+        const float yp = centre[y], xp = centre[x];
+        // rasterize_cuda_kernel.cu:132-135 verbatim (NaN compares false => passes)
+        if ((e.A(0, yp) < e.B(0, xp)) || (e.A(1, yp) < e.B(1, xp)) || (e.A(2, yp) < e.B(2, xp))) continue;
+        float wgt[3], zp;
+        if (!shade(f, fi, (float)x, (float)y, near_, far_, wgt, zp)) continue;
+        const unsigned long long key = ((unsigned long long)ordered_bits(zp) << 32) | (uint32_t)fn;
+        atomicMin(&keys[(size_t)(y - r0) * is + x], key);
+    }
+}
+
 constexpr int kListCap = 6144;   // compacted in-band faces per CTA (overflow is processed in place)
+constexpr int kHeavyCap = 2048;  // faces with a large search window, scattered one per warp
+constexpr int kLightArea = 100;   // window pixels up to which one thread scatters the face by itself
 
 // Pre-pass (used when a workspace is supplied): every face is culled and classified ONCE per mesh and a packed
 // (band << 24 | face) entry is appended to the mesh's bin for each band its window touches, so the raster CTAs
@@ -262,7 +297,8 @@ rasterize_kernel(const float *__restrict__ faces, int F, int is, int band_rows, 
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
     float *centre = reinterpret_cast<float *>(keys + (size_t)band_rows * is);
     int *list = reinterpret_cast<int *>(centre + is);
-    __shared__ int list_n;
+    int *heavy = list + kListCap;
+    __shared__ int list_n, heavy_n;
 
     const int mesh = blockIdx.x / n_bands;
     const int band = blockIdx.x % n_bands;
@@ -274,7 +310,7 @@ rasterize_kernel(const float *__restrict__ faces, int F, int is, int band_rows, 
     for (int i = threadIdx.x; i < npix; i += blockDim.x) keys[i] = kEmptyKey;
     // rasterize_cuda_kernel.cu:113-114: pixel centre in f64, rounded once
     for (int i = threadIdx.x; i < is; i += blockDim.x) centre[i] = (float)((2. * i + 1 - is) / is);
-    if (threadIdx.x == 0) list_n = 0;
+    if (threadIdx.x == 0) { list_n = 0; heavy_n = 0; }
     __syncthreads();
 
     const float *mf = faces + (size_t)mesh * F * 9;
@@ -343,9 +379,31 @@ rasterize_kernel(const float *__restrict__ faces, int F, int is, int band_rows, 
             Edges e;
             make_edges(f, e);
             const Window w = classify(f, e, centre, is, isf, r0, r1);
-            if (w.tier >= 0) scatter_face(f, e, w, fn, centre, keys, is, isf, r0, r1, near_, far_);
+            if (w.tier >= 0) {
+                const bool light = w.tier == 0 && (w.row_hi - w.row_lo + 1) * (w.col_hi - w.col_lo + 1) <= kLightArea;
+                int slot = kHeavyCap;
+                if (!light) slot = atomicAdd(&heavy_n, 1);
+                if (slot < kHeavyCap) heavy[slot] = fn;                 // large window: one warp per face below
+                else scatter_face(f, e, w, fn, centre, keys, is, isf, r0, r1, near_, far_);
+            }
         }
         __syncwarp();
+    }
+    __syncthreads();
+    {
+        const int n_heavy = min(heavy_n, kHeavyCap);
+        const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+        for (int h = wid; h < n_heavy; h += nw) {
+            const int fn = heavy[h];
+            float f[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) f[k] = __ldg(mf + (size_t)fn * 9 + k);
+            Edges e;
+            make_edges(f, e);
+            const Window w = classify(f, e, centre, is, isf, r0, r1);
+            if (w.tier >= 0) scatter_face_warp(f, e, w, fn, centre, keys, is, isf, r0, r1, near_, far_, lane);
+            __syncwarp();
+        }
     }
     __syncthreads();
 
@@ -505,7 +563,7 @@ extern "C" int hoig_rasterize_fim_wim(const float *faces, int B, int F, int imag
     if (band_rows > is) band_rows = is;
     HOIG_REQUIRE(band_rows >= 1, "rasterize: image too wide");
     const int n_bands = ceil_div(is, band_rows);
-    const size_t smem = (size_t)band_rows * is * sizeof(unsigned long long) + (size_t)is * sizeof(float) + (size_t)kListCap * sizeof(int);
+    const size_t smem = (size_t)band_rows * is * sizeof(unsigned long long) + (size_t)is * sizeof(float) + (size_t)(kListCap + kHeavyCap) * sizeof(int);
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(rasterize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
