@@ -29,6 +29,16 @@ TABLE = dict(spade_layers=(1, 1, 0, 0), attn_layers=tuple(range(1, 10)))
 METRIC = "images/sec at 256x256 (HOGAN generator forward)"
 
 
+def _conv_traffic(batch):
+    """DRAM bytes per conv launch from the committed ncu capture (profiles/), valid for the batch it was taken at."""
+    for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True):
+        if name.endswith("_conv_traffic.json"):
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if t.get("batch", 64) == batch:
+                return t.get("dram_bytes_per_launch")
+    return None
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -139,7 +149,7 @@ def run_ours(args):
     from hoig_b200.generator import composite, create
 
     B = args.batch
-    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    dtype = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}[args.dtype]
     torch.manual_seed(1234 + rank)
     g = create("generator_spade_attn", dtype=dtype, **CFG)
     g.init_weights()
@@ -247,7 +257,8 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "kernel": "conv_umma_kernel (hoig_conv2d)", "achieved": achieved, "peak": sustained,
                          "unit": "TFLOP/s", "frac": achieved / sustained, "peak_source": f"{peak_src} bf16 sustained (kernel timed inside a long step)",
                          "launches_per_step": conv_n / args.steps, "conv_share_of_step": conv_ms / max(ms, 1e-9),
-                         "flops_per_image": GFLOP_PER_IMAGE * 1e9, "traffic": None},
+                         "flops_per_image": GFLOP_PER_IMAGE * 1e9, "traffic": _conv_traffic(B),
+                         "traffic_note": "mean DRAM read+write bytes per conv launch, ncu capture under profiles/ (bf16, batch 64)"},
             "kernel_time_share": shares}
     if args.cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
@@ -266,7 +277,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step (BASELINE config: 64)")
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16", "f32"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()
     if args.impl == "reference":

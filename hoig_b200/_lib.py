@@ -13,7 +13,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_C", "libhoig_b200.so")
 
-HOIG_F32, HOIG_BF16 = 0, 1
+HOIG_F32, HOIG_BF16, HOIG_F16 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
 CONV, CONV_TRANSPOSED, CONV_LOCAL_ATTN = 0, 1, 2
 

@@ -48,7 +48,7 @@ extern "C" int hoig_check_device(void)
 extern "C" int hoig_conv2d(const hoigConvDesc *desc, hoigStream_t stream)
 {
     if (!desc) { hoig::set_error("conv2d: null descriptor"); return HOIG_ERR_INVALID; }
-    if (desc->dtype == HOIG_BF16) return hoig::conv2d_umma(desc, hoig::as_stream(stream));
+    if (desc->dtype == HOIG_BF16 || desc->dtype == HOIG_F16) return hoig::conv2d_umma(desc, hoig::as_stream(stream));
     return hoig::conv2d_simt(desc, hoig::as_stream(stream));
 }
 

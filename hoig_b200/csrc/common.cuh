@@ -1,6 +1,7 @@
 // common.cuh -- shared helpers for the hoig_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -35,6 +36,35 @@ template <> struct DT<__nv_bfloat16> {
     static __device__ __forceinline__ void st(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
 };
 
+template <> struct DT<__half> {
+    static __device__ __forceinline__ float ld(const __half *p) { return __half2float(*p); }
+    static __device__ __forceinline__ void st(__half *p, float v) { *p = __float2half_rn(v); }
+};
+
+// two 16-bit storage values <-> two floats
+template <typename T> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi)
+{
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&t);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi)
+{
+    __half2 t = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&t);
+}
+template <typename T> __device__ __forceinline__ void unpack2(uint32_t w, float &lo, float &hi);
+template <> __device__ __forceinline__ void unpack2<__nv_bfloat16>(uint32_t w, float &lo, float &hi)
+{
+    lo = __uint_as_float(w << 16);
+    hi = __uint_as_float(w & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void unpack2<__half>(uint32_t w, float &lo, float &hi)
+{
+    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w));
+    lo = f.x; hi = f.y;
+}
+
 // 8 consecutive channels (one 16-byte chunk for bf16, two for f32) <-> float[8]
 __device__ __forceinline__ void load8(const float *p, float v[8])
 {
@@ -50,6 +80,20 @@ __device__ __forceinline__ void load8(const __nv_bfloat16 *p, float v[8])
         v[2 * i] = __uint_as_float(w[i] << 16);
         v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
     }
+}
+__device__ __forceinline__ void load8(const __half *p, float v[8])
+{
+    const uint4 r = *reinterpret_cast<const uint4 *>(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) unpack2<__half>(w[i], v[2 * i], v[2 * i + 1]);
+}
+__device__ __forceinline__ void store8(__half *p, const float v[8])
+{
+    uint4 r;
+    r.x = pack2<__half>(v[0], v[1]); r.y = pack2<__half>(v[2], v[3]);
+    r.z = pack2<__half>(v[4], v[5]); r.w = pack2<__half>(v[6], v[7]);
+    *reinterpret_cast<uint4 *>(p) = r;
 }
 __device__ __forceinline__ void store8(float *p, const float v[8])
 {
@@ -72,6 +116,7 @@ __device__ __forceinline__ void store8(__nv_bfloat16 *p, const float v[8])
 template <typename T> __device__ __forceinline__ float round_to(float v);
 template <> __device__ __forceinline__ float round_to<float>(float v) { return v; }
 template <> __device__ __forceinline__ float round_to<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+template <> __device__ __forceinline__ float round_to<__half>(float v) { return __half2float(__float2half_rn(v)); }
 
 __device__ __forceinline__ float apply_act(float v, int act)
 {

@@ -39,7 +39,7 @@ static InputView full_view(const void *base, int H, int W, int64_t ld)
 int plan_conv(const hoigConvDesc *d, int bm, ConvPlan *plan)
 {
     HOIG_REQUIRE(d && d->src0 && d->weight && d->dst, "conv2d: null pointer");
-    HOIG_REQUIRE(d->dtype == HOIG_F32 || d->dtype == HOIG_BF16, "conv2d: bad dtype %d", d->dtype);
+    HOIG_REQUIRE(d->dtype == HOIG_F32 || d->dtype == HOIG_BF16 || d->dtype == HOIG_F16, "conv2d: bad dtype %d", d->dtype);
     HOIG_REQUIRE(d->mode >= HOIG_CONV && d->mode <= HOIG_CONV_LOCAL_ATTN, "conv2d: bad mode %d", d->mode);
     HOIG_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->OH > 0 && d->OW > 0 && d->Cout > 0, "conv2d: bad shape");
     HOIG_REQUIRE(d->C0 > 0 && d->C0 % 8 == 0 && d->C1 >= 0 && d->C1 % 8 == 0, "conv2d: C0/C1 must be multiples of 8 (got %d,%d)", d->C0, d->C1);

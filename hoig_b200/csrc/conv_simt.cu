@@ -142,6 +142,7 @@ int conv2d_simt(const hoigConvDesc *d, cudaStream_t stream)
         const ConvParams &p = plan.launch[i];
         dim3 grid((unsigned)(p.N * p.tiles_per_image), (unsigned)ceil_div(p.Cout, BN));
         if (d->dtype == HOIG_F32) conv_simt_kernel<float><<<grid, THREADS, 0, stream>>>(p);
+        else if (d->dtype == HOIG_F16) conv_simt_kernel<__half><<<grid, THREADS, 0, stream>>>(p);
         else conv_simt_kernel<__nv_bfloat16><<<grid, THREADS, 0, stream>>>(p);
         const int rc = check_launch("conv_simt_kernel");
         if (rc != HOIG_OK) return rc;

@@ -23,6 +23,8 @@
 // smem: ring of STAGES x (A 16 KB + B BN*128 B), 1024-byte aligned for SWIZZLE_128B.
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "conv_common.cuh"
 
 namespace hoig {
@@ -196,6 +198,7 @@ __device__ __forceinline__ float transpose_reduce16(const float v[16], int lane)
 }
 
 // ------------------------------------------------------------------------ kernel
+template <typename T>   // T = T or __half (16-bit storage; tcgen05 kind::f16 handles both)
 __global__ void __launch_bounds__(THREADS, 1)
 conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
@@ -250,7 +253,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
             const int row = threadIdx.x - EPI_WARPS * 32;  // 0..127 : A row == pixel of the tile
             const uint32_t row_off = (uint32_t)row * 128u;
             const uint32_t sw = (uint32_t)(row & 7);
-            const __nv_bfloat16 *src0 = static_cast<const __nv_bfloat16 *>(p.view[0].base);
+            const T *src0 = static_cast<const T *>(p.view[0].base);
             uint32_t it = 0;  // running k-block counter across tiles
             int pending = 0;  // k-blocks issued but not yet signalled
             uint32_t sig_it = 0;
@@ -268,14 +271,14 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                     if (p.mode != HOIG_CONV_LOCAL_ATTN) {
                         if (P.cpt_shift < 0 && (p.Cin & 63) == 0) {
                             // all 8 chunks of this k-block share one tap: one bounds test, one base pointer
-                            const __nv_bfloat16 *src = src0;
+                            const T *src = src0;
                             uint32_t bytes = 0;
                             if (valid && tap64 < p.ntaps) {
                                 const bool second = c64 >= p.C0;
                                 const InputView &vw = second ? p.view1 : p.view[p.tap_map[tap64]];
                                 const int iy = gy * p.stride + p.tap_dy[tap64], ix = gx * p.stride + p.tap_dx[tap64];
                                 if (iy >= 0 && iy < vw.H && ix >= 0 && ix < vw.W) {
-                                    src = static_cast<const __nv_bfloat16 *>(vw.base) + view_off(vw, n_img, iy, ix) + (second ? c64 - p.C0 : c64);
+                                    src = static_cast<const T *>(vw.base) + view_off(vw, n_img, iy, ix) + (second ? c64 - p.C0 : c64);
                                     bytes = 16;
                                 }
                             }
@@ -288,7 +291,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const int chunk = kb * 8 + j;
-                                const __nv_bfloat16 *src = src0;
+                                const T *src = src0;
                                 uint32_t bytes = 0;
                                 int tap, c;
                                 if (P.cpt_shift >= 0) { tap = chunk >> P.cpt_shift; c = (chunk - (tap << P.cpt_shift)) * 8; }
@@ -298,7 +301,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                                     const InputView &vw = second ? p.view1 : p.view[p.tap_map[tap]];
                                     const int iy = gy * p.stride + p.tap_dy[tap], ix = gx * p.stride + p.tap_dx[tap];
                                     if (iy >= 0 && iy < vw.H && ix >= 0 && ix < vw.W) {
-                                        src = static_cast<const __nv_bfloat16 *>(vw.base) + view_off(vw, n_img, iy, ix) + (second ? c - p.C0 : c);
+                                        src = static_cast<const T *>(vw.base) + view_off(vw, n_img, iy, ix) + (second ? c - p.C0 : c);
                                         bytes = 16;
                                     }
                                 }
@@ -323,7 +326,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                             const int r = tap / p.KH, sx = tap - r * p.KH;
                             if (c < p.C0) {
                                 const int iy = max(min(gy + r - p.KH / 2, vt.H - 1), 0), ix = max(min(gx + sx - p.KH / 2, vt.W - 1), 0);
-                                cp_async_16(dst_j, static_cast<const __nv_bfloat16 *>(vt.base) + view_off(vt, n_img, iy, ix) + c, 16);
+                                cp_async_16(dst_j, static_cast<const T *>(vt.base) + view_off(vt, n_img, iy, ix) + c, 16);
                             } else {
                                 c -= p.C0;
                                 if (tap != cached_tap) {
@@ -331,7 +334,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                                     t = be_tap(fl[0], fl[1], gy, gx, r, sx, p.KH, vs.H, vs.W);
                                     cached_tap = tap;
                                 }
-                                const __nv_bfloat16 *sb = static_cast<const __nv_bfloat16 *>(vs.base) + (int64_t)n_img * vs.sn + c;
+                                const T *sb = static_cast<const T *>(vs.base) + (int64_t)n_img * vs.sn + c;
                                 float acc[8];
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -342,8 +345,8 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
 #pragma unroll
                                     for (int e = 0; e < 8; ++e) acc[e] = __fmaf_rn(t.w[q], u[e], acc[e]);
                                 }
-                                st_shared_v4(dst_j, pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
-                                             pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+                                st_shared_v4(dst_j, pack2<T>(acc[0], acc[1]), pack2<T>(acc[2], acc[3]),
+                                             pack2<T>(acc[4], acc[5]), pack2<T>(acc[6], acc[7]));
                             }
                         }
                     }
@@ -408,7 +411,10 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
     } else if (warp == MMA_WARP) {
         // ========================================================== MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            // instruction descriptor: D = f32 (bit 4), A/B format bf16 = 1 / f16 = 0 (bits 7-9 / 10-12), K-major A and B,
+            // N >> 3 at bit 17, M >> 4 at bit 24
+            constexpr uint32_t kFmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
+            const uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
                 const uint32_t acc = tcount & 1;
@@ -436,8 +442,8 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
         const int quad = warp & 3, half = warp >> 2;               // half = chunk group of this warp
         const int ngrp = P.tma_a ? 3 : 2;                          // groups share the chunks round-robin
         const int epi_threads = ngrp * 128;
-        const __nv_bfloat16 *res = static_cast<const __nv_bfloat16 *>(p.residual);
-        __nv_bfloat16 *dst = static_cast<__nv_bfloat16 *>(p.dst);
+        const T *res = static_cast<const T *>(p.residual);
+        T *dst = static_cast<T *>(p.dst);
         const bool vec_ok = ((p.ldd & 7) == 0) && (!res || (p.ldr & 7) == 0);
         const int n_chunks = BN / 16;
         uint32_t tcount = 0;
@@ -470,8 +476,8 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                         ncol = n0 - ph * pc;
                         mm = m + (int64_t)(ph >> 1) * p.OWf + (ph & 1);
                     }
-                    __nv_bfloat16 *drow = dst + mm * p.ldd + ncol - c0;
-                    const __nv_bfloat16 *rrow = res ? res + mm * p.ldr + ncol - c0 : nullptr;
+                    T *drow = dst + mm * p.ldd + ncol - c0;
+                    const T *rrow = res ? res + mm * p.ldr + ncol - c0 : nullptr;
                     float v[16];
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
@@ -491,7 +497,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                             for (int j = 0; j < 8; ++j) v[8 + j] += u[j];
                         } else {
                             for (int j = 0; j < 16; ++j)
-                                if (n0 + j < p.Cout) v[j] += __bfloat162float(rrow[c0 + j]);
+                                if (n0 + j < p.Cout) v[j] += DT<T>::ld(rrow + c0 + j);
                         }
                     }
                     if (p.act_table) {
@@ -505,21 +511,23 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                     }
                     uint32_t pk[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                    for (int j = 0; j < 8; ++j) pk[j] = pack2<T>(v[2 * j], v[2 * j + 1]);
                     if (valid) {
                         if (full && vec_ok) {
                             *reinterpret_cast<uint4 *>(drow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                             *reinterpret_cast<uint4 *>(drow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                         } else {
                             for (int j = 0; j < 16; ++j)
-                                if (n0 + j < p.Cout) drow[c0 + j] = __float2bfloat16_rn(v[j]);
+                                if (n0 + j < p.Cout) DT<T>::st(drow + c0 + j, v[j]);
                         }
                     }
                     if (p.stats) {
                         float q[16];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {   // statistics of the values as stored (bf16-rounded)
-                            const float lo = valid ? __uint_as_float(pk[j] << 16) : 0.f, hi = valid ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
+                            float lo, hi;
+                        unpack2<T>(pk[j], lo, hi);
+                        lo = valid ? lo : 0.f; hi = valid ? hi : 0.f;
                             v[2 * j] = lo; v[2 * j + 1] = hi;
                             q[2 * j] = lo * lo; q[2 * j + 1] = hi * hi;
                         }
@@ -587,12 +595,12 @@ EncodeTiledFn encode_fn()
 }
 
 int make_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
-             const cuuint32_t *box, const char *what)
+             const cuuint32_t *box, const char *what, int dtype)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return HOIG_ERR_CUDA; }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), dims, strides_bytes, box,
+    const CUresult r = fn(map, dtype == HOIG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), dims, strides_bytes, box,
                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r); return HOIG_ERR_CUDA; }
@@ -601,7 +609,7 @@ int make_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t *dim
 
 int g_prefetch_tiles = 0;   // measured: L2 prefetch of future tiles HURTS (the streaming convs are L2->SM bandwidth bound, not latency bound)
 
-int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather)
+int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int dtype)
 {
     UmmaParams P;
     P.c = cp;
@@ -638,7 +646,7 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather)
         const cuuint64_t dims[2] = {(cuuint64_t)p.Kpad, (cuuint64_t)p.Npad};
         const cuuint64_t strides[1] = {(cuuint64_t)p.ldw * 2};
         const cuuint32_t box[2] = {BK, (cuuint32_t)P.BN};
-        st = make_map(&map_w, p.weight, 2, dims, strides, box, "weights");
+        st = make_map(&map_w, p.weight, 2, dims, strides, box, "weights", dtype);
         if (st != HOIG_OK) return st;
     }
     for (int v = 0; v < 4; ++v) map_a[v] = map_w;
@@ -650,7 +658,7 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather)
             const InputView &vw = p.view[v];
             const cuuint64_t dims[4] = {(cuuint64_t)p.C0, (cuuint64_t)vw.W, (cuuint64_t)vw.H, (cuuint64_t)p.N};
             const cuuint64_t strides[3] = {(cuuint64_t)vw.sx * 2, (cuuint64_t)vw.sy * 2, (cuuint64_t)vw.sn * 2};
-            st = make_map(&map_a[v], vw.base, 4, dims, strides, box, "activations");
+            st = make_map(&map_a[v], vw.base, 4, dims, strides, box, "activations", dtype);
             if (st != HOIG_OK) return st;
         }
     }
@@ -660,13 +668,15 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather)
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess)
+        if (cudaFuncSetAttribute(conv_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess)
             return check_launch("conv_umma smem attribute");
     }
     const int total = P.m_tiles * P.n_tiles;
     const int grid = total < num_sms ? total : num_sms;
     const size_t smem = (size_t)STG_BYTES + (size_t)P.stages * stage_bytes + 1024;
-    conv_umma_kernel<<<grid, THREADS, smem, stream>>>(P, map_w, map_a[0], map_a[1], map_a[2], map_a[3]);
+    if (dtype == HOIG_F16) conv_umma_kernel<__half><<<grid, THREADS, smem, stream>>>(P, map_w, map_a[0], map_a[1], map_a[2], map_a[3]);
+    else conv_umma_kernel<__nv_bfloat16><<<grid, THREADS, smem, stream>>>(P, map_w, map_a[0], map_a[1], map_a[2], map_a[3]);
     return check_launch("conv_umma_kernel");
 }
 
@@ -686,7 +696,7 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
         if (pf) g_prefetch_tiles = atoi(pf);
     }
     for (int i = 0; i < plan.n; ++i) {
-        st = launch_one(plan.launch[i], stream, g_force_gather);
+        st = launch_one(plan.launch[i], stream, g_force_gather, d->dtype);
         if (st != HOIG_OK) return st;
     }
     return HOIG_OK;

@@ -489,6 +489,7 @@ template <typename F> int dispatch(int dtype, F f)
 {
     if (dtype == HOIG_F32) return f((float *)nullptr);
     if (dtype == HOIG_BF16) return f((__nv_bfloat16 *)nullptr);
+    if (dtype == HOIG_F16) return f((__half *)nullptr);
     set_error("bad dtype %d", dtype);
     return HOIG_ERR_INVALID;
 }

@@ -159,8 +159,8 @@ class GeneratorB200(nn.Module):
         self.attn_layers = list(attn_layers)
         self.conv_dim = conv_dim
         self.dims = dict(bg_dim=bg_dim, img_dim=img_dim, obj_dim=obj_dim, img_cond_dim=img_cond_dim, obj_cond_dim=obj_cond_dim)
-        if dtype not in (torch.bfloat16, torch.float32):
-            raise ValueError("GeneratorB200: dtype must be torch.bfloat16 (tensor-core path) or torch.float32 (parity path)")
+        if dtype not in (torch.bfloat16, torch.float16, torch.float32):
+            raise ValueError("GeneratorB200: dtype must be torch.bfloat16 / torch.float16 (tensor-core path) or torch.float32 (parity path)")
         self.compute_dtype = dtype
         # K (= taps x input channels) from which InstanceNorm statistics are accumulated in the conv epilogue
         self.stats_epilogue_min_k = int(os.environ.get("HOIG_STATS_EPILOGUE_MIN_K", "0"))
@@ -421,7 +421,7 @@ class GeneratorB200(nn.Module):
         hidden = self._new(n, h, h, ATTN_HIDDEN)
         w2 = self._cached(p + "2#w2", [self._p(p + "2.weight")],
                           lambda: self._p(p + "2.weight").detach().float().reshape(ATTN_K * ATTN_K, ATTN_HIDDEN).contiguous())
-        if self.compute_dtype == torch.bfloat16:
+        if self.compute_dtype != torch.float32:
             # tensor-core path: extract the 2 x 25 taps once (bandwidth-bound), then the k5s5 conv is a plain
             # TMA-fed GEMM over K = 25*2C and attn_finish re-reads the source taps instead of re-sampling them
             unf = ops.attn_unfold(src, tsf, flows[key], self._new(n, h, h, 2 * ATTN_K * ATTN_K * c), ATTN_K)

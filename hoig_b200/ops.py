@@ -14,9 +14,9 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, CONV, CONV_LOCAL_ATTN,  # noqa: F401
-                   CONV_TRANSPOSED, HOIG_BF16, HOIG_F32, ConvDesc)
+                   CONV_TRANSPOSED, HOIG_BF16, HOIG_F16, HOIG_F32, ConvDesc)
 
-_DT = {torch.float32: HOIG_F32, torch.bfloat16: HOIG_BF16}
+_DT = {torch.float32: HOIG_F32, torch.bfloat16: HOIG_BF16, torch.float16: HOIG_F16}
 
 
 def _stream() -> int:

@@ -14,8 +14,8 @@
  * (n,y,x,c) of a tensor with pixel stride `ld` lives at
  * base[((n*H + y)*W + x)*ld + c].  `ld >= C` lets a tensor be a channel slice
  * of a wider buffer (the U-Net skip concatenations are never materialised
- * separately).  dtype: HOIG_F32 (SIMT fp32 parity path) or HOIG_BF16
- * (tcgen05 tensor-core path, fp32 accumulate).
+ * separately).  dtype: HOIG_F32 (SIMT fp32 parity path), HOIG_BF16 or HOIG_F16
+ * (tcgen05 tensor-core path, kind::f16, fp32 accumulate; same rate, 8 vs 11 mantissa bits).
  */
 #ifndef HOIG_B200_H_
 #define HOIG_B200_H_
@@ -37,7 +37,7 @@ typedef enum {
     HOIG_ERR_ARCH = -4       /* device is not sm_100 */
 } hoigStatus;
 
-typedef enum { HOIG_F32 = 0, HOIG_BF16 = 1 } hoigDType;
+typedef enum { HOIG_F32 = 0, HOIG_BF16 = 1, HOIG_F16 = 2 } hoigDType;
 typedef enum { HOIG_ACT_NONE = 0, HOIG_ACT_RELU = 1, HOIG_ACT_LEAKY = 2, HOIG_ACT_TANH = 3, HOIG_ACT_SIGMOID = 4 } hoigAct;
 typedef enum { HOIG_CONV = 0, HOIG_CONV_TRANSPOSED = 1, HOIG_CONV_LOCAL_ATTN = 2 } hoigConvMode;
 

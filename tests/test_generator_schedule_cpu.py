@@ -93,6 +93,20 @@ def test_schedule_bf16_emulation_within_rel_l2(monkeypatch):
         assert rel <= 3e-2, (i, rel)   # bf16 storage at 64x64 / conv_dim 16; the GPU gate (1e-2) is on the full config
 
 
+def test_schedule_f16_emulation_within_rel_l2(monkeypatch):
+    emu_ops.install(monkeypatch)
+    table = dict(spade_layers=(1, 1, 0, 0), attn_layers=tuple(range(1, 10)))
+    sd = gr.init_state_dict(seed=0, jitter=0.05, **SMALL, **table)
+    g = create("generator_spade_attn", dtype=torch.float16, **SMALL)
+    g.load_state_dict(sd)
+    inp = synth.generator_inputs(1, seed=1, size=64)
+    outs = g(**inp)
+    with torch.no_grad():
+        ref = gr.generator_forward(sd, **inp, **table)
+    for i, (a, b) in enumerate(zip(outs, ref)):
+        assert ((a - b).norm() / b.norm()).item() <= 1e-2, i
+
+
 def test_packed_cache_invalidates_on_update(monkeypatch):
     emu_ops.install(monkeypatch)
     g = create("generator_base", dtype=torch.float32, **SMALL)

@@ -99,6 +99,19 @@ def test_bf16_full_config_rel_l2(golden_dir):
         assert np.linalg.norm(a - b) / np.linalg.norm(b) <= BF16_REL_L2
 
 
+def test_f16_full_config_rel_l2(golden_dir):
+    """fp16 storage / fp16 tensor-core operands (same kernels, same rate as bf16, 11-bit mantissa): meets north_star's
+    relative L2 <= 1e-2 on every output, against the fp32 CUDA path and against the unmodified-reference fixture."""
+    sd, inp, o16 = _run("generator_spade_attn", FULL, torch.float16, 1, 256)
+    _, _, o32 = _run("generator_spade_attn", FULL, torch.float32, 1, 256)
+    _, rel = _stats(o16, o32)
+    assert rel <= 1e-2
+    g = np.load(os.path.join(golden_dir, "generator_full.npz"))
+    for i, o in enumerate(o16):
+        a, b = o[:, :, ::8, ::8].numpy(), g[f"out{i}_sample"]
+        assert np.linalg.norm(a - b) / np.linalg.norm(b) <= 1e-2
+
+
 def test_batch_slot_isolation_bf16():
     """Idea borrowed from thirdparty/neural_renderer/tests/utils.py:11-27: a sample's result must not depend on
     its batch slot or on its neighbours (InstanceNorm statistics are per sample)."""

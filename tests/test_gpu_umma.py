@@ -84,3 +84,20 @@ def test_umma_matches_simt_bf16_bitwise_mostly():
     print("umma vs simt: maxabs", diff.max().item(), "fraction differing", (diff > 0).float().mean().item())
     # fp32 accumulation order differs (tile-K vs 16-wide K steps): at most one bf16 ulp (2^-8 relative) apart
     assert (diff <= 2.0 ** -7 * b.float().abs() + 1e-3).all()
+
+
+F16_CASES = [c for c in CONV_CASES if c[0] in ("3x3_s1_c64", "3x3_s1_k4608", "3x3_s2", "7x7_stem_c8", "7x1_stem_c64", "convT_3x3_s2",
+                                                "attn_c64", "1x1_k3200_attn_gemm", "7x7_heads_merged_act_table", "3x3_s1_c128_n512_bias_res")]
+
+
+@pytest.mark.parametrize("case", F16_CASES, ids=[c[0] for c in F16_CASES])
+def test_conv_f16_umma(case):
+    """fp16 operands (kind::f16 with the f16 format bits) through the same kernel template."""
+    out, ref, st, st_ref = _run_conv(case, torch.float16)
+    Cout = case[4]
+    ok, rel = _report("umma f16 " + case[0], out[..., :Cout], ref[..., :Cout], 3e-3, 3e-3)
+    if not ok:
+        _dump_pattern(case[0], out[..., :Cout], ref[..., :Cout])
+    assert ok and rel < 2e-3
+    if st is not None:
+        assert torch.allclose(st.cpu(), st_ref, rtol=1e-3, atol=0.2)
