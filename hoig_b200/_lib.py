@@ -40,6 +40,12 @@ class ConvDesc(Structure):
     ]
 
 
+class HaloConvSeg(Structure):
+    """Mirror of ``hoigHaloConvSeg``."""
+    _fields_ = [("src", c_void_p), ("ld", c_int64), ("N", c_int), ("Hp", c_int), ("Wp", c_int), ("C", c_int),
+                ("weight", c_void_p), ("dst", c_void_p), ("ldd", c_int64)]
+
+
 _SIGNATURES = {
     # name: (restype, argtypes)
     "hoig_version": (c_char_p, []),
@@ -73,6 +79,11 @@ _SIGNATURES = {
                                  c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_void_p]),
     "hoig_attn_unfold": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                  c_int, c_int, c_void_p]),
+    "hoig_replicate_pad": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "hoig_conv2d_halo": (c_int, [c_int, c_int, c_int, c_int, POINTER(HaloConvSeg), c_int, c_void_p]),
+    "hoig_set_halo_variant": (None, [c_int]),
+    "hoig_attn_combine": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                  c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "hoig_grid_sample": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int,
                                  c_int, c_int, c_void_p]),
     "hoig_composite": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p]),

@@ -25,6 +25,7 @@ int check_launch(const char *what)
 
 int conv2d_simt(const hoigConvDesc *d, cudaStream_t stream);
 int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream);
+int conv2d_halo(int dtype, int KH, int KW, int Cout, const hoigHaloConvSeg *segs, int nsegs, cudaStream_t stream);
 
 }  // namespace hoig
 
@@ -57,4 +58,9 @@ extern "C" int hoig_conv2d_simt(const hoigConvDesc *desc, hoigStream_t stream)
 {
     if (!desc) { hoig::set_error("conv2d: null descriptor"); return HOIG_ERR_INVALID; }
     return hoig::conv2d_simt(desc, hoig::as_stream(stream));
+}
+
+extern "C" int hoig_conv2d_halo(int dtype, int KH, int KW, int Cout, const hoigHaloConvSeg *segs, int nsegs, hoigStream_t stream)
+{
+    return hoig::conv2d_halo(dtype, KH, KW, Cout, segs, nsegs, hoig::as_stream(stream));
 }

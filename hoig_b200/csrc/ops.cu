@@ -437,6 +437,169 @@ attn_unfold_kernel(const T *__restrict__ src, int64_t lds, const T *__restrict__
     }
 }
 
+// block_extractor_kernel.cu:62-69 clamping materialised once: dst[n,y,x,:] = src[n, clamp(y-pad), clamp(x-pad), :]
+template <typename T>
+__global__ void replicate_pad_kernel(const T *__restrict__ src, int64_t lds, T *__restrict__ dst, int64_t ldd, int N, int h, int C, int pad)
+{
+    const int hp = h + 2 * pad, chunks = C / 8;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)N * hp * hp * chunks) return;
+    const int cc = (int)(i % chunks);
+    const int64_t pix = i / chunks;
+    const int x = (int)(pix % hp), y = (int)((pix / hp) % hp), n = (int)(pix / ((int64_t)hp * hp));
+    const int sy = max(min(y - pad, h - 1), 0), sx = max(min(x - pad, h - 1), 0);
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src + (((int64_t)n * h + sy) * h + sx) * lds + cc * 8);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst + pix * ldd + cc * 8);
+    if (sizeof(T) == 2) d4[0] = s4[0];
+    else { d4[0] = s4[0]; d4[1] = s4[1]; }
+}
+
+__device__ __forceinline__ void load4(const __nv_bfloat16 *p, float v[4])
+{
+    const uint2 r = *reinterpret_cast<const uint2 *>(p);
+    unpack2<__nv_bfloat16>(r.x, v[0], v[1]); unpack2<__nv_bfloat16>(r.y, v[2], v[3]);
+}
+__device__ __forceinline__ void load4(const __half *p, float v[4])
+{
+    const uint2 r = *reinterpret_cast<const uint2 *>(p);
+    unpack2<__half>(r.x, v[0], v[1]); unpack2<__half>(r.y, v[2], v[3]);
+}
+__device__ __forceinline__ void load4(const float *p, float v[4])
+{
+    const float4 r = *reinterpret_cast<const float4 *>(p);
+    v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+}
+
+// extract_attn.py:24-28 with the k5s5 conv commuted through the bilinear interpolation (include/hoig_b200.h,
+// "local attention, tensor-core formulation").  Eight lanes per pixel, four pixels per warp:
+//   hidden (128 ch, 16 per lane) = LeakyReLU(Gt(p) + sum_q w_q Gs(p0+q) + b1)
+//   logits = W2 hidden + b2 (partial dot products per lane, butterfly over the 8 lanes), softmax in registers
+//   coef   = the KK attention weights x the 4 bilinear weights folded into one (K+1)^2 patch
+//   dst    = tgt + (1/KK) sum_u coef[u] * src[clamp(p0 - K/2 + u)]
+template <typename T, int KK>
+__global__ void __launch_bounds__(256)
+attn_combine_kernel(const T *__restrict__ gt, int64_t ldgt, const T *__restrict__ gs, int64_t ldgs, const float *__restrict__ b1,
+                    const float *__restrict__ w2, const float *__restrict__ b2, const T *__restrict__ src, int64_t lds,
+                    const float *__restrict__ flow, const T *__restrict__ tgt, int64_t ldt, T *__restrict__ dst, int64_t ldd,
+                    int64_t npix_total, int h, int C)
+{
+    constexpr int K = (KK == 25) ? 5 : 3;
+    constexpr int HID = 128, PK = K + 1, R = K / 2;
+    __shared__ __align__(16) float s_w2[KK][HID];
+    __shared__ __align__(16) float s_b1[HID];
+    __shared__ float s_b2[KK];
+    for (int i = threadIdx.x; i < KK * HID; i += blockDim.x) (&s_w2[0][0])[i] = w2[i];
+    for (int i = threadIdx.x; i < HID; i += blockDim.x) s_b1[i] = b1[i];
+    for (int i = threadIdx.x; i < KK; i += blockDim.x) s_b2[i] = b2[i];
+    __syncthreads();
+    const int lane = threadIdx.x % 32, sub = lane & 7, grp = lane >> 3;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32, nwarps = (int64_t)gridDim.x * blockDim.x / 32;
+    const int hpt = h + 2 * R, hps = h + 4 * R;
+    for (int64_t base = warp0 * 4; base < npix_total; base += nwarps * 4) {
+        const bool valid = base + grp < npix_total;
+        const int64_t pix = valid ? base + grp : npix_total - 1;   // idle groups shadow the last pixel: the warp stays converged
+        const int x = (int)(pix % h), y = (int)((pix / h) % h);
+        const int64_t n = pix / ((int64_t)h * h);
+        // centre tap of be_tap(): all k*k taps share these fractions
+        const float dx = __fadd_rn(__fadd_rn(flow[pix * 2], 0.f), (float)x), dy = __fadd_rn(__fadd_rn(flow[pix * 2 + 1], 0.f), (float)y);
+        const float fdx = floorf(dx), fdy = floorf(dy);
+        const float wx1 = __fsub_rn(dx, fdx), wx0 = __fsub_rn(1.f, wx1), wy1 = __fsub_rn(dy, fdy), wy0 = __fsub_rn(1.f, wy1);
+        const int x0 = (int)fminf(fmaxf(fdx, -(float)(K + 2)), (float)(h + K + 2));
+        const int y0 = (int)fminf(fmaxf(fdy, -(float)(K + 2)), (float)(h + K + 2));
+
+        // ---- hidden: channels 32*i + 4*sub + j
+        float hv[16];
+        {
+            const T *g = gt + ((n * hpt + y + R) * hpt + x + R) * ldgt + 4 * sub;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                load4(g + 32 * i, hv + 4 * i);
+                const float4 bv = *reinterpret_cast<const float4 *>(&s_b1[32 * i + 4 * sub]);
+                hv[4 * i] += bv.x; hv[4 * i + 1] += bv.y; hv[4 * i + 2] += bv.z; hv[4 * i + 3] += bv.w;
+            }
+#pragma unroll
+            for (int qy = 0; qy < 2; ++qy)
+#pragma unroll
+                for (int qx = 0; qx < 2; ++qx) {
+                    const int cy = max(min(y0 + qy, h - 1 + R), -R) + 2 * R, cx = max(min(x0 + qx, h - 1 + R), -R) + 2 * R;
+                    const float w = __fmul_rn(qx ? wx1 : wx0, qy ? wy1 : wy0);
+                    const T *gq = gs + ((n * hps + cy) * hps + cx) * ldgs + 4 * sub;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float u[4];
+                        load4(gq + 32 * i, u);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) hv[4 * i + j] = fmaf(w, u[j], hv[4 * i + j]);
+                    }
+                }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) hv[j] = hv[j] > 0.f ? hv[j] : 0.01f * hv[j];
+        }
+        // ---- logits + softmax (every lane of the group ends up with all KK weights)
+        float a[KK];
+#pragma unroll
+        for (int t = 0; t < KK; ++t) {
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 wv = *reinterpret_cast<const float4 *>(&s_w2[t][32 * i + 4 * sub]);
+                acc = fmaf(hv[4 * i], wv.x, acc); acc = fmaf(hv[4 * i + 1], wv.y, acc);
+                acc = fmaf(hv[4 * i + 2], wv.z, acc); acc = fmaf(hv[4 * i + 3], wv.w, acc);
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            a[t] = acc + s_b2[t];
+        }
+        float mx = a[0];
+#pragma unroll
+        for (int t = 1; t < KK; ++t) mx = fmaxf(mx, a[t]);
+        float den = 0.f;
+#pragma unroll
+        for (int t = 0; t < KK; ++t) { a[t] = expf(a[t] - mx); den += a[t]; }
+        const float inv = 1.0f / (den * (float)KK);
+        // ---- fold attention weights x bilinear weights into the (K+1)^2 patch
+        float coef[PK][PK];
+#pragma unroll
+        for (int uy = 0; uy < PK; ++uy)
+#pragma unroll
+            for (int ux = 0; ux < PK; ++ux) {
+                float c = 0.f;
+                if (uy < K && ux < K) c = fmaf(a[uy * K + ux], wy0 * wx0, c);
+                if (uy < K && ux > 0) c = fmaf(a[uy * K + ux - 1], wy0 * wx1, c);
+                if (uy > 0 && ux < K) c = fmaf(a[(uy - 1) * K + ux], wy1 * wx0, c);
+                if (uy > 0 && ux > 0) c = fmaf(a[(uy - 1) * K + ux - 1], wy1 * wx1, c);
+                coef[uy][ux] = c * inv;
+            }
+        int poff[PK];   // x offsets (elements) of the patch columns
+#pragma unroll
+        for (int u = 0; u < PK; ++u) poff[u] = max(min(x0 - R + u, h - 1), 0);
+        const T *splane = src + n * (int64_t)h * h * lds;
+        for (int cc = sub; cc < C / 8; cc += 8) {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+            for (int uy = 0; uy < PK; ++uy) {
+                const int py = max(min(y0 - R + uy, h - 1), 0);
+                const T *srow = splane + (int64_t)py * h * lds + cc * 8;
+#pragma unroll
+                for (int ux = 0; ux < PK; ++ux) {
+                    float u[8];
+                    load8(srow + (int64_t)poff[ux] * lds, u);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(coef[uy][ux], u[j], acc[j]);
+                }
+            }
+            float tv[8];
+            load8(tgt + pix * ldt + cc * 8, tv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tv[j] += acc[j];
+            if (valid) store8(dst + pix * ldd + cc * 8, tv);
+        }
+    }
+}
+
 // x7[b,y,x, s*C + c] = x[b,c,y,x+s-k/2]  (zero outside the row / beyond k*C), from the NCHW f32 input
 template <typename T>
 __global__ void hunfold_kernel(const float *__restrict__ src, int B, int C, int H, int W, int k, T *__restrict__ dst, int64_t ldd, int Cpad)
@@ -708,5 +871,46 @@ extern "C" int hoig_hfold_nchw(const void *z, int64_t ldz, int dtype, int B, int
         using T = std::remove_pointer_t<decltype(tag)>;
         hfold_kernel<T><<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>((const T *)z, ldz, B, H, W, G, k, act_table, segs);
         return check_launch("hfold_kernel");
+    });
+}
+
+extern "C" int hoig_replicate_pad(const void *src, int64_t lds, void *dst, int64_t ldd, int dtype, int N, int h, int C, int pad,
+                                  hoigStream_t stream)
+{
+    HOIG_REQUIRE(src && dst && pad >= 0, "replicate_pad: bad argument");
+    HOIG_REQUIRE(C % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0 && lds >= C && ldd >= C, "replicate_pad: channels / strides must be multiples of 8");
+    const int64_t n = (int64_t)N * (h + 2 * pad) * (h + 2 * pad) * (C / 8);
+    if (n == 0) return HOIG_OK;
+    return dispatch(dtype, [&](auto *tag) {
+        using T = std::remove_pointer_t<decltype(tag)>;
+        replicate_pad_kernel<T><<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>((const T *)src, lds, (T *)dst, ldd, N, h, C, pad);
+        return check_launch("replicate_pad_kernel");
+    });
+}
+
+extern "C" int hoig_attn_combine(const void *gt, int64_t ldgt, const void *gs, int64_t ldgs, int Chid, const float *b1, const float *w2,
+                                 const float *b2, const void *src, int64_t lds, const float *flow, const void *tgt, int64_t ldt,
+                                 void *dst, int64_t ldd, int dtype, int N, int h, int C, int k, hoigStream_t stream)
+{
+    HOIG_REQUIRE(gt && gs && b1 && w2 && b2 && src && flow && tgt && dst, "attn_combine: null pointer");
+    HOIG_REQUIRE(Chid == 128, "attn_combine: hidden width %d not supported (extract_attn.py:11 uses 128)", Chid);
+    HOIG_REQUIRE(k == 5 || k == 3, "attn_combine: kernel size %d not supported (3 or 5)", k);
+    HOIG_REQUIRE(C % 8 == 0 && lds % 8 == 0 && ldt % 8 == 0 && ldd % 8 == 0 && ldgt % 4 == 0 && ldgs % 4 == 0,
+                 "attn_combine: channels / strides must be multiples of 8");
+    const int64_t npix = (int64_t)N * h * h;
+    if (npix == 0) return HOIG_OK;
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int64_t want = (npix + 31) / 32;
+    const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+    return dispatch(dtype, [&](auto *tag) {
+        using T = std::remove_pointer_t<decltype(tag)>;
+        if (k == 5)
+            attn_combine_kernel<T, 25><<<grid, 256, 0, as_stream(stream)>>>((const T *)gt, ldgt, (const T *)gs, ldgs, b1, w2, b2, (const T *)src,
+                                                                           lds, flow, (const T *)tgt, ldt, (T *)dst, ldd, npix, h, C);
+        else
+            attn_combine_kernel<T, 9><<<grid, 256, 0, as_stream(stream)>>>((const T *)gt, ldgt, (const T *)gs, ldgs, b1, w2, b2, (const T *)src,
+                                                                          lds, flow, (const T *)tgt, ldt, (T *)dst, ldd, npix, h, C);
+        return check_launch("attn_combine_kernel");
     });
 }

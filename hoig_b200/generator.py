@@ -164,6 +164,7 @@ class GeneratorB200(nn.Module):
         self.compute_dtype = dtype
         # K (= taps x input channels) from which InstanceNorm statistics are accumulated in the conv epilogue
         self.stats_epilogue_min_k = int(os.environ.get("HOIG_STATS_EPILOGUE_MIN_K", "0"))
+        self.attn_commuted = os.environ.get("HOIG_ATTN_COMMUTED", "1") != "0"   # 0: tap-unfold + 1x1 GEMM attention
         self._layout = parameter_layout(bg_dim, img_dim, obj_dim, img_cond_dim, obj_cond_dim, conv_dim, repeat_num,
                                         self.n_down, self.spade_layers, self.attn_layers)
         for top in ("bg_model", "obj_model", "src_model", "tsf_model"):
@@ -421,6 +422,19 @@ class GeneratorB200(nn.Module):
         hidden = self._new(n, h, h, ATTN_HIDDEN)
         w2 = self._cached(p + "2#w2", [self._p(p + "2.weight")],
                           lambda: self._p(p + "2.weight").detach().float().reshape(ATTN_K * ATTN_K, ATTN_HIDDEN).contiguous())
+        if self.compute_dtype != torch.float32 and c % 64 == 0 and self.attn_commuted:
+            # tensor-core path: the k5s5 conv commutes with the bilinear interpolation (hoig_b200.h, "local attention,
+            # tensor-core formulation"): two dense 5x5 convs over replicate-padded rasters (one launch, activation
+            # halo reused across taps), then one kernel for interpolation + 1x1 conv + softmax + weighted source patch
+            r = ATTN_K // 2
+            prm = self._p(p + "0.weight")
+            wt = self._cached(p + "0#wt", [prm], lambda: pack_conv_weight(prm.detach()[:, :c], self.compute_dtype))
+            ws = self._cached(p + "0#ws", [prm], lambda: pack_conv_weight(prm.detach()[:, c:], self.compute_dtype))
+            tpad = ops.replicate_pad(tsf, self._new(n, h + 2 * r, h + 2 * r, c), r)
+            spad = ops.replicate_pad(src, self._new(n, h + 4 * r, h + 4 * r, c), 2 * r)
+            gt, gs = ops.conv2d_halo([(tpad, wt, self._new(n, h + 2 * r, h + 2 * r, ATTN_HIDDEN)),
+                                      (spad, ws, self._new(n, h + 4 * r, h + 4 * r, ATTN_HIDDEN))], ATTN_K, ATTN_K, ATTN_HIDDEN)
+            return ops.attn_combine(gt, gs, self._f32(p + "0.bias"), w2, self._f32(p + "2.bias"), src, flows[key], tsf, tsf, ATTN_K)
         if self.compute_dtype != torch.float32:
             # tensor-core path: extract the 2 x 25 taps once (bandwidth-bound), then the k5s5 conv is a plain
             # TMA-fed GEMM over K = 25*2C and attn_finish re-reads the source taps instead of re-sampling them

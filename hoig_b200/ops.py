@@ -276,6 +276,55 @@ def attn_unfold(src: torch.Tensor, tgt: torch.Tensor, flow: torch.Tensor, out: t
     return out
 
 
+def replicate_pad(x: torch.Tensor, out: torch.Tensor, pad: int) -> torch.Tensor:
+    """out (N,h+2p,h+2p,C) = x with its edge pixels replicated ``pad`` times (BlockExtractor's clamped taps)."""
+    N, h, _, C = x.shape
+    xp, ldx = _nhwc(x, "x")
+    op, ldo = _nhwc(out, "out")
+    if out.shape != (N, h + 2 * pad, h + 2 * pad, C):
+        raise ValueError(f"replicate_pad: out has shape {tuple(out.shape)}")
+    _lib.check(_lib.lib().hoig_replicate_pad(xp, ldx, op, ldo, _dt(x), N, h, C, pad, _stream()), "replicate_pad")
+    return out
+
+
+def conv2d_halo(segments, kh: int, kw: int, cout: int):
+    """Dense kh x kw stride-1 conv over padded rasters on the tensor cores (raw accumulators, 16-bit dtypes).
+
+    ``segments``: one or two ``(x, packed_weight, out)`` with x (N,Hp,Wp,C) and out (N,Hp,Wp,cout); both run in ONE launch.
+    Interior pixels (>= k//2 from the raster border) get the exact convolution, border pixels are don't-care."""
+    segs = (_lib.HaloConvSeg * len(segments))()
+    for sg, (x, w, out) in zip(segs, segments):
+        xp, ldx = _nhwc(x, "x")
+        op, ldo = _nhwc(out, "out")
+        N, Hp, Wp, C = x.shape
+        if out.shape[:3] != x.shape[:3] or out.shape[3] != cout or w.dtype != x.dtype or out.dtype != x.dtype:
+            raise ValueError("conv2d_halo: out must be (N,Hp,Wp,cout) of the input dtype")
+        if tuple(w.shape) != (cout, kh * kw * C) or not w.is_contiguous():
+            raise ValueError(f"conv2d_halo: packed weight must be ({cout},{kh * kw * C}), got {tuple(w.shape)}")
+        sg.src, sg.ld, sg.N, sg.Hp, sg.Wp, sg.C = xp, ldx, N, Hp, Wp, C
+        sg.weight, sg.dst, sg.ldd = w.data_ptr(), op, ldo
+    dt = _dt(segments[0][0])
+    _lib.check(_lib.lib().hoig_conv2d_halo(dt, kh, kw, cout, segs, len(segments), _stream()), "conv2d_halo")
+    return [s[2] for s in segments]
+
+
+def attn_combine(gt: torch.Tensor, gs: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, src: torch.Tensor,
+                 flow: torch.Tensor, tgt: torch.Tensor, out: torch.Tensor, k: int) -> torch.Tensor:
+    """out = tgt + local-attention warp of src, from the commuted k x k convs gt (target) and gs (source, extended grid)."""
+    N, h, _, C = src.shape
+    gtp, ldgt = _nhwc(gt, "gt")
+    gsp, ldgs = _nhwc(gs, "gs")
+    sp, lds = _nhwc(src, "src")
+    tp, ldt = _nhwc(tgt, "tgt")
+    op, ldo = _nhwc(out, "out")
+    if gt.shape[1] != h + k - 1 or gs.shape[1] != h + 2 * (k - 1) or gt.shape[3] != gs.shape[3]:
+        raise ValueError("attn_combine: gt must be (N,h+k-1,h+k-1,Chid) and gs (N,h+2k-2,h+2k-2,Chid)")
+    _lib.check(_lib.lib().hoig_attn_combine(gtp, ldgt, gsp, ldgs, gt.shape[3], _f32c(b1, "b1"), _f32c(w2, "w2"), _f32c(b2, "b2"),
+                                            sp, lds, _f32c(flow, "flow"), tp, ldt, op, ldo, _dt(src), N, h, C, k, _stream()),
+               "attn_combine")
+    return out
+
+
 def grid_sample(x: torch.Tensor, grid: torch.Tensor, out: torch.Tensor, tgt: Optional[torch.Tensor] = None):
     N, h, _, C = x.shape
     xp, ldx = _nhwc(x, "x")

@@ -180,6 +180,41 @@ int hoig_attn_finish(const void *hidden, int64_t ldh, int Chid, const float *w2,
  * it (`unfold`) instead of re-sampling. */
 int hoig_attn_unfold(const void *src, int64_t lds, const void *tgt, int64_t ldt, const float *flow, void *out,
                      int64_t ldo, int dtype, int N, int h, int C, int k, hoigStream_t stream);
+/* ---- local attention, tensor-core formulation (extract_attn.py:19-28 re-associated) -----------------------
+ * The k x k stride-k conv over cat[BlockExtractor(tgt,0), BlockExtractor(src,flow)] is linear in the extracted
+ * taps and every tap of one pixel shares the same bilinear fractions (block_extractor_kernel.cu:57-82), so
+ *     conv(cat[...])(p) = Gt(p) + sum_{q in 2x2} w_q(p) * Gs(p0 + q),
+ * with Gt = k x k conv of the replicate-padded target, Gs = k x k conv of the replicate-padded source evaluated on
+ * the (h+k-1)^2 extended grid (each tap clamps on its own, so a corner up to k/2 pixels outside the image still
+ * sees distinct taps), p0 = floor(p + flow(p)).  Same sum, different association: results agree with the
+ * reference to rounding (tests gate the tensor-core path at the north-star tolerance); the fp32 parity path keeps
+ * the reference's order of operations (HOIG_CONV_LOCAL_ATTN).
+ *
+ * hoig_replicate_pad: dst[n, y, x, :] = src[n, clamp(y-pad), clamp(x-pad), :], dst (N, h+2pad, h+2pad, C). */
+int hoig_replicate_pad(const void *src, int64_t lds, void *dst, int64_t ldd, int dtype, int N, int h, int C, int pad,
+                       hoigStream_t stream);
+/* Dense KH x KW stride-1 convolution over padded rasters (N, Hp, Wp, C) -> (N, Hp, Wp, Cout), bf16 / fp16 tensor
+ * cores, raw accumulators (no bias / activation).  out[m] = sum_{r,s,c} W[n][(r*KW+s)*C + c] * in[m + (r-KH/2)*Wp +
+ * (s-KW/2)][c] over the flattened pixel index m (zero outside the tensor): pixels at least KH/2 rows and KW/2
+ * columns inside their image get the exact convolution, the others hold finite don't-care values.  `weight` is the
+ * packed (Cout, KH*KW*C) matrix of hoig_conv_packed_dims.  Up to two problems (segments) share one launch. */
+typedef struct hoigHaloConvSeg {
+    const void *src; int64_t ld;
+    int N, Hp, Wp, C;
+    const void *weight;
+    void *dst; int64_t ldd;
+} hoigHaloConvSeg;
+int hoig_conv2d_halo(int dtype, int KH, int KW, int Cout, const hoigHaloConvSeg *segs, int nsegs, hoigStream_t stream);
+/* Test hook: A-operand strategy of hoig_conv2d_halo (0 = one box per kernel row, taps by shifted descriptors;
+ * 2 = one box per tap). */
+void hoig_set_halo_variant(int v);
+/* Tail of the attention block for the formulation above: hidden = LeakyReLU(Gt + bilinear(Gs) + b1); 1x1 conv to
+ * k*k logits; softmax; dst = tgt + (1/k^2) * sum_t a_t * BlockExtractor(src,flow)_t, the 25 x 4 bilinear taps
+ * folded into one (k+1)^2 patch of coefficients.  gt: (N, h+k-1, h+k-1, Chid) with the image at offset k/2;
+ * gs: (N, h+2(k-1), h+2(k-1), Chid) with extended-grid cell (0,0) at offset k/2; src/tgt/dst (N,h,h,C). */
+int hoig_attn_combine(const void *gt, int64_t ldgt, const void *gs, int64_t ldgs, int Chid, const float *b1, const float *w2,
+                      const float *b2, const void *src, int64_t lds, const float *flow, const void *tgt, int64_t ldt,
+                      void *dst, int64_t ldd, int dtype, int N, int h, int C, int k, hoigStream_t stream);
 /* generator.py:475-478 stn: F.grid_sample(x, grid) bilinear / zeros / align_corners=False;
  * x, dst NHWC (N,h,h,C); grid (N,h,h,2) f32; dst = tgt + sample when tgt != NULL. */
 int hoig_grid_sample(const void *x, int64_t ldx, const float *grid, const void *tgt, int64_t ldt,

@@ -156,6 +156,57 @@ def attn_finish(hidden, w2, b2, src, flow, tgt, out, k, unfold=None):
     return out
 
 
+def replicate_pad(x, out, pad):
+    y = F.pad(x.float().permute(0, 3, 1, 2), (pad, pad, pad, pad), mode="replicate").permute(0, 2, 3, 1)
+    out.copy_(y.to(out.dtype))
+    return out
+
+
+def conv2d_halo(segments, kh, kw, cout):
+    """Contract: exact conv at pixels >= k//2 inside the raster; the border ring is don't-care (NaN here, so a
+    consumer that reads it fails the parity tests)."""
+    outs = []
+    for x, w, out in segments:
+        c = x.shape[3]
+        wt = unpack_weight(w, cout, kh, kw, c)
+        y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, None, padding=(kh // 2, kw // 2)).permute(0, 2, 3, 1).contiguous()
+        ry, rx = kh // 2, kw // 2
+        y[:, :ry] = float("nan"); y[:, y.shape[1] - ry:] = float("nan")
+        y[:, :, :rx] = float("nan"); y[:, :, y.shape[2] - rx:] = float("nan")
+        out.copy_(y.to(out.dtype))
+        outs.append(out)
+    return outs
+
+
+def attn_combine(gt, gs, b1, w2, b2, src, flow, tgt, out, k):
+    """include/hoig_b200.h "local attention, tensor-core formulation", restated with torch indexing."""
+    n, h, _, c = src.shape
+    r = k // 2
+    ys, xs = torch.meshgrid(torch.arange(h), torch.arange(h), indexing="ij")
+    dx, dy = flow[..., 0] + xs.float(), flow[..., 1] + ys.float()
+    fx, fy = torch.floor(dx), torch.floor(dy)
+    wx, wy = [1 - (dx - fx), dx - fx], [1 - (dy - fy), dy - fy]
+    x0, y0 = fx.clamp(-(k + 2), h + k + 2).long(), fy.clamp(-(k + 2), h + k + 2).long()
+    b = torch.arange(n).view(n, 1, 1)
+    hid = gt[:, r:r + h, r:r + h].float() + b1
+    for qy in range(2):
+        for qx in range(2):
+            cy, cx = (y0 + qy).clamp(-r, h - 1 + r) + 2 * r, (x0 + qx).clamp(-r, h - 1 + r) + 2 * r
+            hid = hid + (wy[qy] * wx[qx])[..., None] * gs[b, cy, cx].float()
+    hid = F.leaky_relu(hid, 0.01)
+    a = F.softmax(hid @ w2.t() + b2, 3)
+    res = torch.zeros(n, h, h, c)
+    sf = src.float()
+    for ty in range(k):
+        for tx in range(k):
+            for qy in range(2):
+                for qx in range(2):
+                    py, px = (y0 - r + ty + qy).clamp(0, h - 1), (x0 - r + tx + qx).clamp(0, h - 1)
+                    res += (a[..., ty * k + tx] * wy[qy] * wx[qx])[..., None] * sf[b, py, px]
+    out.copy_((tgt.float() + res / (k * k)).to(out.dtype))
+    return out
+
+
 def grid_sample(x, grid, out, tgt=None):
     y = F.grid_sample(x.float().permute(0, 3, 1, 2), grid, mode="bilinear", padding_mode="zeros", align_corners=False)
     y = y.permute(0, 2, 3, 1)
@@ -201,7 +252,7 @@ def install(monkeypatch):
         if k.isupper():
             setattr(emu, k, getattr(real_ops, k))
     for name in ("conv2d", "nchw_to_nhwc", "nhwc_to_nchw", "seg_resize", "plane_stats", "instnorm_apply", "resize_flow",
-                 "attn_finish", "attn_unfold", "grid_sample", "composite", "hunfold_nchw", "hfold_nchw"):
+                 "attn_finish", "attn_unfold", "replicate_pad", "conv2d_halo", "attn_combine", "grid_sample", "composite", "hunfold_nchw", "hfold_nchw"):
         setattr(emu, name, globals()[name])
     monkeypatch.setattr(G, "ops", emu)
     return emu

@@ -6,6 +6,7 @@ import os
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from hoig_b200 import synth
 from hoig_b200.generator import GeneratorB200, create, parameter_layout
@@ -116,3 +117,32 @@ def test_packed_cache_invalidates_on_update(monkeypatch):
         g.get_parameter("bg_model.model.0.weight").mul_(2.0)
     w2 = g._w("bg_model.model.0.weight")
     assert w2 is not w1 and torch.allclose(w2, w1 * 2)
+
+
+def test_commuted_attention_equals_block_extractor_formulation():
+    """The tensor-core attention (two dense 5x5 convs over replicate-padded rasters + bilinear interpolation of the
+    source conv) is the same sum as extract_attn.py:24-28 over BlockExtractor taps, including taps clamped at the
+    image border and flows that leave the image."""
+    from hoig_b200.packing import pack_conv_weight
+    g = torch.Generator().manual_seed(5)
+    n, h, c, k, hid = 2, 12, 64, 5, 128
+    src, tgt = torch.randn(n, h, h, c, generator=g), torch.randn(n, h, h, c, generator=g)
+    flow = torch.randn(n, h, h, 2, generator=g) * 4.0
+    flow[0, 0, 0] = torch.tensor([-30.0, 25.0]); flow[1, 5, 5] = torch.tensor([40.0, -0.5]); flow[1, 3, 2] = torch.tensor([2.0, -3.0])
+    w0 = torch.randn(hid, 2 * c, k, k, generator=g) * 0.02
+    b1, w2, b2 = torch.randn(hid, generator=g) * 0.1, torch.randn(k * k, hid, generator=g) * 0.2, torch.randn(k * k, generator=g) * 0.1
+    # reference association: taps -> k5s5 conv (as a GEMM over the unfolded taps) -> finish
+    unf = emu_ops.attn_unfold(src, tgt, flow, torch.empty(n, h, h, 2 * k * k * c), k)
+    wfull = w0.permute(0, 2, 3, 1).reshape(hid, k * k * 2 * c)          # K order (tap, [tgt C | src C])
+    hidden = F.leaky_relu(unf @ wfull.t() + b1, 0.01)
+    ref = emu_ops.attn_finish(hidden, w2, b2, src, flow, tgt, torch.empty(n, h, h, c), k, unfold=unf)
+    # commuted association
+    r = k // 2
+    tpad = emu_ops.replicate_pad(tgt, torch.empty(n, h + 2 * r, h + 2 * r, c), r)
+    spad = emu_ops.replicate_pad(src, torch.empty(n, h + 4 * r, h + 4 * r, c), 2 * r)
+    wt, ws = pack_conv_weight(w0[:, :c], torch.float32), pack_conv_weight(w0[:, c:], torch.float32)
+    gt, gs = emu_ops.conv2d_halo([(tpad, wt, torch.empty(n, h + 2 * r, h + 2 * r, hid)),
+                                  (spad, ws, torch.empty(n, h + 4 * r, h + 4 * r, hid))], k, k, hid)
+    out = emu_ops.attn_combine(gt, gs, b1, w2, b2, src, flow, tgt, torch.empty(n, h, h, c), k)
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() <= 2e-5
