@@ -100,7 +100,9 @@ conv_halo_kernel(const HaloParams P, const __grid_constant__ CUtensorMap map_a0,
         // ================================================================ TMA producer
         if (lane == 0) {
             const uint32_t box_bytes = (uint32_t)(HM + P.KW - 1) * 128u;
-            uint32_t ia = 0, ib = 0;
+            uint32_t sa = 0, pa = 0, sb = 0, pb = 0;   // ring positions / phases, kept incrementally (no divisions on this thread)
+            const uint32_t afull0 = smem_u32(&afull[0]), aempty0 = smem_u32(&aempty[0]);
+            const uint32_t bfull0 = smem_u32(&bfull[0]), bempty0 = smem_u32(&bempty[0]);
             for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
                 const int sg = (P.nsegs > 1 && tile >= P.seg[1].tile0) ? 1 : 0;
                 const HaloSeg &S = P.seg[sg];
@@ -110,22 +112,20 @@ conv_halo_kernel(const HaloParams P, const __grid_constant__ CUtensorMap map_a0,
                     for (int cb = 0; cb < S.cblocks; ++cb) {
                         for (int s = 0; s < P.KW; ++s) {
                             if (s == 0 || per_tap) {
-                                const int st = ia % P.a_stages;
-                                mbar_wait(smem_u32(&aempty[st]), ((ia / P.a_stages) & 1) ^ 1);
-                                const uint32_t bar = smem_u32(&afull[st]);
-                                const uint32_t dst = a_base + (uint32_t)st * A_STAGE;
+                                mbar_wait(aempty0 + 8u * sa, pa ^ 1u);
+                                const uint32_t bar = afull0 + 8u * sa;
+                                const uint32_t dst = a_base + sa * (uint32_t)A_STAGE;
                                 const int64_t row0 = m0 + (int64_t)(r - hh) * S.pitch - hw + (per_tap ? s : 0);
                                 mbar_arrive_expect_tx(bar, 2 * box_bytes);
                                 tma_load_2d(dst, ma, bar, cb * HBK, (int)row0);
                                 tma_load_2d(dst + A_HALF_BYTES, ma, bar, cb * HBK, (int)(row0 + HM));
-                                ++ia;
+                                if (++sa == (uint32_t)P.a_stages) { sa = 0; pa ^= 1u; }
                             }
-                            const int st = ib % P.b_stages;
-                            mbar_wait(smem_u32(&bempty[st]), ((ib / P.b_stages) & 1) ^ 1);
-                            const uint32_t bar = smem_u32(&bfull[st]);
+                            mbar_wait(bempty0 + 8u * sb, pb ^ 1u);
+                            const uint32_t bar = bfull0 + 8u * sb;
                             mbar_arrive_expect_tx(bar, b_stage);
-                            tma_load_2d(b_base + (uint32_t)st * b_stage, mw, bar, ((r * P.KW + s) * S.cblocks + cb) * HBK, 0);
-                            ++ib;
+                            tma_load_2d(b_base + sb * b_stage, mw, bar, ((r * P.KW + s) * S.cblocks + cb) * HBK, 0);
+                            if (++sb == (uint32_t)P.b_stages) { sb = 0; pb ^= 1u; }
                         }
                     }
             }
@@ -135,7 +135,10 @@ conv_halo_kernel(const HaloParams P, const __grid_constant__ CUtensorMap map_a0,
         if (lane == 0) {
             constexpr uint32_t kFmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
             const uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(HM >> 4) << 24);
-            uint32_t ia = 0, ib = 0, tcount = 0;
+            uint32_t sa = 0, pa = 0, sb = 0, pb = 0, tcount = 0;
+            const uint32_t afull0 = smem_u32(&afull[0]), aempty0 = smem_u32(&aempty[0]);
+            const uint32_t bfull0 = smem_u32(&bfull[0]), bempty0 = smem_u32(&bempty[0]);
+            const uint64_t adesc0 = umma_desc(a_base), bdesc0 = umma_desc(b_base);   // + (byte offset >> 4)
             for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++tcount) {
                 const int sg = (P.nsegs > 1 && tile >= P.seg[1].tile0) ? 1 : 0;
                 const HaloSeg &S = P.seg[sg];
@@ -146,35 +149,34 @@ conv_halo_kernel(const HaloParams P, const __grid_constant__ CUtensorMap map_a0,
                 uint32_t first = 1;
                 for (int r = 0; r < P.KH; ++r)
                     for (int cb = 0; cb < S.cblocks; ++cb) {
-                        uint32_t a_addr = 0;
-                        int a_st = 0;
+                        uint64_t da = 0;
+                        uint32_t a_st = 0;
                         for (int s = 0; s < P.KW; ++s) {
                             if (s == 0 || per_tap) {
-                                a_st = ia % P.a_stages;
-                                mbar_wait(smem_u32(&afull[a_st]), (ia / P.a_stages) & 1);
-                                a_addr = a_base + (uint32_t)a_st * A_STAGE;
-                                ++ia;
+                                a_st = sa;
+                                mbar_wait(afull0 + 8u * sa, pa);
+                                da = adesc0 + (uint64_t)(sa * (uint32_t)(A_STAGE >> 4));
+                                if (++sa == (uint32_t)P.a_stages) { sa = 0; pa ^= 1u; }
                             }
-                            const int b_st = ib % P.b_stages;
-                            mbar_wait(smem_u32(&bfull[b_st]), (ib / P.b_stages) & 1);
-                            ++ib;
+                            const uint32_t b_st = sb;
+                            mbar_wait(bfull0 + 8u * sb, pb);
+                            if (++sb == (uint32_t)P.b_stages) { sb = 0; pb ^= 1u; }
                             tc_fence_after();
-                            const uint32_t b_addr = b_base + (uint32_t)b_st * b_stage;
-                            const uint32_t shift = per_tap ? 0u : (uint32_t)s * 128u;   // one pixel row per tap
+                            const uint64_t db = bdesc0 + (uint64_t)(b_st * (b_stage >> 4));
+                            // Tap s reads the box s pixel rows (128 B each) further on.  Descriptor start addresses that are NOT
+                            // multiples of the 1024 B swizzle period are fine as they are (base-offset field 0): the 128B swizzle
+                            // is a function of the absolute smem address, for the TMA write and the UMMA read alike.  Measured on
+                            // B200; setting base_offset = (addr >> 7) & 7 breaks it.
+                            const uint64_t das = da + (uint64_t)(per_tap ? 0 : s * 8);
 #pragma unroll
-                            for (int half = 0; half < 2; ++half) {
-                                const uint32_t ah = a_addr + (uint32_t)half * A_HALF_BYTES + shift;
-                                // Descriptor start addresses that are NOT multiples of the 1024 B swizzle period are fine as they
-                                // are (base-offset field 0): the 128B swizzle is a function of the absolute smem address, for the
-                                // TMA write and the UMMA read alike.  Measured on B200; setting base_offset = (addr >> 7) & 7 breaks it.
+                            for (int half = 0; half < 2; ++half)
 #pragma unroll
                                 for (int k = 0; k < HBK / 16; ++k)
-                                    umma_bf16(d_tmem + (uint32_t)(half * BN), umma_desc(ah + k * 32), umma_desc(b_addr + k * 32), idesc,
-                                              (first && k == 0) ? 0u : 1u);
-                            }
+                                    umma_bf16(d_tmem + (uint32_t)(half * BN), das + (uint64_t)(half * (A_HALF_BYTES >> 4) + 2 * k),
+                                              db + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
                             first = 0;
-                            umma_commit(smem_u32(&bempty[b_st]));
-                            if (s == P.KW - 1 || per_tap) umma_commit(smem_u32(&aempty[a_st]));
+                            umma_commit(bempty0 + 8u * b_st);
+                            if (s == P.KW - 1 || per_tap) umma_commit(aempty0 + 8u * a_st);
                         }
                     }
                 umma_commit(smem_u32(&tfull[acc]));

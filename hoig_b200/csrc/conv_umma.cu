@@ -53,6 +53,7 @@ struct UmmaParams {
     int tma_a;       // 1: activations by TMA boxes, 0: cp.async / register gather
     int cpt_shift;   // log2(Cin / 8) when Cin < 64 (chunk -> tap by shift), -1: generic division
     int prefetch_tiles;  // TMA-A: L2-prefetch the activation boxes this many tile rounds ahead (0 = off)
+    int debug;           // timing knock-outs (HOIG_UMMA_DEBUG, results are garbage): 1 = epilogue only drains TMEM, 2 = A tile loaded once per tile
 };
 
 // ------------------------------------------------------------------------ kernel
@@ -229,7 +230,8 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
         // ======================================================== TMA producer
         if (lane == 0) {
             const CUtensorMap *maps[4] = {&map_a0, &map_a1, &map_a2, &map_a3};
-            uint32_t it = 0;
+            uint32_t st = 0, ph = 0;
+            const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
             const uint32_t tx_bytes = (uint32_t)(BN * BK * 2) + (P.tma_a ? (uint32_t)A_STAGE_BYTES : 0u);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = tile / P.n_tiles, nt = tile % P.n_tiles;
@@ -250,19 +252,22 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                     }
                 }
                 int tap = 0, c = 0;
-                for (int kb = 0; kb < P.k_blocks; ++kb, ++it) {
-                    const int s = it % P.stages;
-                    mbar_wait(smem_u32(&empty_bar[s]), ((it / P.stages) & 1) ^ 1);
-                    const uint32_t bar = smem_u32(&full_bar[s]);
-                    const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
-                    mbar_arrive_expect_tx(bar, tx_bytes);
-                    if (P.tma_a) {
+                for (int kb = 0; kb < P.k_blocks; ++kb) {
+                    // ring position / phase kept incrementally: a runtime division per k-block on this single
+                    // thread costs more than the MMAs of a short k-block
+                    mbar_wait(empty0 + 8u * st, ph ^ 1u);
+                    const uint32_t bar = full0 + 8u * st;
+                    const uint32_t a_dst = smem_base + st * (uint32_t)stage_bytes;
+                    const bool skip_a = (P.debug & 2) && kb > 0;
+                    mbar_arrive_expect_tx(bar, skip_a ? (uint32_t)(BN * BK * 2) : tx_bytes);
+                    if (P.tma_a && !skip_a) {
                         const int tt = tap < p.ntaps ? tap : p.ntaps - 1;   // K padding blocks: any finite data (weights are zero)
                         tma_load_4d(a_dst, maps[p.tap_map[tt]], bar, c, gx0 + p.tap_dx[tt], gy0 + p.tap_dy[tt], n_img);
                         c += BK;
                         if (c >= p.Cin) { c = 0; ++tap; }
                     }
                     tma_load_2d(a_dst + A_STAGE_BYTES, &map_w, bar, kb * BK, nt * BN);
+                    if (++st == (uint32_t)P.stages) { st = 0; ph ^= 1u; }
                 }
             }
         }
@@ -273,22 +278,25 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
             // N >> 3 at bit 17, M >> 4 at bit 24
             constexpr uint32_t kFmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
             const uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            uint32_t it = 0, tcount = 0;
+            uint32_t st = 0, ph = 0, tcount = 0;
+            const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+            const uint64_t desc0 = umma_desc(smem_base);             // + (byte offset >> 4) addresses any tile of the ring
+            const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
                 const uint32_t acc = tcount & 1;
                 mbar_wait(smem_u32(&tempty_bar[acc]), ((tcount >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)BN;
-                for (int kb = 0; kb < P.k_blocks; ++kb, ++it) {
-                    const int s = it % P.stages;
-                    mbar_wait(smem_u32(&full_bar[s]), (it / P.stages) & 1);
+                for (int kb = 0; kb < P.k_blocks; ++kb) {
+                    mbar_wait(full0 + 8u * st, ph);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
-                    const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+                    const uint64_t da = desc0 + (uint64_t)(st * stage16);
+                    const uint64_t db = da + (uint64_t)(A_STAGE_BYTES >> 4);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        umma_bf16(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), idesc, (kb | k) ? 1u : 0u);
-                    umma_commit(smem_u32(&empty_bar[s]));   // frees the smem stage when these MMAs retire
+                        umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(empty0 + 8u * st);   // frees the smem stage when these MMAs retire
+                    if (++st == (uint32_t)P.stages) { st = 0; ph ^= 1u; }
                 }
                 umma_commit(smem_u32(&tfull_bar[acc]));     // accumulator complete
             }
@@ -398,6 +406,10 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                         }
                     }
             };
+            if (P.debug & 1) {
+                for (int ch = half; ch < n_chunks; ch += ngrp) { tmem_ld16(t_row + (uint32_t)(ch * 16), ra); tmem_ld_wait(ra); }
+                if (ra[0] == 0x7fc12345u && valid) dst[m * p.ldd] = T(0);
+            } else {
             if (half < n_chunks) tmem_ld16(t_row + (uint32_t)(half * 16), ra);
             for (int ch = half; ch < n_chunks; ch += 2 * ngrp) {
                 tmem_ld_wait(ra);
@@ -408,6 +420,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                     if (ch + 2 * ngrp < n_chunks) tmem_ld16(t_row + (uint32_t)((ch + 2 * ngrp) * 16), ra);
                     finalize(rb, ch + ngrp);
                 }
+            }
             }
             // accumulator drained: hand the TMEM stage back to the MMA warp
             tc_fence_before();
@@ -434,6 +447,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
     }
 }
 
+int g_umma_debug = 0;
 int g_prefetch_tiles = 0;   // measured: L2 prefetch of future tiles HURTS (the streaming convs are L2->SM bandwidth bound, not latency bound)
 
 int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int dtype)
@@ -465,6 +479,7 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
 
     // streaming inputs (larger than a fraction of L2) need HBM latency hidden beyond the smem ring
     const double in_bytes = (double)p.N * p.view[0].sn * 2.0;
+    P.debug = g_umma_debug;
     P.prefetch_tiles = (P.tma_a && g_prefetch_tiles > 0 && in_bytes > 48e6) ? g_prefetch_tiles : 0;
 
     CUtensorMap map_w, map_a[4];
@@ -521,6 +536,8 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
         g_force_gather = (e && e[0] == '1') ? 1 : 0;
         const char *pf = getenv("HOIG_UMMA_PREFETCH_TILES");
         if (pf) g_prefetch_tiles = atoi(pf);
+        const char *dbg = getenv("HOIG_UMMA_DEBUG");
+        if (dbg) g_umma_debug = atoi(dbg);
     }
     for (int i = 0; i < plan.n; ++i) {
         st = launch_one(plan.launch[i], stream, g_force_gather, d->dtype);

@@ -477,7 +477,7 @@ __device__ __forceinline__ void load4(const float *p, float v[4])
 //   coef   = the KK attention weights x the 4 bilinear weights folded into one (K+1)^2 patch
 //   dst    = tgt + (1/KK) sum_u coef[u] * src[clamp(p0 - K/2 + u)]
 template <typename T, int KK>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 attn_combine_kernel(const T *__restrict__ gt, int64_t ldgt, const T *__restrict__ gs, int64_t ldgs, const float *__restrict__ b1,
                     const float *__restrict__ w2, const float *__restrict__ b2, const T *__restrict__ src, int64_t lds,
                     const float *__restrict__ flow, const T *__restrict__ tgt, int64_t ldt, T *__restrict__ dst, int64_t ldd,
@@ -488,6 +488,7 @@ attn_combine_kernel(const T *__restrict__ gt, int64_t ldgt, const T *__restrict_
     __shared__ __align__(16) float s_w2[KK][HID];
     __shared__ __align__(16) float s_b1[HID];
     __shared__ float s_b2[KK];
+    __shared__ float s_coef[8][4][PK * PK + 4];
     for (int i = threadIdx.x; i < KK * HID; i += blockDim.x) (&s_w2[0][0])[i] = w2[i];
     for (int i = threadIdx.x; i < HID; i += blockDim.x) s_b1[i] = b1[i];
     for (int i = threadIdx.x; i < KK; i += blockDim.x) s_b2[i] = b2[i];
@@ -558,8 +559,10 @@ attn_combine_kernel(const T *__restrict__ gt, int64_t ldgt, const T *__restrict_
 #pragma unroll
         for (int t = 0; t < KK; ++t) { a[t] = expf(a[t] - mx); den += a[t]; }
         const float inv = 1.0f / (den * (float)KK);
-        // ---- fold attention weights x bilinear weights into the (K+1)^2 patch
-        float coef[PK][PK];
+        // ---- fold attention weights x bilinear weights into the (K+1)^2 patch (kept in shared memory: the gather
+        //      loop below then needs few registers and more warps fit on the SM to hide its load latency)
+        float *cf = &s_coef[threadIdx.x / 32][grp][0];
+        __syncwarp();
 #pragma unroll
         for (int uy = 0; uy < PK; ++uy)
 #pragma unroll
@@ -569,26 +572,26 @@ attn_combine_kernel(const T *__restrict__ gt, int64_t ldgt, const T *__restrict_
                 if (uy < K && ux > 0) c = fmaf(a[uy * K + ux - 1], wy0 * wx1, c);
                 if (uy > 0 && ux < K) c = fmaf(a[(uy - 1) * K + ux], wy1 * wx0, c);
                 if (uy > 0 && ux > 0) c = fmaf(a[(uy - 1) * K + ux - 1], wy1 * wx1, c);
-                coef[uy][ux] = c * inv;
+                if (((uy * PK + ux) & 7) == sub) cf[uy * PK + ux] = c * inv;
             }
-        int poff[PK];   // x offsets (elements) of the patch columns
-#pragma unroll
-        for (int u = 0; u < PK; ++u) poff[u] = max(min(x0 - R + u, h - 1), 0);
+        __syncwarp();
         const T *splane = src + n * (int64_t)h * h * lds;
+        const int xb = x0 - R, yb = y0 - R;
         for (int cc = sub; cc < C / 8; cc += 8) {
             float acc[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
+#pragma unroll 2
             for (int uy = 0; uy < PK; ++uy) {
-                const int py = max(min(y0 - R + uy, h - 1), 0);
+                const int py = max(min(yb + uy, h - 1), 0);
                 const T *srow = splane + (int64_t)py * h * lds + cc * 8;
 #pragma unroll
                 for (int ux = 0; ux < PK; ++ux) {
                     float u[8];
-                    load8(srow + (int64_t)poff[ux] * lds, u);
+                    load8(srow + (int64_t)max(min(xb + ux, h - 1), 0) * lds, u);
+                    const float c = cf[uy * PK + ux];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(coef[uy][ux], u[j], acc[j]);
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(c, u[j], acc[j]);
                 }
             }
             float tv[8];
