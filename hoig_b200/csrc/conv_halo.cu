@@ -98,7 +98,7 @@ conv_halo_kernel(const HaloParams P, const __grid_constant__ CUtensorMap map_a0,
 
     if (warp == 0) {
         // ================================================================ TMA producer
-        if (lane == 0) {
+        {   // whole warp runs the loop; one elected lane issues (see elect_one())
             const uint32_t box_bytes = (uint32_t)(HM + P.KW - 1) * 128u;
             uint32_t sa = 0, pa = 0, sb = 0, pb = 0;   // ring positions / phases, kept incrementally (no divisions on this thread)
             const uint32_t afull0 = smem_u32(&afull[0]), aempty0 = smem_u32(&aempty[0]);
@@ -116,15 +116,21 @@ conv_halo_kernel(const HaloParams P, const __grid_constant__ CUtensorMap map_a0,
                                 const uint32_t bar = afull0 + 8u * sa;
                                 const uint32_t dst = a_base + sa * (uint32_t)A_STAGE;
                                 const int64_t row0 = m0 + (int64_t)(r - hh) * S.pitch - hw + (per_tap ? s : 0);
-                                mbar_arrive_expect_tx(bar, 2 * box_bytes);
-                                tma_load_2d(dst, ma, bar, cb * HBK, (int)row0);
-                                tma_load_2d(dst + A_HALF_BYTES, ma, bar, cb * HBK, (int)(row0 + HM));
+                                if (elect_one()) {
+                                    mbar_arrive_expect_tx(bar, 2 * box_bytes);
+                                    tma_load_2d(dst, ma, bar, cb * HBK, (int)row0);
+                                    tma_load_2d(dst + A_HALF_BYTES, ma, bar, cb * HBK, (int)(row0 + HM));
+                                }
+                                __syncwarp();
                                 if (++sa == (uint32_t)P.a_stages) { sa = 0; pa ^= 1u; }
                             }
                             mbar_wait(bempty0 + 8u * sb, pb ^ 1u);
                             const uint32_t bar = bfull0 + 8u * sb;
-                            mbar_arrive_expect_tx(bar, b_stage);
-                            tma_load_2d(b_base + sb * b_stage, mw, bar, ((r * P.KW + s) * S.cblocks + cb) * HBK, 0);
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx(bar, b_stage);
+                                tma_load_2d(b_base + sb * b_stage, mw, bar, ((r * P.KW + s) * S.cblocks + cb) * HBK, 0);
+                            }
+                            __syncwarp();
                             if (++sb == (uint32_t)P.b_stages) { sb = 0; pb ^= 1u; }
                         }
                     }
@@ -132,7 +138,7 @@ conv_halo_kernel(const HaloParams P, const __grid_constant__ CUtensorMap map_a0,
         }
     } else if (warp == 1) {
         // ================================================================== MMA issuer
-        if (lane == 0) {
+        {   // whole warp runs the loop; one elected lane issues
             constexpr uint32_t kFmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
             const uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(HM >> 4) << 24);
             uint32_t sa = 0, pa = 0, sb = 0, pb = 0, tcount = 0;
@@ -168,18 +174,22 @@ conv_halo_kernel(const HaloParams P, const __grid_constant__ CUtensorMap map_a0,
                             // is a function of the absolute smem address, for the TMA write and the UMMA read alike.  Measured on
                             // B200; setting base_offset = (addr >> 7) & 7 breaks it.
                             const uint64_t das = da + (uint64_t)(per_tap ? 0 : s * 8);
+                            if (elect_one()) {
 #pragma unroll
-                            for (int half = 0; half < 2; ++half)
+                                for (int half = 0; half < 2; ++half)
 #pragma unroll
-                                for (int k = 0; k < HBK / 16; ++k)
-                                    umma_bf16(d_tmem + (uint32_t)(half * BN), das + (uint64_t)(half * (A_HALF_BYTES >> 4) + 2 * k),
-                                              db + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
+                                    for (int k = 0; k < HBK / 16; ++k)
+                                        umma_bf16(d_tmem + (uint32_t)(half * BN), das + (uint64_t)(half * (A_HALF_BYTES >> 4) + 2 * k),
+                                                  db + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
+                                umma_commit(bempty0 + 8u * b_st);
+                                if (s == P.KW - 1 || per_tap) umma_commit(aempty0 + 8u * a_st);
+                            }
+                            __syncwarp();
                             first = 0;
-                            umma_commit(bempty0 + 8u * b_st);
-                            if (s == P.KW - 1 || per_tap) umma_commit(aempty0 + 8u * a_st);
                         }
                     }
-                umma_commit(smem_u32(&tfull[acc]));
+                if (elect_one()) umma_commit(smem_u32(&tfull[acc]));
+                __syncwarp();
             }
         }
     } else {

@@ -35,8 +35,9 @@ constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int EPI_WARPS = 8, PROD_WARPS = 4;    // epilogue warp w: TMEM lane quadrant w % 4, 16-column chunks of parity w / 4
-constexpr int TMA_WARP = 12, MMA_WARP = 13;
-constexpr int THREADS = 448;
+constexpr int EPI_END = 16;                     // warps 12-15: a further epilogue group
+constexpr int TMA_WARP = 16, MMA_WARP = 17, WB_WARP = 18;   // WB: weight-tile TMA producer in TMA-A mode
+constexpr int THREADS = 640;
 constexpr int MAX_STAGES = 8;
 constexpr int LOOKAHEAD = 3;           // cp.async groups in flight per producer thread
 constexpr int STG_BYTES = 0;
@@ -53,6 +54,7 @@ struct UmmaParams {
     int tma_a;       // 1: activations by TMA boxes, 0: cp.async / register gather
     int cpt_shift;   // log2(Cin / 8) when Cin < 64 (chunk -> tap by shift), -1: generic division
     int prefetch_tiles;  // TMA-A: L2-prefetch the activation boxes this many tile rounds ahead (0 = off)
+    int tpi_shift;       // log2(tiles_per_image) when it is a power of two, else -1
     int debug;           // timing knock-outs (HOIG_UMMA_DEBUG, results are garbage): 1 = epilogue only drains TMEM, 2 = A tile loaded once per tile
 };
 
@@ -80,14 +82,14 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
     const int npix = p.GH * p.GW;
 
     if (threadIdx.x == 0) {
-        const uint32_t full_count = P.tma_a ? 1u : (uint32_t)(PROD_WARPS * 32 + 1);
+        const uint32_t full_count = P.tma_a ? 2u : (uint32_t)(PROD_WARPS * 32 + 1);   // TMA-A: one arrive.expect_tx per producer thread
         for (int s = 0; s < P.stages; ++s) {
             mbar_init(smem_u32(&full_bar[s]), full_count);
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&tfull_bar[a]), 1);
-            mbar_init(smem_u32(&tempty_bar[a]), (uint32_t)((P.tma_a ? EPI_WARPS + PROD_WARPS : EPI_WARPS) * 32));
+            mbar_init(smem_u32(&tempty_bar[a]), (uint32_t)((P.tma_a ? EPI_END : EPI_END - PROD_WARPS) * 32));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -226,31 +228,23 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                 ++sig_it; --pending;
             }
         }
-    } else if (warp == TMA_WARP) {
-        // ======================================================== TMA producer
-        if (lane == 0) {
+    } else if (warp == TMA_WARP || warp == WB_WARP) {
+        // ======================================================== TMA producers
+        // TMA-A mode: warp TMA_WARP streams the activation boxes, warp WB_WARP the weight tiles (two threads, because one
+        // thread's wait + expect_tx + two TMA issues per k-block take longer than the four MMAs of a narrow-N k-block).
+        // Gather mode: TMA_WARP streams the weight tiles, WB_WARP has nothing to do.
+        const bool do_a = P.tma_a && warp == TMA_WARP;
+        const bool do_b = P.tma_a ? warp == WB_WARP : warp == TMA_WARP;
+        if (do_a || do_b) {   // whole warp runs the loop; one elected lane issues
             const CUtensorMap *maps[4] = {&map_a0, &map_a1, &map_a2, &map_a3};
             uint32_t st = 0, ph = 0;
             const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
-            const uint32_t tx_bytes = (uint32_t)(BN * BK * 2) + (P.tma_a ? (uint32_t)A_STAGE_BYTES : 0u);
+            const uint32_t b_bytes = (uint32_t)(BN * BK * 2);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = tile / P.n_tiles, nt = tile % P.n_tiles;
                 const int n_img = mt / p.tiles_per_image;
                 const int pix0 = (mt % p.tiles_per_image) * BM;
                 const int gy0 = pix0 / p.GW, gx0 = pix0 % p.GW;
-                if (P.prefetch_tiles && nt == 0) {
-                    // The ring holds ~190 KB per SM; at HBM latency that caps a streaming conv at ~50 GB/s per SM.
-                    // Pull the activation boxes of the tile this CTA will reach `prefetch_tiles` rounds from now into L2.
-                    const int ft = tile + P.prefetch_tiles * (int)gridDim.x;
-                    if (ft < total_tiles) {
-                        const int fmt = ft / P.n_tiles;
-                        const int fn = fmt / p.tiles_per_image, fpix = (fmt % p.tiles_per_image) * BM;
-                        const int fy = fpix / p.GW, fx = fpix % p.GW;
-                        for (int t = 0; t < p.ntaps; ++t)
-                            for (int cc = 0; cc < p.Cin; cc += BK)
-                                tma_prefetch_4d(maps[p.tap_map[t]], cc, fx + p.tap_dx[t], fy + p.tap_dy[t], fn);
-                    }
-                }
                 int tap = 0, c = 0;
                 for (int kb = 0; kb < P.k_blocks; ++kb) {
                     // ring position / phase kept incrementally: a runtime division per k-block on this single
@@ -258,22 +252,31 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                     mbar_wait(empty0 + 8u * st, ph ^ 1u);
                     const uint32_t bar = full0 + 8u * st;
                     const uint32_t a_dst = smem_base + st * (uint32_t)stage_bytes;
-                    const bool skip_a = (P.debug & 2) && kb > 0;
-                    mbar_arrive_expect_tx(bar, skip_a ? (uint32_t)(BN * BK * 2) : tx_bytes);
-                    if (P.tma_a && !skip_a) {
+                    if (do_a) {
+                        const bool skip_a = (P.debug & 2) && kb > 0;
                         const int tt = tap < p.ntaps ? tap : p.ntaps - 1;   // K padding blocks: any finite data (weights are zero)
-                        tma_load_4d(a_dst, maps[p.tap_map[tt]], bar, c, gx0 + p.tap_dx[tt], gy0 + p.tap_dy[tt], n_img);
+                        if (elect_one()) {
+                            if (skip_a) {
+                                mbar_arrive(bar);
+                            } else {
+                                mbar_arrive_expect_tx(bar, (uint32_t)A_STAGE_BYTES);
+                                tma_load_4d(a_dst, maps[p.tap_map[tt]], bar, c, gx0 + p.tap_dx[tt], gy0 + p.tap_dy[tt], n_img);
+                            }
+                        }
                         c += BK;
                         if (c >= p.Cin) { c = 0; ++tap; }
+                    } else if (elect_one()) {
+                        mbar_arrive_expect_tx(bar, b_bytes);
+                        tma_load_2d(a_dst + A_STAGE_BYTES, &map_w, bar, kb * BK, nt * BN);
                     }
-                    tma_load_2d(a_dst + A_STAGE_BYTES, &map_w, bar, kb * BK, nt * BN);
+                    __syncwarp();
                     if (++st == (uint32_t)P.stages) { st = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == MMA_WARP) {
         // ========================================================== MMA issuer
-        if (lane == 0) {
+        {   // whole warp runs the loop (waits, fences); one elected lane issues the MMAs and commits
             // instruction descriptor: D = f32 (bit 4), A/B format bf16 = 1 / f16 = 0 (bits 7-9 / 10-12), K-major A and B,
             // N >> 3 at bit 17, M >> 4 at bit 24
             constexpr uint32_t kFmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
@@ -292,37 +295,47 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                     tc_fence_after();
                     const uint64_t da = desc0 + (uint64_t)(st * stage16);
                     const uint64_t db = da + (uint64_t)(A_STAGE_BYTES >> 4);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-                    umma_commit(empty0 + 8u * st);   // frees the smem stage when these MMAs retire
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                        umma_commit(empty0 + 8u * st);   // frees the smem stage when these MMAs retire
+                    }
+                    __syncwarp();
                     if (++st == (uint32_t)P.stages) { st = 0; ph ^= 1u; }
                 }
-                umma_commit(smem_u32(&tfull_bar[acc]));     // accumulator complete
+                if (elect_one()) umma_commit(smem_u32(&tfull_bar[acc]));     // accumulator complete
+                __syncwarp();
             }
         }
-    } else {
+    } else if (warp < EPI_END) {
         // ============================================================ epilogue
         // lane == tile row within the warp's TMEM lane quadrant; the two warps of a quadrant take
         // alternate 16-column chunks.  Chunk i+1 is in flight (tcgen05.ld) while chunk i is finalised.
-        const int quad = warp & 3, half = warp >> 2;               // half = chunk group of this warp
-        const int ngrp = P.tma_a ? 3 : 2;                          // groups share the chunks round-robin
+        // warp groups {0-3}, {4-7}, ({8-11} in TMA-A mode), {12-15}: each group covers the four TMEM lane quadrants and the
+        // groups share the 16-column chunks round-robin
+        const int quad = warp & 3;
+        const int ngrp = P.tma_a ? 4 : 3;
+        const int half = (!P.tma_a && warp >= EPI_WARPS + PROD_WARPS) ? 2 : warp >> 2;   // chunk group of this warp
         const int epi_threads = ngrp * 128;
+        const int epi_tid = half * 128 + quad * 32 + lane;
         const T *res = static_cast<const T *>(p.residual);
         T *dst = static_cast<T *>(p.dst);
         const bool vec_ok = ((p.ldd & 7) == 0) && (!res || (p.ldr & 7) == 0);
         const int n_chunks = BN / 16;
+        const bool all_valid = npix % BM == 0;
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-            const int mt = tile / P.n_tiles, nt = tile % P.n_tiles;
-            const int n_img = mt / p.tiles_per_image;
-            const int pix = (mt % p.tiles_per_image) * BM + quad * 32 + lane;
+            int mt = tile, nt = 0;
+            if (P.n_tiles > 1) { mt = tile / P.n_tiles; nt = tile - mt * P.n_tiles; }
+            const int n_img = P.tpi_shift >= 0 ? mt >> P.tpi_shift : mt / p.tiles_per_image;
+            const int pix = (mt - n_img * p.tiles_per_image) * BM + quad * 32 + lane;
             const bool valid = pix < npix;
             const int64_t m = valid ? out_pixel(p, n_img, pix) : 0;
             const int pc = p.phase_cout;     // > 0: transposed conv, column n = phase * pc + channel
             const uint32_t acc = tcount & 1;
             epi_bar(epi_threads);                       // previous tile fully drained: s_bias / s_stats reusable
-            for (int i = threadIdx.x; i < BN; i += epi_threads) {
+            for (int i = epi_tid; i < BN; i += epi_threads) {
                 const int n = nt * BN + i;
                 s_bias[i] = (p.bias && n < p.Cout) ? __ldg(p.bias + (pc ? n % pc : n)) : 0.f;
             }
@@ -346,10 +359,13 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                     const T *rrow = res ? res + mm * p.ldr + ncol - c0 : nullptr;
                     float v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        const float4 bv = *reinterpret_cast<const float4 *>(&s_bias[c0 + j]);
-                        v[j] = __uint_as_float(r[j]) + bv.x;         v[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
-                        v[j + 2] = __uint_as_float(r[j + 2]) + bv.z; v[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 bv = *reinterpret_cast<const float4 *>(&s_bias[c0 + j]);
+                            v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+                        }
                     }
                     const bool full = n0 + 16 <= p.Cout;
                     if (res && valid) {
@@ -388,14 +404,13 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                         }
                     }
                     if (p.stats) {
+                        // Statistics of the fp32 values (before the 16-bit store rounding, i.e. closer to the reference's fp32
+                        // activations); rows past the end of the plane contribute nothing.
                         float q[16];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {   // statistics of the values as stored (bf16-rounded)
-                            float lo, hi;
-                        unpack2<T>(pk[j], lo, hi);
-                        lo = valid ? lo : 0.f; hi = valid ? hi : 0.f;
-                            v[2 * j] = lo; v[2 * j + 1] = hi;
-                            q[2 * j] = lo * lo; q[2 * j + 1] = hi * hi;
+                        for (int j = 0; j < 16; ++j) {
+                            if (!all_valid) v[j] = valid ? v[j] : 0.f;
+                            q[j] = v[j] * v[j];
                         }
                         const float cs = transpose_reduce16(v, lane);
                         const float cq = transpose_reduce16(q, lane);
@@ -427,7 +442,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
             mbar_arrive(smem_u32(&tempty_bar[acc]));
             if (p.stats) {
                 epi_bar(epi_threads);
-                for (int i = threadIdx.x; i < 2 * BN; i += epi_threads) {
+                for (int i = epi_tid; i < 2 * BN; i += epi_threads) {
                     const int which = i / BN, col = i % BN;
                     const int n = nt * BN + col;
                     const float tot = s_stats[0][which][col] + s_stats[1][which][col] + s_stats[2][which][col] + s_stats[3][which][col];
@@ -480,6 +495,8 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     // streaming inputs (larger than a fraction of L2) need HBM latency hidden beyond the smem ring
     const double in_bytes = (double)p.N * p.view[0].sn * 2.0;
     P.debug = g_umma_debug;
+    P.tpi_shift = -1;
+    if ((p.tiles_per_image & (p.tiles_per_image - 1)) == 0) { P.tpi_shift = 0; while ((1 << P.tpi_shift) < p.tiles_per_image) ++P.tpi_shift; }
     P.prefetch_tiles = (P.tma_a && g_prefetch_tiles > 0 && in_bytes > 48e6) ? g_prefetch_tiles : 0;
 
     CUtensorMap map_w, map_a[4];

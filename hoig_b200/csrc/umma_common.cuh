@@ -69,6 +69,16 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
+// One lane of a CONVERGED warp.  Single-thread roles (TMA producer, MMA issuer) run their loops on the whole warp and
+// guard only the issue with this: under `if (lane == 0)` the compiler wraps every uniform-datapath instruction
+// (UTCHMMA, UTMALDG, UTCBAR) in an ELECT / BRA.U.ANY loop plus R2UR moves, which costs more than a narrow MMA itself.
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1):
 // start address >> 4 | LBO (unused for swizzled K-major, canonical 1) | SBO = 1024 B (8 rows x 128 B)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
