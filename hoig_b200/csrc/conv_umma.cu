@@ -23,6 +23,8 @@
 // smem: ring of STAGES x (A 16 KB + B BN*128 B), 1024-byte aligned for SWIZZLE_128B.
 #include <cuda.h>
 
+#include <string.h>
+
 #include <type_traits>
 
 #include "conv_common.cuh"
@@ -59,7 +61,12 @@ struct UmmaParams {
 };
 
 // ------------------------------------------------------------------------ kernel
-template <typename T>   // T = T or __half (16-bit storage; tcgen05 kind::f16 handles both)
+// T = __nv_bfloat16 or __half (16-bit storage; tcgen05 kind::f16 handles both).
+// NCTA = 2: CTA pair (cluster of 2, cta_group::2).  The pair computes a 256-pixel x BN tile: each CTA stages its own 128
+// pixels of A and HALF of the weight tile (BN/2 rows), the leader (cluster rank 0) issues 256 x BN x 16 MMAs that read both
+// CTAs' shared memory, and each CTA drains its own 128 TMEM lanes.  Weight traffic (L2->SM and smem writes) per CTA halves,
+// which is what bounds the wide-N convs: TMA writes and UMMA operand reads share the 128 B/clk shared-memory port.
+template <typename T, int NCTA>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
@@ -74,12 +81,14 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
     const ConvParams &p = P.c;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int BN = P.BN;
-    const int stage_bytes = A_STAGE_BYTES + BN * BK * 2;
+    const int stage_bytes = A_STAGE_BYTES + (BN / NCTA) * BK * 2;
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     const uint32_t stg_base = smem_u32(smem);                  // epilogue staging first (1024-aligned)
     const uint32_t smem_base = stg_base + STG_BYTES;           // then the operand ring
-    const int total_tiles = P.m_tiles * P.n_tiles;
+    const int total_tiles = (P.m_tiles / NCTA) * P.n_tiles;    // tiles of NCTA*128 pixels x BN channels
     const int npix = p.GH * p.GW;
+    const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;  // 0 = leader of the pair
+    const int tile0 = (int)blockIdx.x / NCTA, tile_step = (int)gridDim.x / NCTA;
 
     if (threadIdx.x == 0) {
         const uint32_t full_count = P.tma_a ? 2u : (uint32_t)(PROD_WARPS * 32 + 1);   // TMA-A: one arrive.expect_tx per producer thread
@@ -89,21 +98,27 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&tfull_bar[a]), 1);
-            mbar_init(smem_u32(&tempty_bar[a]), (uint32_t)((P.tma_a ? EPI_END : EPI_END - PROD_WARPS) * 32));
+            mbar_init(smem_u32(&tempty_bar[a]), (uint32_t)(NCTA * (P.tma_a ? EPI_END : EPI_END - PROD_WARPS) * 32));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < 4 * 2 * 256; i += blockDim.x) (&s_stats[0][0][0])[i] = 0.f;
     if (warp == MMA_WARP) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_smem)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (NCTA == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_smem)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_smem)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     if (warp == TMA_WARP && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
         if (P.tma_a) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a0) : "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    if (NCTA == 2) cluster_sync();   // the peer's barriers must be initialised before anything is signalled on them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
@@ -118,7 +133,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
             uint32_t it = 0;  // running k-block counter across tiles
             int pending = 0;  // k-blocks issued but not yet signalled
             uint32_t sig_it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < total_tiles; tile += tile_step) {
                 const int mt = tile / P.n_tiles;
                 const int n_img = mt / p.tiles_per_image;
                 const int pix = (mt % p.tiles_per_image) * BM + row;
@@ -238,10 +253,15 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
         if (do_a || do_b) {   // whole warp runs the loop; one elected lane issues
             const CUtensorMap *maps[4] = {&map_a0, &map_a1, &map_a2, &map_a3};
             uint32_t st = 0, ph = 0;
-            const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
-            const uint32_t b_bytes = (uint32_t)(BN * BK * 2);
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile / P.n_tiles, nt = tile % P.n_tiles;
+            const uint32_t empty0 = smem_u32(&empty_bar[0]);
+            // the "full" barriers live in the leader CTA: both CTAs' TMA loads complete on them
+            const uint32_t full0 = NCTA == 2 ? mapa(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
+            const uint32_t b_rows = (uint32_t)(BN / NCTA);
+            const uint32_t b_bytes = (uint32_t)(BN * BK * 2);          // whole pair
+            for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+                int mt = tile, nt = 0;
+                if (P.n_tiles > 1) { mt = tile / P.n_tiles; nt = tile - mt * P.n_tiles; }
+                mt = mt * NCTA + (int)rank;
                 const int n_img = mt / p.tiles_per_image;
                 const int pix0 = (mt % p.tiles_per_image) * BM;
                 const int gy0 = pix0 / p.GW, gx0 = pix0 % p.GW;
@@ -253,11 +273,14 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                     const uint32_t bar = full0 + 8u * st;
                     const uint32_t a_dst = smem_base + st * (uint32_t)stage_bytes;
                     if (do_a) {
-                        const bool skip_a = (P.debug & 2) && kb > 0;
+                        const bool skip_a = NCTA == 1 && (P.debug & 2) && kb > 0;
                         const int tt = tap < p.ntaps ? tap : p.ntaps - 1;   // K padding blocks: any finite data (weights are zero)
                         if (elect_one()) {
                             if (skip_a) {
                                 mbar_arrive(bar);
+                            } else if (NCTA == 2) {
+                                if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[0]) + 8u * st, 2u * (uint32_t)A_STAGE_BYTES);
+                                tma_load_4d_2sm(a_dst, maps[p.tap_map[tt]], bar, c, gx0 + p.tap_dx[tt], gy0 + p.tap_dy[tt], n_img);
                             } else {
                                 mbar_arrive_expect_tx(bar, (uint32_t)A_STAGE_BYTES);
                                 tma_load_4d(a_dst, maps[p.tap_map[tt]], bar, c, gx0 + p.tap_dx[tt], gy0 + p.tap_dy[tt], n_img);
@@ -266,8 +289,13 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                         c += BK;
                         if (c >= p.Cin) { c = 0; ++tap; }
                     } else if (elect_one()) {
-                        mbar_arrive_expect_tx(bar, b_bytes);
-                        tma_load_2d(a_dst + A_STAGE_BYTES, &map_w, bar, kb * BK, nt * BN);
+                        if (NCTA == 2) {
+                            if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[0]) + 8u * st, b_bytes);
+                            tma_load_2d_2sm(a_dst + A_STAGE_BYTES, &map_w, bar, kb * BK, nt * BN + (int)(rank * b_rows));
+                        } else {
+                            mbar_arrive_expect_tx(bar, b_bytes);
+                            tma_load_2d(a_dst + A_STAGE_BYTES, &map_w, bar, kb * BK, nt * BN);
+                        }
                     }
                     __syncwarp();
                     if (++st == (uint32_t)P.stages) { st = 0; ph ^= 1u; }
@@ -276,16 +304,16 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
         }
     } else if (warp == MMA_WARP) {
         // ========================================================== MMA issuer
-        {   // whole warp runs the loop (waits, fences); one elected lane issues the MMAs and commits
+        if (rank == 0) {   // leader only.  Whole warp runs the loop (waits, fences); one elected lane issues the MMAs and commits
             // instruction descriptor: D = f32 (bit 4), A/B format bf16 = 1 / f16 = 0 (bits 7-9 / 10-12), K-major A and B,
-            // N >> 3 at bit 17, M >> 4 at bit 24
+            // N >> 3 at bit 17, M >> 4 at bit 24 (M = 256 for the CTA pair)
             constexpr uint32_t kFmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
-            const uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((NCTA * BM) >> 4) << 24);
             uint32_t st = 0, ph = 0, tcount = 0;
             const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
             const uint64_t desc0 = umma_desc(smem_base);             // + (byte offset >> 4) addresses any tile of the ring
             const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tcount) {
                 const uint32_t acc = tcount & 1;
                 mbar_wait(smem_u32(&tempty_bar[acc]), ((tcount >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -297,14 +325,21 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                     const uint64_t db = da + (uint64_t)(A_STAGE_BYTES >> 4);
                     if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k)
-                            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-                        umma_commit(empty0 + 8u * st);   // frees the smem stage when these MMAs retire
+                        for (int k = 0; k < BK / 16; ++k) {
+                            if (NCTA == 2) umma_bf16_2sm(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                            else umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                        }
+                        // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+                        if (NCTA == 2) umma_commit_2sm(empty0 + 8u * st);
+                        else umma_commit(empty0 + 8u * st);
                     }
                     __syncwarp();
                     if (++st == (uint32_t)P.stages) { st = 0; ph ^= 1u; }
                 }
-                if (elect_one()) umma_commit(smem_u32(&tfull_bar[acc]));     // accumulator complete
+                if (elect_one()) {   // accumulator complete (signalled in both CTAs of a pair)
+                    if (NCTA == 2) umma_commit_2sm(smem_u32(&tfull_bar[acc]));
+                    else umma_commit(smem_u32(&tfull_bar[acc]));
+                }
                 __syncwarp();
             }
         }
@@ -325,9 +360,11 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
         const int n_chunks = BN / 16;
         const bool all_valid = npix % BM == 0;
         uint32_t tcount = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t tempty0 = NCTA == 2 ? mapa(smem_u32(&tempty_bar[0]), 0) : smem_u32(&tempty_bar[0]);   // in the leader CTA
+        for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tcount) {
             int mt = tile, nt = 0;
             if (P.n_tiles > 1) { mt = tile / P.n_tiles; nt = tile - mt * P.n_tiles; }
+            mt = mt * NCTA + (int)rank;
             const int n_img = P.tpi_shift >= 0 ? mt >> P.tpi_shift : mt / p.tiles_per_image;
             const int pix = (mt - n_img * p.tiles_per_image) * BM + quad * 32 + lane;
             const bool valid = pix < npix;
@@ -439,7 +476,8 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
             }
             // accumulator drained: hand the TMEM stage back to the MMA warp
             tc_fence_before();
-            mbar_arrive(smem_u32(&tempty_bar[acc]));
+            if (NCTA == 2) mbar_arrive_cluster(tempty0 + 8u * acc);
+            else mbar_arrive(tempty0 + 8u * acc);
             if (p.stats) {
                 epi_bar(epi_threads);
                 for (int i = epi_tid; i < 2 * BN; i += epi_threads) {
@@ -455,15 +493,44 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (NCTA == 2) cluster_sync();   // neither CTA may exit (or free TMEM) while its peer can still touch its smem / barriers
+    else __syncthreads();
     if (warp == MMA_WARP) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+        if (NCTA == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
 }
 
 int g_umma_debug = 0;
-int g_prefetch_tiles = 0;   // measured: L2 prefetch of future tiles HURTS (the streaming convs are L2->SM bandwidth bound, not latency bound)
+int g_prefetch_tiles = 0;   // kept for HOIG_UMMA_PREFETCH_TILES compatibility; L2 prefetch of future tiles was measured to hurt and is gone   // measured: L2 prefetch of future tiles HURTS (the streaming convs are L2->SM bandwidth bound, not latency bound)
+
+int g_pair_mode = 1;        // 0: one CTA per tile; 1: CTA pairs (cta_group::2) where they pay off; 2: pairs wherever legal (tests)
+
+template <typename T, int NCTA>
+int launch_kernel(const UmmaParams &P, const CUtensorMap &map_w, const CUtensorMap *map_a, int grid, size_t smem, cudaStream_t stream)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(conv_umma_kernel<T, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess)
+            return check_launch("conv_umma smem attribute");
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = NCTA > 1 ? 1 : 0;
+    if (cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, NCTA>, P, map_w, map_a[0], map_a[1], map_a[2], map_a[3]) != cudaSuccess)
+        return check_launch("conv_umma_kernel launch");
+    return check_launch("conv_umma_kernel");
+}
 
 int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int dtype)
 {
@@ -475,10 +542,6 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     P.n_tiles = ceil_div(p.Npad, P.BN);
     P.m_tiles = p.N * p.tiles_per_image;
     P.k_blocks = p.Kpad / BK;
-    const int stage_bytes = A_STAGE_BYTES + P.BN * BK * 2;
-    P.stages = RING_BUDGET / stage_bytes;
-    if (P.stages > MAX_STAGES) P.stages = MAX_STAGES;
-    HOIG_REQUIRE(P.stages >= LOOKAHEAD + 1, "conv2d: not enough shared memory stages");
     P.cpt_shift = -1;
     if (p.Cin < 64) {
         const int cpt = p.Cin / 8;
@@ -491,20 +554,28 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     if (P.tma_a)   // view strides must be 16-byte multiples for a tensor map
         for (int v = 0; v < p.nviews; ++v)
             if ((p.view[v].sx * 2) % 16 || ((uintptr_t)p.view[v].base % 16)) P.tma_a = 0;
+    // CTA pairs: TMA-fed activations, an even number of 128-pixel tiles, and a weight tile that splits into two
+    // halves of whole 16-row groups
+    // Short reductions stay on single CTAs: a pair pays cluster-scope barrier latency per tile, measured to cost more than
+    // the halved weight traffic saves below ~12 k-blocks (7x1 stems, 64->128 stride-2, 128->64 transposed).
+    const bool pair_ok = P.tma_a && P.m_tiles % 2 == 0 && P.BN % 32 == 0 && p.Npad % P.BN == 0;
+    const int ncta = (pair_ok && (g_pair_mode == 2 || (g_pair_mode == 1 && P.k_blocks >= 12))) ? 2 : 1;
+    const int stage_bytes = A_STAGE_BYTES + (P.BN / ncta) * BK * 2;
+    P.stages = RING_BUDGET / stage_bytes;
+    if (P.stages > MAX_STAGES) P.stages = MAX_STAGES;
+    HOIG_REQUIRE(P.stages >= LOOKAHEAD + 1, "conv2d: not enough shared memory stages");
 
-    // streaming inputs (larger than a fraction of L2) need HBM latency hidden beyond the smem ring
-    const double in_bytes = (double)p.N * p.view[0].sn * 2.0;
     P.debug = g_umma_debug;
     P.tpi_shift = -1;
     if ((p.tiles_per_image & (p.tiles_per_image - 1)) == 0) { P.tpi_shift = 0; while ((1 << P.tpi_shift) < p.tiles_per_image) ++P.tpi_shift; }
-    P.prefetch_tiles = (P.tma_a && g_prefetch_tiles > 0 && in_bytes > 48e6) ? g_prefetch_tiles : 0;
+    P.prefetch_tiles = 0;
 
     CUtensorMap map_w, map_a[4];
     int st;
     {
         const cuuint64_t dims[2] = {(cuuint64_t)p.Kpad, (cuuint64_t)p.Npad};
         const cuuint64_t strides[1] = {(cuuint64_t)p.ldw * 2};
-        const cuuint32_t box[2] = {BK, (cuuint32_t)P.BN};
+        const cuuint32_t box[2] = {BK, (cuuint32_t)(P.BN / ncta)};
         st = make_map(&map_w, p.weight, 2, dims, strides, box, "weights", dtype);
         if (st != HOIG_OK) return st;
     }
@@ -527,16 +598,15 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaFuncSetAttribute(conv_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess ||
-            cudaFuncSetAttribute(conv_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess)
-            return check_launch("conv_umma smem attribute");
     }
-    const int total = P.m_tiles * P.n_tiles;
-    const int grid = total < num_sms ? total : num_sms;
+    const int total = (P.m_tiles / ncta) * P.n_tiles;
+    const int units = num_sms / ncta;                       // CTAs or CTA pairs that fit the GPU
+    const int grid = (total < units ? total : units) * ncta;
     const size_t smem = (size_t)STG_BYTES + (size_t)P.stages * stage_bytes + 1024;
-    if (dtype == HOIG_F16) conv_umma_kernel<__half><<<grid, THREADS, smem, stream>>>(P, map_w, map_a[0], map_a[1], map_a[2], map_a[3]);
-    else conv_umma_kernel<__nv_bfloat16><<<grid, THREADS, smem, stream>>>(P, map_w, map_a[0], map_a[1], map_a[2], map_a[3]);
-    return check_launch("conv_umma_kernel");
+    if (dtype == HOIG_F16)
+        return ncta == 2 ? launch_kernel<__half, 2>(P, map_w, map_a, grid, smem, stream) : launch_kernel<__half, 1>(P, map_w, map_a, grid, smem, stream);
+    return ncta == 2 ? launch_kernel<__nv_bfloat16, 2>(P, map_w, map_a, grid, smem, stream)
+                     : launch_kernel<__nv_bfloat16, 1>(P, map_w, map_a, grid, smem, stream);
 }
 
 }  // namespace
@@ -553,6 +623,8 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
         g_force_gather = (e && e[0] == '1') ? 1 : 0;
         const char *pf = getenv("HOIG_UMMA_PREFETCH_TILES");
         if (pf) g_prefetch_tiles = atoi(pf);
+        const char *pm = getenv("HOIG_UMMA_2CTA");
+        if (pm) g_pair_mode = atoi(pm);
         const char *dbg = getenv("HOIG_UMMA_DEBUG");
         if (dbg) g_umma_debug = atoi(dbg);
     }
@@ -568,3 +640,5 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
 // Diagnostic switch: route every bf16 conv through the cp.async gather A-operand path
 // (1) or let eligible convs use TMA boxes (0).
 extern "C" void hoig_set_umma_gather_only(int on) { hoig::g_force_gather = on ? 1 : 0; }
+// Diagnostic switch: 0 = one CTA per tile, 1 = CTA pairs (cta_group::2) where they pay off (default), 2 = wherever legal.
+extern "C" void hoig_set_umma_pair_mode(int on) { hoig::g_pair_mode = on; }

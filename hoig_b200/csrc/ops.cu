@@ -106,12 +106,15 @@ __global__ void __launch_bounds__(256, 4) instnorm_apply_kernel(const T *__restr
     extern __shared__ float sm[];  // mean[C] | scale[C] | shift[C]
     float *meanv = sm, *scale = sm + C, *shift = sm + 2 * C;
     const int n = blockIdx.y;
+    const double inv_hw = 1.0 / (double)HW;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const double s = stats[((int64_t)n * C + c) * 2], q = stats[((int64_t)n * C + c) * 2 + 1];
-        const double mean = s / HW;
-        double var = q / HW - mean * mean;
+        // the cancellation-prone part (E[x^2] - mean^2) stays in double; 1/sqrt runs in fp32 like the reference's
+        // instance norm (a double sqrt + divide per channel per CTA used to cost as much as the CTA's pixels)
+        const double2 sq = *reinterpret_cast<const double2 *>(stats + ((int64_t)n * C + c) * 2);
+        const double mean = sq.x * inv_hw;
+        double var = sq.y * inv_hw - mean * mean;
         if (var < 0) var = 0;
-        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float rstd = 1.0f / sqrtf((float)var + eps);
         const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
         meanv[c] = (float)mean;
         scale[c] = rstd * g;

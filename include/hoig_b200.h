@@ -139,6 +139,8 @@ int hoig_conv2d(const hoigConvDesc *desc, hoigStream_t stream);
  * forces the bf16 kernel's A operand through the cp.async gather path instead of TMA boxes. */
 int hoig_conv2d_simt(const hoigConvDesc *desc, hoigStream_t stream);
 void hoig_set_umma_gather_only(int on);
+/* Test hook: 0 = one CTA per tile, 1 (default) = CTA pairs (cta_group::2) for long reductions, 2 = pairs wherever legal. */
+void hoig_set_umma_pair_mode(int on);
 /* Tuning hook: pixels per rasterizer band (256..16384; the band's 64-bit key buffer lives in shared memory). */
 void hoig_set_rasterizer_band_pixels(int n);
 

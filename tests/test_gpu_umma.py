@@ -101,3 +101,25 @@ def test_conv_f16_umma(case):
     assert ok and rel < 2e-3
     if st is not None:
         assert torch.allclose(st.cpu(), st_ref, rtol=1e-3, atol=0.2)
+
+
+PAIR_CASES = [c for c in CONV_CASES if c[0] in ("3x3_s1_k4608", "3x3_s1_c128", "3x3_s2", "7x1_stem_c64", "convT_3x3_s2", "1x1_k3200_attn_gemm",
+                                                 "3x3_s1_c128_n512_bias_res", "3x3_s1_c64")]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=[c[0] for c in PAIR_CASES])
+def test_cta_pair_equals_single_cta(case):
+    """cta_group::2 (256-pixel tiles over a CTA pair, half the weight tile per CTA) accumulates in the same k order as the
+    one-CTA kernel: outputs are bit-identical, the per-plane statistics agree to fp32 summation order."""
+    import hoig_b200._lib as L
+    outs = []
+    for mode in (0, 2):
+        L.lib().hoig_set_umma_pair_mode(mode)
+        try:
+            out, ref, st, st_ref = _run_conv(case, torch.bfloat16)
+        finally:
+            L.lib().hoig_set_umma_pair_mode(1)
+        outs.append((out.cpu(), None if st is None else st.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    if outs[0][1] is not None:
+        assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-3)
