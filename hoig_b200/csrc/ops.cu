@@ -628,6 +628,76 @@ __global__ void hunfold_kernel(const float *__restrict__ src, int B, int C, int 
     }
 }
 
+struct FoldSegs8 {          // per output channel g: its NCHW plane base (image 0) and the image stride in elements
+    float *out[8];
+    int64_t bstride[8];
+};
+// Same result, staged through shared memory: a CTA takes 128 consecutive pixels of one image row, loads the C input rows
+// (plus k/2 halo pixels each side) with coalesced reads, and writes each pixel's Cpad channels as consecutive 16-byte
+// chunks from consecutive lanes (the per-pixel kernel above scatters 16-byte pieces 128+ bytes apart).
+template <typename T>
+__global__ void __launch_bounds__(256) hunfold_row_kernel(const float *__restrict__ src, int C, int H, int W, int k, T *__restrict__ dst,
+                                                          int64_t ldd, int Cpad)
+{
+    constexpr int PX = 128, MAXC = 16, MAXK = 7;
+    __shared__ float tile[MAXC][PX + MAXK - 1];
+    __shared__ int8_t s_of[256], c_of[256];   // channel kc -> (tap s, input channel c), s = -1: zero padding
+    const int segs = W / PX;
+    const int x0 = (blockIdx.x % segs) * PX, y = (blockIdx.x / segs) % H, b = blockIdx.x / (segs * H);
+    const int halo = k / 2, tw = PX + k - 1;
+    for (int i = threadIdx.x; i < Cpad; i += blockDim.x) {
+        const int sft = i / C;
+        s_of[i] = sft < k ? (int8_t)sft : (int8_t)-1;
+        c_of[i] = (int8_t)(i - sft * C);
+    }
+    const float *row = src + ((int64_t)b * C * H + y) * W;
+    for (int i = threadIdx.x; i < C * tw; i += blockDim.x) {
+        const int c = i / tw, j = i - c * tw, xx = x0 - halo + j;
+        tile[c][j] = (xx >= 0 && xx < W) ? __ldg(row + (int64_t)c * H * W + xx) : 0.f;
+    }
+    __syncthreads();
+    const int chunks = Cpad / 8;
+    T *drow = dst + (((int64_t)b * H + y) * W + x0) * ldd;
+    for (int i = threadIdx.x; i < PX * chunks; i += blockDim.x) {
+        const int px = i / chunks, ch = i - px * chunks;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int kc = ch * 8 + j, sft = s_of[kc];
+            v[j] = sft >= 0 ? tile[c_of[kc]][px + sft] : 0.f;
+        }
+        store8(drow + (int64_t)px * ldd + ch * 8, v);
+    }
+}
+
+// hfold for G == 8 (the merged heads): one thread per pixel reads the k neighbours' 8 partial sums as one 16-byte load each
+// and writes the 8 output planes with coalesced stores.
+template <typename T>
+__global__ void hfold8_kernel(const T *__restrict__ z, int64_t ldz, int B, int H, int W, int k, const int *__restrict__ act_table,
+                              FoldSegs8 segs)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * H * W) return;
+    const int x = (int)(i % W), y = (int)((i / W) % H), b = (int)(i / ((int64_t)W * H));
+    float acc[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) acc[g] = 0.f;
+    const T *zrow = z + ((int64_t)b * H + y) * W * ldz;
+    for (int sft = 0; sft < k; ++sft) {
+        const int xx = x + sft - k / 2;
+        if (xx < 0 || xx >= W) continue;
+        float v[8];
+        load8(zrow + (int64_t)xx * ldz + sft * 8, v);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) acc[g] += v[g];
+    }
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const float r = apply_act(acc[g], act_table ? act_table[g] : HOIG_ACT_NONE);
+        if (segs.out[g]) segs.out[g][(int64_t)b * segs.bstride[g] + (int64_t)y * W + x] = r;
+    }
+}
+
 struct FoldSegs {
     float *out[4];
     int c0[4], n[4], nseg;
@@ -854,7 +924,10 @@ extern "C" int hoig_hunfold_nchw(const float *src, int B, int C, int H, int W, i
     if (n == 0) return HOIG_OK;
     return dispatch(dtype, [&](auto *tag) {
         using T = std::remove_pointer_t<decltype(tag)>;
-        hunfold_kernel<T><<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>(src, B, C, H, W, k, (T *)dst, ldd, Cpad);
+        if (W % 128 == 0 && C <= 16 && k <= 7 && Cpad <= 256)
+            hunfold_row_kernel<T><<<(unsigned)(n / 128), 256, 0, as_stream(stream)>>>(src, C, H, W, k, (T *)dst, ldd, Cpad);
+        else
+            hunfold_kernel<T><<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>(src, B, C, H, W, k, (T *)dst, ldd, Cpad);
         return check_launch("hunfold_kernel");
     });
 }
@@ -873,9 +946,21 @@ extern "C" int hoig_hfold_nchw(const void *z, int64_t ldz, int dtype, int B, int
     }
     const int64_t n = (int64_t)B * G * H * W;
     if (n == 0) return HOIG_OK;
+    FoldSegs8 s8;
+    for (int g = 0; g < 8; ++g) {
+        s8.out[g] = nullptr; s8.bstride[g] = 0;
+        for (int q = 0; q < nseg; ++q)
+            if (g >= seg_c0[q] && g < seg_c0[q] + seg_n[q]) {
+                s8.out[g] = outs[q] + (int64_t)(g - seg_c0[q]) * H * W;
+                s8.bstride[g] = (int64_t)seg_n[q] * H * W;
+            }
+    }
     return dispatch(dtype, [&](auto *tag) {
         using T = std::remove_pointer_t<decltype(tag)>;
-        hfold_kernel<T><<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>((const T *)z, ldz, B, H, W, G, k, act_table, segs);
+        if (G == 8 && ldz % 8 == 0)
+            hfold8_kernel<T><<<ceil_div((int64_t)B * H * W, TPB), TPB, 0, as_stream(stream)>>>((const T *)z, ldz, B, H, W, k, act_table, s8);
+        else
+            hfold_kernel<T><<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>((const T *)z, ldz, B, H, W, G, k, act_table, segs);
         return check_launch("hfold_kernel");
     });
 }

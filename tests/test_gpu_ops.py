@@ -169,6 +169,17 @@ def test_fold_and_unfold_ops():
         assert ok
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("C,k,cpad", [(9, 7, 64), (3, 7, 24), (8, 3, 24), (16, 5, 80)])
+def test_hunfold_row_kernel_matches_contract(dtype, C, k, cpad):
+    """Rows that are multiples of 128 pixels take the shared-memory staged kernel."""
+    g = torch.Generator().manual_seed(11)
+    x = _rand(g, 2, C, 5, 256)
+    a = ops.hunfold_nchw(x.cuda(), torch.empty(2, 5, 256, cpad, dtype=dtype, device="cuda"), k)
+    b = emu_ops.hunfold_nchw(x, torch.empty(2, 5, 256, cpad, dtype=dtype), k)
+    assert torch.equal(a.cpu(), b)
+
+
 # --------------------------------------------------------------------------- convolution
 CONV_CASES = [
     # name, N, H, Cin, Cout, k, stride, mode, extras
