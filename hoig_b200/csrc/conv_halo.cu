@@ -32,8 +32,9 @@ constexpr int HBM = 2 * HM;                  // rows per tile
 constexpr int HBK = 64;
 constexpr int A_HALF_BYTES = 17 * 1024;      // (128 + up to 7 halo rows) x 128 B, rounded up to the 1024 B swizzle period
 constexpr int A_STAGE = 2 * A_HALF_BYTES;
-constexpr int H_THREADS = 320;
+constexpr int H_THREADS = 352;
 constexpr int H_EPI_WARP0 = 2, H_EPI_WARPS = 8;
+constexpr int H_MMA_WARP0 = 1, H_MMA_WARP1 = 10;   // one issuing warp per accumulator half
 constexpr int H_MAX_STAGES = 8;
 constexpr int H_SMEM_TOTAL = 216 * 1024;
 
@@ -74,9 +75,10 @@ conv_halo_kernel(const HaloParams P, const __grid_constant__ CUtensorMap map_a0,
     const bool per_tap = P.variant == 2;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P.a_stages; ++s) { mbar_init(smem_u32(&afull[s]), 1); mbar_init(smem_u32(&aempty[s]), 1); }
-        for (int s = 0; s < P.b_stages; ++s) { mbar_init(smem_u32(&bfull[s]), 1); mbar_init(smem_u32(&bempty[s]), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tfull[a]), 1); mbar_init(smem_u32(&tempty[a]), H_EPI_WARPS * 32); }
+        // "empty" and "accumulator full" take one tcgen05.commit from each of the two MMA-issuing warps
+        for (int s = 0; s < P.a_stages; ++s) { mbar_init(smem_u32(&afull[s]), 1); mbar_init(smem_u32(&aempty[s]), 2); }
+        for (int s = 0; s < P.b_stages; ++s) { mbar_init(smem_u32(&bfull[s]), 1); mbar_init(smem_u32(&bempty[s]), 2); }
+        for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tfull[a]), 2); mbar_init(smem_u32(&tempty[a]), H_EPI_WARPS * 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -136,8 +138,12 @@ conv_halo_kernel(const HaloParams P, const __grid_constant__ CUtensorMap map_a0,
                     }
             }
         }
-    } else if (warp == 1) {
-        // ================================================================== MMA issuer
+    } else if (warp == H_MMA_WARP0 || warp == H_MMA_WARP1) {
+        // ================================================================== MMA issuers
+        // One warp per 128-row accumulator half.  A single thread sustains one 128 x N x 16 MMA per ~65-100 cycles of issue
+        // overhead, more than a narrow (N <= 128) MMA executes in (48-64 cycles, scripts/probes/mma_probe.cu); two
+        // independent issue streams fill the tensor pipe.
+        const int half = warp == H_MMA_WARP0 ? 0 : 1;
         {   // whole warp runs the loop; one elected lane issues
             constexpr uint32_t kFmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
             const uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(HM >> 4) << 24);
@@ -176,11 +182,9 @@ conv_halo_kernel(const HaloParams P, const __grid_constant__ CUtensorMap map_a0,
                             const uint64_t das = da + (uint64_t)(per_tap ? 0 : s * 8);
                             if (elect_one()) {
 #pragma unroll
-                                for (int half = 0; half < 2; ++half)
-#pragma unroll
-                                    for (int k = 0; k < HBK / 16; ++k)
-                                        umma_bf16(d_tmem + (uint32_t)(half * BN), das + (uint64_t)(half * (A_HALF_BYTES >> 4) + 2 * k),
-                                                  db + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
+                                for (int k = 0; k < HBK / 16; ++k)
+                                    umma_bf16(d_tmem + (uint32_t)(half * BN), das + (uint64_t)(half * (A_HALF_BYTES >> 4) + 2 * k),
+                                              db + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
                                 umma_commit(bempty0 + 8u * b_st);
                                 if (s == P.KW - 1 || per_tap) umma_commit(aempty0 + 8u * a_st);
                             }
@@ -192,9 +196,9 @@ conv_halo_kernel(const HaloParams P, const __grid_constant__ CUtensorMap map_a0,
                 __syncwarp();
             }
         }
-    } else {
+    } else if (warp >= H_EPI_WARP0 && warp < H_EPI_WARP0 + H_EPI_WARPS) {
         // ==================================================================== epilogue
-        const int quad = warp & 3, half = (warp - H_EPI_WARP0) >> 2;
+        const int quad = warp & 3, half = (warp - H_EPI_WARP0) >> 2;   // warps 2-9
         const int n_chunks = P.Cout / 16;
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++tcount) {

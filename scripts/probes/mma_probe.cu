@@ -42,7 +42,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 __global__ void __launch_bounds__(128, 1) probe(int N, int naccs, int per_commit, int iters, int kstep_mode, int extra, long long *out)
 {
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
-    __shared__ __align__(8) uint64_t bar, bar2, bar3;
+    __shared__ __align__(8) uint64_t bar, bar2, bar3, bar4[4];
     __shared__ uint32_t tmem_base_s;
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) ((uint32_t *)smem)[i] = 0;
@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int naccs, int per_commit
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar3)));
+        for (int w = 0; w < 4; ++w) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar4[w])));
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar3)) : "memory");   // phase 0 of bar3 is complete
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -62,33 +63,33 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int naccs, int per_commit
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
-    if (threadIdx.x < 32) {
+    const int nissue = extra < 1 ? 1 : extra;
+    if (threadIdx.x < 32 * nissue) {
+        const int wid = threadIdx.x / 32;
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t a = smem_u32(smem), b = a + 16384;
         uint32_t ncommit = 0;
         const long long t0 = clock64();
         const uint64_t da = umma_desc(a), db = umma_desc(b);
         const uint32_t amask = (uint32_t)naccs - 1, bar_a = smem_u32(&bar);
-        const int shift = kstep_mode ? 2 : 0;
+        const int shift = (kstep_mode & 2) ? 0 : 2;
 #pragma unroll 1
         for (int i = 0; i < iters; i += 4) {
             if (elect_one()) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t acc_i = ((uint32_t)(i + j) >> shift) & amask;
-                    umma(tmem + acc_i * (uint32_t)N, da + (uint64_t)(kstep_mode ? j * 2 : 0), db + (uint64_t)(kstep_mode ? j * 2 : 0), idesc, 1u);
+                    umma(tmem + (acc_i + (uint32_t)wid * (uint32_t)naccs) * (uint32_t)N, da + (uint64_t)(kstep_mode ? j * 2 : 0), db + (uint64_t)(kstep_mode ? j * 2 : 0), idesc, 1u);
                 }
                 if (per_commit) { commit(bar_a); ++ncommit; }
             }
             __syncwarp();
-            if (extra & 1) mbar_wait(smem_u32(&bar3), 0);                                  // already-complete wait
-            if (extra & 2) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (extra & 4) { long long t = clock64(); while (clock64() - t < 200) { } }    // 200 idle cycles
+
         }
         const long long t1 = clock64();
-        if (elect_one()) commit(smem_u32(&bar2));      // fires when every MMA above has retired
+        if (elect_one()) commit(smem_u32(&bar4[wid]));      // fires when every MMA above has retired
         __syncwarp();
-        mbar_wait(smem_u32(&bar2), 0);
+        mbar_wait(smem_u32(&bar4[wid]), 0);
         const long long t2 = clock64();
         if (blockIdx.x == 0 && threadIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
     }
@@ -103,13 +104,13 @@ int main()
     cudaMalloc(&out, 16);
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     const int iters = 4096;
-    printf("grid N naccs per_commit extra(1=wait,2=fence,4=200cyc idle) | issue cyc/MMA | total cyc/MMA | floor(N/2)\n");
+    printf("grid N naccs per_commit issuing warps (each its own accumulator; cycles are per MMA of ONE warp) | issue cyc/MMA | total cyc/MMA | floor(N/2)\n");
     for (int grid : {1, 148})
         for (int N : {64, 128, 256})
-            for (int naccs : {1, 2})
+            for (int naccs : {1})
                 for (int pc : {4})
-                    for (int ks : {0, 1, 2, 3, 4, 7}) {
-                        if (naccs * N > 512 || grid == 1) continue;
+                    for (int ks : {1, 2, 4}) {     // ks = number of issuing warps here
+                        if (naccs * ks * N > 512 || grid == 1) continue;
                         probe<<<grid, 128, 50 * 1024 + 1024>>>(N, naccs, pc, iters, 1, ks, out);
                         long long h[2];
                         cudaError_t e = cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
