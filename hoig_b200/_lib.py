@@ -83,6 +83,7 @@ _SIGNATURES = {
     "hoig_conv2d_halo": (c_int, [c_int, c_int, c_int, c_int, POINTER(HaloConvSeg), c_int, c_void_p]),
     "hoig_set_halo_variant": (None, [c_int]),
     "hoig_set_umma_pair_mode": (None, [c_int]),
+    "hoig_set_umma_dual_mode": (None, [c_int]),
     "hoig_attn_combine": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "hoig_grid_sample": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int,

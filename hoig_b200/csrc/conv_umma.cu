@@ -38,7 +38,7 @@ constexpr int BK = 64;                 // bf16 elements per k-block = one 128-by
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int EPI_WARPS = 8, PROD_WARPS = 4;    // epilogue warp w: TMEM lane quadrant w % 4, 16-column chunks of parity w / 4
 constexpr int EPI_END = 16;                     // warps 12-15: a further epilogue group
-constexpr int TMA_WARP = 16, MMA_WARP = 17, WB_WARP = 18;   // WB: weight-tile TMA producer in TMA-A mode
+constexpr int TMA_WARP = 16, MMA_WARP = 17, WB_WARP = 18, MMA2_WARP = 19;   // MMA2: second issue stream (dual mode)   // WB: weight-tile TMA producer in TMA-A mode
 constexpr int THREADS = 640;
 constexpr int MAX_STAGES = 8;
 constexpr int LOOKAHEAD = 3;           // cp.async groups in flight per producer thread
@@ -57,6 +57,8 @@ struct UmmaParams {
     int cpt_shift;   // log2(Cin / 8) when Cin < 64 (chunk -> tap by shift), -1: generic division
     int prefetch_tiles;  // TMA-A: L2-prefetch the activation boxes this many tile rounds ahead (0 = off)
     int tpi_shift;       // log2(tiles_per_image) when it is a power of two, else -1
+    int dual;            // 1: two independent pipelines per CTA (narrow N): tiles alternate between two MMA-issuing warps,
+                         //    each with its own half of the smem ring and two of the four TMEM accumulator stages
     int debug;           // timing knock-outs (HOIG_UMMA_DEBUG, results are garbage): 1 = epilogue only drains TMEM, 2 = A tile loaded once per tile
 };
 
@@ -73,7 +75,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3)
 {
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
-    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[4], tempty_bar[4];
     __shared__ uint32_t tmem_base_smem;
     __shared__ float s_stats[4][2][256];   // per TMEM lane quadrant: plain += by its owning warps, no shared atomics
     __shared__ __align__(16) float s_bias[256 + 32];
@@ -96,7 +98,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
             mbar_init(smem_u32(&full_bar[s]), full_count);
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < 4; ++a) {
             mbar_init(smem_u32(&tfull_bar[a]), 1);
             mbar_init(smem_u32(&tempty_bar[a]), (uint32_t)(NCTA * (P.tma_a ? EPI_END : EPI_END - PROD_WARPS) * 32));
         }
@@ -252,73 +254,91 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
         const bool do_b = P.tma_a ? warp == WB_WARP : warp == TMA_WARP;
         if (do_a || do_b) {   // whole warp runs the loop; one elected lane issues
             const CUtensorMap *maps[4] = {&map_a0, &map_a1, &map_a2, &map_a3};
-            uint32_t st = 0, ph = 0;
+            // NP pipelines (1, or 2 in dual mode): pipeline w owns ring stages w, w+NP, ... and the CTA's tiles w, w+NP, ...
+            const int NP = P.dual ? 2 : 1;
+            const uint32_t sp = (uint32_t)(P.stages / NP);             // stages per pipeline
+            uint32_t q[2] = {0, 0}, ph[2] = {0, 0};
             const uint32_t empty0 = smem_u32(&empty_bar[0]);
             // the "full" barriers live in the leader CTA: both CTAs' TMA loads complete on them
             const uint32_t full0 = NCTA == 2 ? mapa(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
             const uint32_t b_rows = (uint32_t)(BN / NCTA);
             const uint32_t b_bytes = (uint32_t)(BN * BK * 2);          // whole pair
-            for (int tile = tile0; tile < total_tiles; tile += tile_step) {
-                int mt = tile, nt = 0;
-                if (P.n_tiles > 1) { mt = tile / P.n_tiles; nt = tile - mt * P.n_tiles; }
-                mt = mt * NCTA + (int)rank;
-                const int n_img = mt / p.tiles_per_image;
-                const int pix0 = (mt % p.tiles_per_image) * BM;
-                const int gy0 = pix0 / p.GW, gx0 = pix0 % p.GW;
+            for (int tbase = tile0; tbase < total_tiles; tbase += NP * tile_step) {
+                int n_img[2], gy0[2], gx0[2], nt[2];
+                bool live[2] = {false, false};
+                for (int w = 0; w < NP; ++w) {
+                    const int tile = tbase + w * tile_step;
+                    live[w] = tile < total_tiles;
+                    int mt = tile;
+                    nt[w] = 0;
+                    if (P.n_tiles > 1) { mt = tile / P.n_tiles; nt[w] = tile - mt * P.n_tiles; }
+                    mt = mt * NCTA + (int)rank;
+                    n_img[w] = mt / p.tiles_per_image;
+                    const int pix0 = (mt % p.tiles_per_image) * BM;
+                    gy0[w] = pix0 / p.GW; gx0[w] = pix0 % p.GW;
+                }
                 int tap = 0, c = 0;
                 for (int kb = 0; kb < P.k_blocks; ++kb) {
-                    // ring position / phase kept incrementally: a runtime division per k-block on this single
-                    // thread costs more than the MMAs of a short k-block
-                    mbar_wait(empty0 + 8u * st, ph ^ 1u);
-                    const uint32_t bar = full0 + 8u * st;
-                    const uint32_t a_dst = smem_base + st * (uint32_t)stage_bytes;
-                    if (do_a) {
-                        const bool skip_a = NCTA == 1 && (P.debug & 2) && kb > 0;
-                        const int tt = tap < p.ntaps ? tap : p.ntaps - 1;   // K padding blocks: any finite data (weights are zero)
-                        if (elect_one()) {
-                            if (skip_a) {
-                                mbar_arrive(bar);
-                            } else if (NCTA == 2) {
-                                if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[0]) + 8u * st, 2u * (uint32_t)A_STAGE_BYTES);
-                                tma_load_4d_2sm(a_dst, maps[p.tap_map[tt]], bar, c, gx0 + p.tap_dx[tt], gy0 + p.tap_dy[tt], n_img);
+                    const int tt = tap < p.ntaps ? tap : p.ntaps - 1;   // K padding blocks: any finite data (weights are zero)
+                    for (int w = 0; w < NP; ++w) {
+                        if (!live[w]) continue;
+                        // ring position / phase kept incrementally: a runtime division per k-block on this single
+                        // thread costs more than the MMAs of a short k-block
+                        const uint32_t st = q[w] * (uint32_t)NP + (uint32_t)w;
+                        mbar_wait(empty0 + 8u * st, ph[w] ^ 1u);
+                        const uint32_t bar = full0 + 8u * st;
+                        const uint32_t a_dst = smem_base + st * (uint32_t)stage_bytes;
+                        if (do_a) {
+                            const bool skip_a = NCTA == 1 && (P.debug & 2) && kb > 0;
+                            if (elect_one()) {
+                                if (skip_a) {
+                                    mbar_arrive(bar);
+                                } else if (NCTA == 2) {
+                                    if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[0]) + 8u * st, 2u * (uint32_t)A_STAGE_BYTES);
+                                    tma_load_4d_2sm(a_dst, maps[p.tap_map[tt]], bar, c, gx0[w] + p.tap_dx[tt], gy0[w] + p.tap_dy[tt], n_img[w]);
+                                } else {
+                                    mbar_arrive_expect_tx(bar, (uint32_t)A_STAGE_BYTES);
+                                    tma_load_4d(a_dst, maps[p.tap_map[tt]], bar, c, gx0[w] + p.tap_dx[tt], gy0[w] + p.tap_dy[tt], n_img[w]);
+                                }
+                            }
+                        } else if (elect_one()) {
+                            if (NCTA == 2) {
+                                if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[0]) + 8u * st, b_bytes);
+                                tma_load_2d_2sm(a_dst + A_STAGE_BYTES, &map_w, bar, kb * BK, nt[w] * BN + (int)(rank * b_rows));
                             } else {
-                                mbar_arrive_expect_tx(bar, (uint32_t)A_STAGE_BYTES);
-                                tma_load_4d(a_dst, maps[p.tap_map[tt]], bar, c, gx0 + p.tap_dx[tt], gy0 + p.tap_dy[tt], n_img);
+                                mbar_arrive_expect_tx(bar, b_bytes);
+                                tma_load_2d(a_dst + A_STAGE_BYTES, &map_w, bar, kb * BK, nt[w] * BN);
                             }
                         }
-                        c += BK;
-                        if (c >= p.Cin) { c = 0; ++tap; }
-                    } else if (elect_one()) {
-                        if (NCTA == 2) {
-                            if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[0]) + 8u * st, b_bytes);
-                            tma_load_2d_2sm(a_dst + A_STAGE_BYTES, &map_w, bar, kb * BK, nt * BN + (int)(rank * b_rows));
-                        } else {
-                            mbar_arrive_expect_tx(bar, b_bytes);
-                            tma_load_2d(a_dst + A_STAGE_BYTES, &map_w, bar, kb * BK, nt * BN);
-                        }
+                        __syncwarp();
+                        if (++q[w] == sp) { q[w] = 0; ph[w] ^= 1u; }
                     }
-                    __syncwarp();
-                    if (++st == (uint32_t)P.stages) { st = 0; ph ^= 1u; }
+                    c += BK;
+                    if (c >= p.Cin) { c = 0; ++tap; }
                 }
             }
         }
-    } else if (warp == MMA_WARP) {
+    } else if (warp == MMA_WARP || (warp == MMA2_WARP && P.dual)) {
         // ========================================================== MMA issuer
         if (rank == 0) {   // leader only.  Whole warp runs the loop (waits, fences); one elected lane issues the MMAs and commits
             // instruction descriptor: D = f32 (bit 4), A/B format bf16 = 1 / f16 = 0 (bits 7-9 / 10-12), K-major A and B,
             // N >> 3 at bit 17, M >> 4 at bit 24 (M = 256 for the CTA pair)
             constexpr uint32_t kFmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
             const uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((NCTA * BM) >> 4) << 24);
-            uint32_t st = 0, ph = 0, tcount = 0;
+            const int NP = P.dual ? 2 : 1, w = warp == MMA_WARP ? 0 : 1;    // this warp's pipeline
+            const uint32_t sp = (uint32_t)(P.stages / NP);
+            uint32_t q = 0, ph = 0;
             const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
             const uint64_t desc0 = umma_desc(smem_base);             // + (byte offset >> 4) addresses any tile of the ring
             const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
-            for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tcount) {
-                const uint32_t acc = tcount & 1;
-                mbar_wait(smem_u32(&tempty_bar[acc]), ((tcount >> 1) & 1) ^ 1);
+            // i = index of the tile in this CTA's sequence; TMEM accumulator stage i % (2*NP), used for the (i / (2*NP))-th time
+            for (uint32_t i = (uint32_t)w; tile0 + (int)i * tile_step < total_tiles; i += (uint32_t)NP) {
+                const uint32_t acc = i % (uint32_t)(2 * NP), use = i / (uint32_t)(2 * NP);
+                mbar_wait(smem_u32(&tempty_bar[acc]), (use & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)BN;
                 for (int kb = 0; kb < P.k_blocks; ++kb) {
+                    const uint32_t st = q * (uint32_t)NP + (uint32_t)w;
                     mbar_wait(full0 + 8u * st, ph);
                     tc_fence_after();
                     const uint64_t da = desc0 + (uint64_t)(st * stage16);
@@ -334,7 +354,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                         else umma_commit(empty0 + 8u * st);
                     }
                     __syncwarp();
-                    if (++st == (uint32_t)P.stages) { st = 0; ph ^= 1u; }
+                    if (++q == sp) { q = 0; ph ^= 1u; }
                 }
                 if (elect_one()) {   // accumulator complete (signalled in both CTAs of a pair)
                     if (NCTA == 2) umma_commit_2sm(smem_u32(&tfull_bar[acc]));
@@ -370,13 +390,14 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
             const bool valid = pix < npix;
             const int64_t m = valid ? out_pixel(p, n_img, pix) : 0;
             const int pc = p.phase_cout;     // > 0: transposed conv, column n = phase * pc + channel
-            const uint32_t acc = tcount & 1;
+            const uint32_t nacc = P.dual ? 4u : 2u;
+            const uint32_t acc = tcount % nacc, use = tcount / nacc;
             epi_bar(epi_threads);                       // previous tile fully drained: s_bias / s_stats reusable
             for (int i = epi_tid; i < BN; i += epi_threads) {
                 const int n = nt * BN + i;
                 s_bias[i] = (p.bias && n < p.Cout) ? __ldg(p.bias + (pc ? n % pc : n)) : 0.f;
             }
-            mbar_wait(smem_u32(&tfull_bar[acc]), (tcount >> 1) & 1);
+            mbar_wait(smem_u32(&tfull_bar[acc]), use & 1);
             tc_fence_after();
             epi_bar(epi_threads);
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)BN;
@@ -505,6 +526,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
 int g_umma_debug = 0;
 int g_prefetch_tiles = 0;   // kept for HOIG_UMMA_PREFETCH_TILES compatibility; L2 prefetch of future tiles was measured to hurt and is gone   // measured: L2 prefetch of future tiles HURTS (the streaming convs are L2->SM bandwidth bound, not latency bound)
 
+int g_dual_mode = 1;        // 1: narrow-N TMA convs run two MMA issue pipelines per CTA (HOIG_UMMA_DUAL=0 disables)
 int g_pair_mode = 1;        // 0: one CTA per tile; 1: CTA pairs (cta_group::2) where they pay off; 2: pairs wherever legal (tests)
 
 template <typename T, int NCTA>
@@ -563,6 +585,11 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     const int stage_bytes = A_STAGE_BYTES + (P.BN / ncta) * BK * 2;
     P.stages = RING_BUDGET / stage_bytes;
     if (P.stages > MAX_STAGES) P.stages = MAX_STAGES;
+    // Narrow tiles (N <= 128): one thread cannot issue 128 x N x 16 MMAs as fast as the tensor pipe retires them
+    // (scripts/probes/mma_probe.cu: ~65-100 cycles of issue overhead vs 48-64 cycles of execution), so two warps
+    // issue, each driving its own pipeline (half of the ring, two of four accumulator stages, alternate tiles).
+    P.dual = (g_dual_mode && P.tma_a && P.BN <= 128 && P.stages >= 4) ? 1 : 0;
+    if (P.dual) P.stages &= ~1;
     HOIG_REQUIRE(P.stages >= LOOKAHEAD + 1, "conv2d: not enough shared memory stages");
 
     P.debug = g_umma_debug;
@@ -623,6 +650,8 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
         g_force_gather = (e && e[0] == '1') ? 1 : 0;
         const char *pf = getenv("HOIG_UMMA_PREFETCH_TILES");
         if (pf) g_prefetch_tiles = atoi(pf);
+        const char *dm = getenv("HOIG_UMMA_DUAL");
+        if (dm) g_dual_mode = atoi(dm);
         const char *pm = getenv("HOIG_UMMA_2CTA");
         if (pm) g_pair_mode = atoi(pm);
         const char *dbg = getenv("HOIG_UMMA_DEBUG");
@@ -642,3 +671,5 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
 extern "C" void hoig_set_umma_gather_only(int on) { hoig::g_force_gather = on ? 1 : 0; }
 // Diagnostic switch: 0 = one CTA per tile, 1 = CTA pairs (cta_group::2) where they pay off (default), 2 = wherever legal.
 extern "C" void hoig_set_umma_pair_mode(int on) { hoig::g_pair_mode = on; }
+// Diagnostic switch: 1 = two MMA issue pipelines per CTA for narrow-N tiles (default), 0 = one.
+extern "C" void hoig_set_umma_dual_mode(int on) { hoig::g_dual_mode = on ? 1 : 0; }

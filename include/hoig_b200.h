@@ -141,6 +141,8 @@ int hoig_conv2d_simt(const hoigConvDesc *desc, hoigStream_t stream);
 void hoig_set_umma_gather_only(int on);
 /* Test hook: 0 = one CTA per tile, 1 (default) = CTA pairs (cta_group::2) for long reductions, 2 = pairs wherever legal. */
 void hoig_set_umma_pair_mode(int on);
+/* Test hook: 1 (default) = narrow-N tensor-core convs run two MMA issue pipelines per CTA, 0 = one. */
+void hoig_set_umma_dual_mode(int on);
 /* Tuning hook: pixels per rasterizer band (256..16384; the band's 64-bit key buffer lives in shared memory). */
 void hoig_set_rasterizer_band_pixels(int n);
 

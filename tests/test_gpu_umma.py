@@ -123,3 +123,27 @@ def test_cta_pair_equals_single_cta(case):
     assert torch.equal(outs[0][0], outs[1][0])
     if outs[0][1] is not None:
         assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-3)
+
+
+DUAL_CASES = [c for c in CONV_CASES if c[0] in ("3x3_s1_c64", "3x3_s1_w64", "3x3_s1_w256_many_tiles", "3x3_s2", "7x1_stem_c64", "1x1_k3200_attn_gemm",
+                                                 "7x7_heads_merged_act_table")]
+
+
+@pytest.mark.parametrize("pair", [0, 2], ids=["single_cta", "cta_pair"])
+@pytest.mark.parametrize("case", DUAL_CASES, ids=[c[0] for c in DUAL_CASES])
+def test_dual_issue_pipelines_equal_single(case, pair):
+    """Two MMA issue pipelines per CTA (narrow N) only change which warp issues which tile: bit-identical outputs."""
+    import hoig_b200._lib as L
+    outs = []
+    L.lib().hoig_set_umma_pair_mode(pair)
+    try:
+        for mode in (0, 1):
+            L.lib().hoig_set_umma_dual_mode(mode)
+            out, ref, st, st_ref = _run_conv(case, torch.bfloat16)
+            outs.append((out.cpu(), None if st is None else st.cpu()))
+    finally:
+        L.lib().hoig_set_umma_dual_mode(1)
+        L.lib().hoig_set_umma_pair_mode(1)
+    assert torch.equal(outs[0][0], outs[1][0])
+    if outs[0][1] is not None:
+        assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-3)
