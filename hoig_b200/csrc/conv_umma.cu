@@ -57,6 +57,7 @@ struct UmmaParams {
     int cpt_shift;   // log2(Cin / 8) when Cin < 64 (chunk -> tap by shift), -1: generic division
     int prefetch_tiles;  // TMA-A: L2-prefetch the activation boxes this many tile rounds ahead (0 = off)
     int tpi_shift;       // log2(tiles_per_image) when it is a power of two, else -1
+    int contig;          // 1: contiguous tile range per CTA, 0: tiles strided by the grid size
     int dual;            // 1: two independent pipelines per CTA (narrow N): tiles alternate between two MMA-issuing warps,
                          //    each with its own half of the smem ring and two of the four TMEM accumulator stages
     int debug;           // timing knock-outs (HOIG_UMMA_DEBUG, results are garbage): 1 = epilogue only drains TMEM, 2 = A tile loaded once per tile
@@ -87,10 +88,16 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     const uint32_t stg_base = smem_u32(smem);                  // epilogue staging first (1024-aligned)
     const uint32_t smem_base = stg_base + STG_BYTES;           // then the operand ring
-    const int total_tiles = (P.m_tiles / NCTA) * P.n_tiles;    // tiles of NCTA*128 pixels x BN channels
     const int npix = p.GH * p.GW;
     const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;  // 0 = leader of the pair
-    const int tile0 = (int)blockIdx.x / NCTA, tile_step = (int)gridDim.x / NCTA;
+    // Each CTA (pair) walks a CONTIGUOUS range of tiles: consecutive tiles then share their image (and n-tile), so the
+    // epilogue flushes the per-plane statistics once per image instead of once per tile, and the vertical taps of
+    // consecutive tiles re-read rows this CTA has just pulled through L2.
+    const int tile_units = (int)gridDim.x / NCTA, unit = (int)blockIdx.x / NCTA;
+    const int all_tiles = (P.m_tiles / NCTA) * P.n_tiles;
+    const int tile0 = P.contig ? (int)((int64_t)unit * all_tiles / tile_units) : unit;
+    const int total_tiles = P.contig ? (int)((int64_t)(unit + 1) * all_tiles / tile_units) : all_tiles;   // end of this CTA's range
+    const int tile_step = P.contig ? 1 : tile_units;
 
     if (threadIdx.x == 0) {
         const uint32_t full_count = P.tma_a ? 2u : (uint32_t)(PROD_WARPS * 32 + 1);   // TMA-A: one arrive.expect_tx per producer thread
@@ -381,6 +388,19 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
         const bool all_valid = npix % BM == 0;
         uint32_t tcount = 0;
         const uint32_t tempty0 = NCTA == 2 ? mapa(smem_u32(&tempty_bar[0]), 0) : smem_u32(&tempty_bar[0]);   // in the leader CTA
+        int cur_img = -1, cur_nt = -1;
+        // per-plane sum / sum of squares of the tiles since the last flush: one atomicAdd(double) per column
+        auto flush_stats = [&](int img, int ntile) {
+            const int pcs = p.phase_cout;
+            for (int i = epi_tid; i < 2 * BN; i += epi_threads) {
+                const int which = i / BN, col = i % BN;
+                const int n = ntile * BN + col;
+                const float tot = s_stats[0][which][col] + s_stats[1][which][col] + s_stats[2][which][col] + s_stats[3][which][col];
+                if (n < p.Cout)
+                    atomicAdd(&p.stats[((int64_t)img * (pcs ? pcs : p.Cout) + (pcs ? n % pcs : n)) * 2 + which], (double)tot);
+                s_stats[0][which][col] = 0.f; s_stats[1][which][col] = 0.f; s_stats[2][which][col] = 0.f; s_stats[3][which][col] = 0.f;
+            }
+        };
         for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tcount) {
             int mt = tile, nt = 0;
             if (P.n_tiles > 1) { mt = tile / P.n_tiles; nt = tile - mt * P.n_tiles; }
@@ -392,14 +412,20 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
             const int pc = p.phase_cout;     // > 0: transposed conv, column n = phase * pc + channel
             const uint32_t nacc = P.dual ? 4u : 2u;
             const uint32_t acc = tcount % nacc, use = tcount / nacc;
-            epi_bar(epi_threads);                       // previous tile fully drained: s_bias / s_stats reusable
-            for (int i = epi_tid; i < BN; i += epi_threads) {
-                const int n = nt * BN + i;
-                s_bias[i] = (p.bias && n < p.Cout) ? __ldg(p.bias + (pc ? n % pc : n)) : 0.f;
+            if (n_img != cur_img || nt != cur_nt) {
+                // new (image, n-tile): hand the finished plane's statistics over and reload the bias slice
+                epi_bar(epi_threads);                   // every warp is done with the previous tiles' s_stats / s_bias
+                if (p.stats && cur_img >= 0) flush_stats(cur_img, cur_nt);
+                if (nt != cur_nt && p.bias)
+                    for (int i = epi_tid; i < BN; i += epi_threads) {
+                        const int n = nt * BN + i;
+                        s_bias[i] = n < p.Cout ? __ldg(p.bias + (pc ? n % pc : n)) : 0.f;
+                    }
+                cur_img = n_img; cur_nt = nt;
+                epi_bar(epi_threads);
             }
             mbar_wait(smem_u32(&tfull_bar[acc]), use & 1);
             tc_fence_after();
-            epi_bar(epi_threads);
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)BN;
             uint32_t ra[16], rb[16];
             auto finalize = [&](const uint32_t (&r)[16], int ch) {
@@ -499,17 +525,10 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
             tc_fence_before();
             if (NCTA == 2) mbar_arrive_cluster(tempty0 + 8u * acc);
             else mbar_arrive(tempty0 + 8u * acc);
-            if (p.stats) {
-                epi_bar(epi_threads);
-                for (int i = epi_tid; i < 2 * BN; i += epi_threads) {
-                    const int which = i / BN, col = i % BN;
-                    const int n = nt * BN + col;
-                    const float tot = s_stats[0][which][col] + s_stats[1][which][col] + s_stats[2][which][col] + s_stats[3][which][col];
-                    if (n < p.Cout)
-                        atomicAdd(&p.stats[((int64_t)n_img * (pc ? pc : p.Cout) + (pc ? n % pc : n)) * 2 + which], (double)tot);
-                    s_stats[0][which][col] = 0.f; s_stats[1][which][col] = 0.f; s_stats[2][which][col] = 0.f; s_stats[3][which][col] = 0.f;
-                }
-            }
+        }
+        if (p.stats && cur_img >= 0) {   // the last plane this CTA touched
+            epi_bar(epi_threads);
+            flush_stats(cur_img, cur_nt);
         }
     }
 
@@ -526,6 +545,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
 int g_umma_debug = 0;
 int g_prefetch_tiles = 0;   // kept for HOIG_UMMA_PREFETCH_TILES compatibility; L2 prefetch of future tiles was measured to hurt and is gone   // measured: L2 prefetch of future tiles HURTS (the streaming convs are L2->SM bandwidth bound, not latency bound)
 
+int g_contig_mode = 1;      // HOIG_UMMA_CONTIG
 int g_dual_mode = 1;        // 1: narrow-N TMA convs run two MMA issue pipelines per CTA (HOIG_UMMA_DUAL=0 disables)
 int g_pair_mode = 1;        // 0: one CTA per tile; 1: CTA pairs (cta_group::2) where they pay off; 2: pairs wherever legal (tests)
 
@@ -588,6 +608,7 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     // Narrow tiles (N <= 128): one thread cannot issue 128 x N x 16 MMAs as fast as the tensor pipe retires them
     // (scripts/probes/mma_probe.cu: ~65-100 cycles of issue overhead vs 48-64 cycles of execution), so two warps
     // issue, each driving its own pipeline (half of the ring, two of four accumulator stages, alternate tiles).
+    P.contig = g_contig_mode;
     P.dual = (g_dual_mode && P.tma_a && P.BN <= 128 && P.stages >= 4) ? 1 : 0;
     if (P.dual) P.stages &= ~1;
     HOIG_REQUIRE(P.stages >= LOOKAHEAD + 1, "conv2d: not enough shared memory stages");
@@ -650,6 +671,8 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
         g_force_gather = (e && e[0] == '1') ? 1 : 0;
         const char *pf = getenv("HOIG_UMMA_PREFETCH_TILES");
         if (pf) g_prefetch_tiles = atoi(pf);
+        const char *cm = getenv("HOIG_UMMA_CONTIG");
+        if (cm) g_contig_mode = atoi(cm);
         const char *dm = getenv("HOIG_UMMA_DUAL");
         if (dm) g_dual_mode = atoi(dm);
         const char *pm = getenv("HOIG_UMMA_2CTA");

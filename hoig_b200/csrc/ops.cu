@@ -61,6 +61,78 @@ __global__ void seg_resize_kernel(const float *__restrict__ seg, int B, int C, i
     store8(dst + bp * ldd + ch * 8, v);
 }
 
+// spade.py:30-31 resize + the 3x3 im2col of mlp_shared's input in one pass: dst[b,y,x, t*C + c] = nearest-resized
+// seg[b,c] at (y + t/3 - 1, x + t%3 - 1), zero outside the image (the conv's zero padding) and for channels >= 9*C.
+// The segmentation map has 3-12 channels; unfolding it once per resolution turns every mlp_shared conv of that resolution
+// into a 1x1 GEMM with K = 64 or 128 that TMA can feed (a 16-byte-chunk gather over 8/16 channels cannot).
+template <typename T>
+__global__ void seg_unfold3_kernel(const float *__restrict__ seg, int B, int C, int Hi, int Wi, T *__restrict__ dst,
+                                   int64_t ldd, int Kpad, int Ho, int Wo)
+{
+    const int chunks = Kpad / 8;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * Ho * Wo * chunks) return;
+    const int ch = (int)(i % chunks);
+    const int64_t bp = i / chunks;
+    const int x = (int)(bp % Wo), y = (int)((bp / Wo) % Ho), b = (int)(bp / ((int64_t)Wo * Ho));
+    const float sy = (float)Hi / (float)Ho, sx = (float)Wi / (float)Wo;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int kc = ch * 8 + j, t = kc / C, c = kc - t * C;
+        const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+        float val = 0.f;
+        if (t < 9 && yy >= 0 && yy < Ho && xx >= 0 && xx < Wo) {
+            const int iy = min((int)floorf(yy * sy), Hi - 1), ix = min((int)floorf(xx * sx), Wi - 1);
+            val = seg[(((int64_t)b * C + c) * Hi + iy) * Wi + ix];
+        }
+        v[j] = val;
+    }
+    store8(dst + bp * ldd + ch * 8, v);
+}
+
+// Same result, staged: a CTA takes PX consecutive pixels of one output row, gathers the three resized source rows (plus one
+// halo pixel each side) into shared memory once, and writes every pixel's Kpad channels as consecutive 16-byte chunks.
+template <typename T>
+__global__ void __launch_bounds__(256) seg_unfold3_row_kernel(const float *__restrict__ seg, int C, int Hi, int Wi, T *__restrict__ dst,
+                                                              int64_t ldd, int Kpad, int Ho, int Wo, int PX)
+{
+    constexpr int MAXPX = 64, MAXC = 16;
+    __shared__ float tile[3][MAXPX + 2][MAXC + 1];
+    __shared__ int8_t t_of[256], c_of[256];   // channel kc -> (tap t, seg channel c), t = -1: zero padding
+    const int segs = Wo / PX;
+    const int x0 = (blockIdx.x % segs) * PX, y = (blockIdx.x / segs) % Ho, b = blockIdx.x / (segs * Ho);
+    for (int i = threadIdx.x; i < Kpad; i += blockDim.x) {
+        const int t = i / C;
+        t_of[i] = t < 9 ? (int8_t)t : (int8_t)-1;
+        c_of[i] = (int8_t)(i - t * C);
+    }
+    const float sy = (float)Hi / (float)Ho, sx = (float)Wi / (float)Wo;
+    for (int i = threadIdx.x; i < 3 * (PX + 2) * C; i += blockDim.x) {
+        const int j = i % (PX + 2), c = (i / (PX + 2)) % C, r = i / (C * (PX + 2));   // consecutive lanes walk along x
+        const int yy = y + r - 1, xx = x0 + j - 1;
+        float val = 0.f;
+        if (yy >= 0 && yy < Ho && xx >= 0 && xx < Wo) {
+            const int iy = min((int)floorf(yy * sy), Hi - 1), ix = min((int)floorf(xx * sx), Wi - 1);
+            val = __ldg(seg + (((int64_t)b * C + c) * Hi + iy) * Wi + ix);
+        }
+        tile[r][j][c] = val;
+    }
+    __syncthreads();
+    const int chunks = Kpad / 8;
+    T *drow = dst + (((int64_t)b * Ho + y) * Wo + x0) * ldd;
+    for (int i = threadIdx.x; i < PX * chunks; i += blockDim.x) {
+        const int px = i / chunks, ch = i - px * chunks;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int kc = ch * 8 + j, t = t_of[kc];
+            v[j] = t >= 0 ? tile[t / 3][px + t % 3][c_of[kc]] : 0.f;
+        }
+        store8(drow + (int64_t)px * ldd + ch * 8, v);
+    }
+}
+
 // ------------------------------------------------------------- instance norm
 // grid (slabs, N); thread = (pixel lane, channel chunk)
 template <typename T>
@@ -1003,5 +1075,23 @@ extern "C" int hoig_attn_combine(const void *gt, int64_t ldgt, const void *gs, i
             attn_combine_kernel<T, 9><<<grid, 256, 0, as_stream(stream)>>>((const T *)gt, ldgt, (const T *)gs, ldgs, b1, w2, b2, (const T *)src,
                                                                           lds, flow, (const T *)tgt, ldt, (T *)dst, ldd, npix, h, C);
         return check_launch("attn_combine_kernel");
+    });
+}
+
+extern "C" int hoig_seg_unfold3(const float *seg, int B, int C, int Hi, int Wi, void *dst, int64_t ldd, int Kpad, int Ho, int Wo,
+                                int dtype, hoigStream_t stream)
+{
+    HOIG_REQUIRE(seg && dst && C > 0 && Kpad % 8 == 0 && Kpad >= 9 * C && ldd >= Kpad && ldd % 8 == 0, "seg_unfold3: bad argument");
+    const int64_t n = (int64_t)B * Ho * Wo * (Kpad / 8);
+    if (n == 0) return HOIG_OK;
+    return dispatch(dtype, [&](auto *tag) {
+        using T = std::remove_pointer_t<decltype(tag)>;
+        const int px = Wo % 64 == 0 ? 64 : (Wo % 32 == 0 ? 32 : 0);
+        if (px && C <= 16 && Kpad <= 256)
+            seg_unfold3_row_kernel<T><<<(unsigned)((int64_t)B * Ho * (Wo / px)), 256, 0, as_stream(stream)>>>(seg, C, Hi, Wi, (T *)dst, ldd, Kpad,
+                                                                                                          Ho, Wo, px);
+        else
+            seg_unfold3_kernel<T><<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>(seg, B, C, Hi, Wi, (T *)dst, ldd, Kpad, Ho, Wo);
+        return check_launch("seg_unfold3_kernel");
     });
 }

@@ -32,7 +32,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .packing import ceil_to, pack_conv_weight, pack_spade_gamma_beta
+from .packing import ceil_to, pack_conv_weight, pack_spade_gamma_beta, pack_unfolded3_weight
 
 NHIDDEN = 128  # spade.py:16
 ATTN_HIDDEN = 128  # extract_attn.py:11
@@ -275,8 +275,21 @@ class GeneratorB200(nn.Module):
     def _spade_apply(self, x, stats, prefix, seg_nchw, seg_cache, out=None):
         """spade.py:24-38 followed by the ReLU every caller applies (generator.py:66-67, 86-88)."""
         n, h, w, c = x.shape
-        s = self._seg(seg_nchw, h, seg_cache)
-        actv, _ = self._conv(s, prefix + "mlp_shared.0.weight", NHIDDEN, 3, bias=prefix + "mlp_shared.0.bias", act=ops.ACT_RELU)
+        if self.compute_dtype != torch.float32:
+            # tensor-core path: the segmentation map is resized AND 3x3-unfolded once per resolution (it has 3-12 channels), so
+            # every mlp_shared conv of that resolution is a TMA-fed 1x1 GEMM with K = 64 / 128
+            key = ("unfold3", h)
+            if key not in seg_cache:
+                b, cs = seg_nchw.shape[:2]
+                seg_cache[key] = ops.seg_unfold3(seg_nchw.float().contiguous(), self._new(b, h, h, ceil_to(9 * cs, 64)))
+            prm = self._p(prefix + "mlp_shared.0.weight")
+            wsh = self._cached(prefix + "mlp_shared.0#u3", [prm], lambda: pack_unfolded3_weight(prm, self.compute_dtype))
+            actv = self._new(n, h, w, NHIDDEN)
+            ops.conv2d(seg_cache[key], wsh, actv, kh=1, kw=1, stride=1, pad=0, bias=self._f32(prefix + "mlp_shared.0.bias"),
+                       act=ops.ACT_RELU)
+        else:
+            s = self._seg(seg_nchw, h, seg_cache)
+            actv, _ = self._conv(s, prefix + "mlp_shared.0.weight", NHIDDEN, 3, bias=prefix + "mlp_shared.0.bias", act=ops.ACT_RELU)
         wgb, bgb = self._gb(prefix)
         gb = self._new(n, h, w, 2 * c)
         ops.conv2d(actv, wgb, gb, kh=3, kw=3, stride=1, pad=1, bias=bgb)

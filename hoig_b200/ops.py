@@ -219,6 +219,16 @@ def seg_resize(seg: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def seg_unfold3(seg: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """seg NCHW f32 -> out (B,Ho,Wo,Kpad): nearest resize + 3x3 im2col, channel t*C + c (zero padded), see hoig_b200.h."""
+    B, C, Hi, Wi = seg.shape
+    _, Ho, Wo, Kpad = out.shape
+    ptr, ld = _nhwc(out, "out")
+    _lib.check(_lib.lib().hoig_seg_unfold3(_f32c(seg, "seg"), B, C, Hi, Wi, ptr, ld, Kpad, Ho, Wo, _dt(out), _stream()),
+               "seg_unfold3")
+    return out
+
+
 def plane_stats(x: torch.Tensor, stats: torch.Tensor) -> torch.Tensor:
     N, H, W, C = x.shape
     ptr, ld = _nhwc(x, "x")

@@ -46,6 +46,16 @@ def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, transposed: bool = Fal
     return out.to(dtype).contiguous()
 
 
+def pack_unfolded3_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """3x3 conv weight (Cout,C,3,3) for a 1x1 GEMM over ``ops.seg_unfold3`` output: column t*C + c, K padded to 64."""
+    w = w.detach().float()
+    cout, c, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    out = torch.zeros(ceil_to(cout, 16), ceil_to(9 * c, 64), dtype=torch.float32, device=w.device)
+    out[:cout, : 9 * c] = w.permute(0, 2, 3, 1).reshape(cout, 9 * c)
+    return out.to(dtype).contiguous()
+
+
 def pack_spade_gamma_beta(wg, bg, wb, bb, dtype):
     """mlp_gamma / mlp_beta (spade.py:22-23) fused into one GEMM with N = 2C:
     rows [0,C) produce gamma, rows [C,2C) beta."""

@@ -223,6 +223,12 @@ int hoig_attn_combine(const void *gt, int64_t ldgt, const void *gs, int64_t ldgs
  * x, dst NHWC (N,h,h,C); grid (N,h,h,2) f32; dst = tgt + sample when tgt != NULL. */
 int hoig_grid_sample(const void *x, int64_t ldx, const float *grid, const void *tgt, int64_t ldt,
                      void *dst, int64_t ldd, int dtype, int N, int h, int C, hoigStream_t stream);
+/* spade.py:30-31 for the tensor-core path: nearest resize of the segmentation map fused with the 3x3 im2col of
+ * mlp_shared's input.  seg NCHW f32 (B,C,Hi,Wi) -> NHWC dtype (B,Ho,Wo,Kpad), channel t*C + c = resized seg channel c at
+ * (y + t/3 - 1, x + t%3 - 1), zero outside the image and for channels >= 9*C.  mlp_shared is then a 1x1 hoig_conv2d over
+ * this tensor with the weight columns in the same (t, c) order. */
+int hoig_seg_unfold3(const float *seg, int B, int C, int Hi, int Wi, void *dst, int64_t ldd, int Kpad, int Ho, int Wo,
+                     int dtype, hoigStream_t stream);
 /* 7x7 convs with few input or output channels (generator.py:99,125,151,223-241) are computed as a 7x1
  * "vertical taps" implicit GEMM plus a horizontal (un)fold, which cuts the operand traffic 7x:
  *  - stems:  hoig_hunfold_nchw builds x7[b,y,x, s*C + c] = x[b,c,y,x+s-k/2] (zero outside, channels padded to Cpad)

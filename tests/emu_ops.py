@@ -95,6 +95,16 @@ def seg_resize(seg, out):
     return nchw_to_nhwc(s, out)
 
 
+def seg_unfold3(seg, out):
+    b, c = seg.shape[:2]
+    _, ho, wo, kpad = out.shape
+    r = F.interpolate(seg, size=(ho, wo), mode="nearest")
+    cols = F.unfold(r, 3, padding=1).reshape(b, c, 9, ho, wo).permute(0, 3, 4, 2, 1).reshape(b, ho, wo, 9 * c)   # (t, c) order
+    out.zero_()
+    out[..., : 9 * c] = cols.to(out.dtype)
+    return out
+
+
 def plane_stats(x, stats):
     xf = x.double()
     stats += torch.stack([xf.sum((1, 2)), (xf * xf).sum((1, 2))], 2).reshape(-1)
@@ -251,7 +261,7 @@ def install(monkeypatch):
     for k in dir(real_ops):
         if k.isupper():
             setattr(emu, k, getattr(real_ops, k))
-    for name in ("conv2d", "nchw_to_nhwc", "nhwc_to_nchw", "seg_resize", "plane_stats", "instnorm_apply", "resize_flow",
+    for name in ("conv2d", "nchw_to_nhwc", "nhwc_to_nchw", "seg_resize", "seg_unfold3", "plane_stats", "instnorm_apply", "resize_flow",
                  "attn_finish", "attn_unfold", "replicate_pad", "conv2d_halo", "attn_combine", "grid_sample", "composite", "hunfold_nchw", "hfold_nchw"):
         setattr(emu, name, globals()[name])
     monkeypatch.setattr(G, "ops", emu)

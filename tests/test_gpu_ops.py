@@ -180,6 +180,17 @@ def test_hunfold_row_kernel_matches_contract(dtype, C, k, cpad):
     assert torch.equal(a.cpu(), b)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("C,hi,ho", [(3, 32, 8), (12, 16, 16), (12, 20, 40), (5, 9, 7), (12, 256, 128), (3, 256, 32), (12, 256, 64)])
+def test_seg_unfold3_matches_contract(dtype, C, hi, ho):
+    g = torch.Generator().manual_seed(13)
+    seg = _rand(g, 2, C, hi, hi)
+    kpad = -(-9 * C // 64) * 64
+    a = ops.seg_unfold3(seg.cuda(), torch.empty(2, ho, ho, kpad, dtype=dtype, device="cuda"))
+    b = emu_ops.seg_unfold3(seg, torch.empty(2, ho, ho, kpad, dtype=dtype))
+    assert torch.equal(a.cpu(), b)
+
+
 # --------------------------------------------------------------------------- convolution
 CONV_CASES = [
     # name, N, H, Cin, Cout, k, stride, mode, extras
