@@ -93,43 +93,41 @@ __global__ void seg_unfold3_kernel(const float *__restrict__ seg, int B, int C, 
 
 // Same result, staged: a CTA takes PX consecutive pixels of one output row, gathers the three resized source rows (plus one
 // halo pixel each side) into shared memory once, and writes every pixel's Kpad channels as consecutive 16-byte chunks.
-template <typename T>
+// A thread keeps ONE 8-channel chunk for all its pixels, so the (tap, channel) decode of its 8 columns happens once.
+template <typename T, int PX>
 __global__ void __launch_bounds__(256) seg_unfold3_row_kernel(const float *__restrict__ seg, int C, int Hi, int Wi, T *__restrict__ dst,
-                                                              int64_t ldd, int Kpad, int Ho, int Wo, int PX)
+                                                              int64_t ldd, int Kpad, int Ho, int Wo)
 {
-    constexpr int MAXPX = 64, MAXC = 16;
-    __shared__ float tile[3][MAXPX + 2][MAXC + 1];
-    __shared__ int8_t t_of[256], c_of[256];   // channel kc -> (tap t, seg channel c), t = -1: zero padding
+    constexpr int MAXC = 16, TW = PX + 2;
+    __shared__ float tile[3 * TW * (MAXC + 1)];     // [r][j][c], c padded to MAXC + 1
     const int segs = Wo / PX;
     const int x0 = (blockIdx.x % segs) * PX, y = (blockIdx.x / segs) % Ho, b = blockIdx.x / (segs * Ho);
-    for (int i = threadIdx.x; i < Kpad; i += blockDim.x) {
-        const int t = i / C;
-        t_of[i] = t < 9 ? (int8_t)t : (int8_t)-1;
-        c_of[i] = (int8_t)(i - t * C);
-    }
     const float sy = (float)Hi / (float)Ho, sx = (float)Wi / (float)Wo;
-    for (int i = threadIdx.x; i < 3 * (PX + 2) * C; i += blockDim.x) {
-        const int j = i % (PX + 2), c = (i / (PX + 2)) % C, r = i / (C * (PX + 2));   // consecutive lanes walk along x
+    for (int i = threadIdx.x; i < 3 * TW * C; i += blockDim.x) {
+        const int j = i % TW, rc = i / TW, c = rc % C, r = rc / C;   // consecutive lanes walk along x
         const int yy = y + r - 1, xx = x0 + j - 1;
         float val = 0.f;
         if (yy >= 0 && yy < Ho && xx >= 0 && xx < Wo) {
             const int iy = min((int)floorf(yy * sy), Hi - 1), ix = min((int)floorf(xx * sx), Wi - 1);
             val = __ldg(seg + (((int64_t)b * C + c) * Hi + iy) * Wi + ix);
         }
-        tile[r][j][c] = val;
+        tile[(r * TW + j) * (MAXC + 1) + c] = val;
+    }
+    const int chunks = Kpad / 8;                     // a power of two <= 32 for the shipped shapes; any divisor of 256 works
+    const int ch = threadIdx.x % chunks, plane = threadIdx.x / chunks, lanes = blockDim.x / chunks;
+    int off[8];                                      // smem offset of column j of this chunk at pixel 0, -1: zero padding
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int kc = ch * 8 + j, t = kc / C, c = kc - t * C;
+        off[j] = t < 9 ? ((t / 3) * TW + t % 3) * (MAXC + 1) + c : -1;
     }
     __syncthreads();
-    const int chunks = Kpad / 8;
-    T *drow = dst + (((int64_t)b * Ho + y) * Wo + x0) * ldd;
-    for (int i = threadIdx.x; i < PX * chunks; i += blockDim.x) {
-        const int px = i / chunks, ch = i - px * chunks;
+    T *drow = dst + (((int64_t)b * Ho + y) * Wo + x0) * ldd + ch * 8;
+    for (int px = plane; px < PX; px += lanes) {
         float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int kc = ch * 8 + j, t = t_of[kc];
-            v[j] = t >= 0 ? tile[t / 3][px + t % 3][c_of[kc]] : 0.f;
-        }
-        store8(drow + (int64_t)px * ldd + ch * 8, v);
+        for (int j = 0; j < 8; ++j) v[j] = off[j] >= 0 ? tile[off[j] + px * (MAXC + 1)] : 0.f;
+        store8(drow + (int64_t)px * ldd, v);
     }
 }
 
@@ -1086,10 +1084,13 @@ extern "C" int hoig_seg_unfold3(const float *seg, int B, int C, int Hi, int Wi, 
     if (n == 0) return HOIG_OK;
     return dispatch(dtype, [&](auto *tag) {
         using T = std::remove_pointer_t<decltype(tag)>;
-        const int px = Wo % 64 == 0 ? 64 : (Wo % 32 == 0 ? 32 : 0);
-        if (px && C <= 16 && Kpad <= 256)
-            seg_unfold3_row_kernel<T><<<(unsigned)((int64_t)B * Ho * (Wo / px)), 256, 0, as_stream(stream)>>>(seg, C, Hi, Wi, (T *)dst, ldd, Kpad,
-                                                                                                          Ho, Wo, px);
+        const bool staged = C <= 16 && Kpad <= 256 && 256 % (Kpad / 8) == 0;
+        if (staged && Wo % 64 == 0)
+            seg_unfold3_row_kernel<T, 64><<<(unsigned)((int64_t)B * Ho * (Wo / 64)), 256, 0, as_stream(stream)>>>(seg, C, Hi, Wi, (T *)dst, ldd,
+                                                                                                             Kpad, Ho, Wo);
+        else if (staged && Wo % 32 == 0)
+            seg_unfold3_row_kernel<T, 32><<<(unsigned)((int64_t)B * Ho * (Wo / 32)), 256, 0, as_stream(stream)>>>(seg, C, Hi, Wi, (T *)dst, ldd,
+                                                                                                             Kpad, Ho, Wo);
         else
             seg_unfold3_kernel<T><<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>(seg, B, C, Hi, Wi, (T *)dst, ldd, Kpad, Ho, Wo);
         return check_launch("seg_unfold3_kernel");
