@@ -37,6 +37,9 @@ class ConvDesc(Structure):
         ("flow", c_void_p),
         ("act_table", c_void_p),
         ("pad_w", c_int),
+        ("spade_x", c_void_p), ("ld_spade_x", c_int64),
+        ("spade_stats", c_void_p),
+        ("spade_eps", ctypes.c_float),
     ]
 
 

@@ -58,6 +58,9 @@ struct ConvParams {
     const float *flow;
     int KH;                 // local attention: kernel size (5)
     int tiles_per_image;
+    const void *spade_x; int64_t ld_spade_x;   // SPADE-modulating epilogue (hoigConvDesc::spade_x), else NULL
+    const double *spade_stats;
+    float spade_eps;
 };
 
 // Bilinear tap set of BlockExtractor for one (pixel, k x k tap): indices into the

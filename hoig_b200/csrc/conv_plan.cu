@@ -48,7 +48,14 @@ int plan_conv(const hoigConvDesc *d, int bm, ConvPlan *plan)
                  "conv2d: bad kernel geometry");
     HOIG_REQUIRE(d->ld0 >= d->C0 && d->ld0 % 8 == 0 && (d->C1 == 0 || (d->ld1 >= d->C1 && d->ld1 % 8 == 0)),
                  "conv2d: source pixel stride must be a multiple of 8 and >= channels");
-    HOIG_REQUIRE(d->ldd >= d->Cout, "conv2d: ldd < Cout");
+    HOIG_REQUIRE(d->ldd >= (d->spade_x ? d->Cout / 2 : d->Cout), "conv2d: ldd < Cout");
+    if (d->spade_x) {
+        HOIG_REQUIRE(d->dtype != HOIG_F32 && d->mode == HOIG_CONV && d->Cout % 16 == 0 && d->Cout <= 2048 && d->spade_stats && !d->stats &&
+                         !d->residual && !d->act_table && d->ld_spade_x >= d->Cout / 2 && d->ld_spade_x % 8 == 0 && d->ldd % 8 == 0 &&
+                         ((uintptr_t)d->spade_x % 16) == 0,
+                     "conv2d(spade epilogue): needs a 16-bit dtype, plain conv mode, Cout = 2*C <= 2048 in 8-channel (gamma, beta) blocks, "
+                     "spade_stats, no stats / residual / act_table, 16-byte aligned x");
+    }
     HOIG_REQUIRE(d->mode != HOIG_CONV_TRANSPOSED || (d->KH == 3 && d->KW == 3 && d->pad == 1),
                  "conv2d(transposed): only the k3 s2 p1 op1 geometry of generator.py:118,201 is supported");
     HOIG_REQUIRE(!d->residual || d->ldr >= d->Cout, "conv2d: ldr < Cout");
@@ -67,6 +74,7 @@ int plan_conv(const hoigConvDesc *d, int bm, ConvPlan *plan)
     base.bias = d->bias; base.act = d->act; base.act_table = d->act_table;
     base.residual = d->residual; base.ldr = d->ldr; base.dst = d->dst; base.ldd = d->ldd;
     base.stats = d->stats; base.flow = d->flow; base.KH = d->KH;
+    base.spade_x = d->spade_x; base.ld_spade_x = d->ld_spade_x; base.spade_stats = d->spade_stats; base.spade_eps = d->spade_eps;
     base.nviews = 1;
     base.view[0] = full_view(d->src0, d->H, d->W, d->ld0);
     if (d->C1) base.view1 = full_view(d->src1, d->H, d->W, d->ld1);

@@ -135,6 +135,7 @@ conv_simt_kernel(const ConvParams p)
 
 int conv2d_simt(const hoigConvDesc *d, cudaStream_t stream)
 {
+    HOIG_REQUIRE(!d || !d->spade_x, "conv2d: the SPADE-modulating epilogue exists on the tensor-core path only");
     ConvPlan plan;
     const int st = plan_conv(d, BM, &plan);
     if (st != HOIG_OK) return st;

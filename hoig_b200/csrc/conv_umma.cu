@@ -389,6 +389,8 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
         uint32_t tcount = 0;
         const uint32_t tempty0 = NCTA == 2 ? mapa(smem_u32(&tempty_bar[0]), 0) : smem_u32(&tempty_bar[0]);   // in the leader CTA
         int cur_img = -1, cur_nt = -1;
+        const bool spade = p.spade_x != nullptr;
+        float *s_mod = &s_stats[0][0][0];   // SPADE epilogue: mean[1024] | rstd[1024] (the statistics buffer is idle in that mode)
         // per-plane sum / sum of squares of the tiles since the last flush: one atomicAdd(double) per column
         auto flush_stats = [&](int img, int ntile) {
             const int pcs = p.phase_cout;
@@ -416,6 +418,18 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                 // new (image, n-tile): hand the finished plane's statistics over and reload the bias slice
                 epi_bar(epi_threads);                   // every warp is done with the previous tiles' s_stats / s_bias
                 if (p.stats && cur_img >= 0) flush_stats(cur_img, cur_nt);
+                if (spade && n_img != cur_img) {        // instance-norm constants of the modulated tensor's planes of this image
+                    const int Cm = p.Cout / 2;
+                    const double inv_hw = 1.0 / (double)npix;
+                    for (int c = epi_tid; c < Cm; c += epi_threads) {
+                        const double2 sq = *reinterpret_cast<const double2 *>(p.spade_stats + ((int64_t)n_img * Cm + c) * 2);
+                        const double mean = sq.x * inv_hw;
+                        double var = sq.y * inv_hw - mean * mean;
+                        if (var < 0) var = 0;
+                        s_mod[c] = (float)mean;
+                        s_mod[1024 + c] = 1.0f / sqrtf((float)var + p.spade_eps);
+                    }
+                }
                 if (nt != cur_nt && p.bias)
                     for (int i = epi_tid; i < BN; i += epi_threads) {
                         const int n = nt * BN + i;
@@ -450,6 +464,21 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                             const float4 bv = *reinterpret_cast<const float4 *>(&s_bias[c0 + j]);
                             v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
                         }
+                    }
+                    if (spade) {
+                        // columns [g0..g7 b0..b7] of channels 8*(n0/16) .. +7: modulate the normalised activation, write 8 channels
+                        const int cb = (n0 >> 4) * 8;
+                        if (valid) {
+                            float xv[8];
+                            load8(static_cast<const T *>(p.spade_x) + m * p.ld_spade_x + cb, xv);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float xn = (xv[j] - s_mod[cb + j]) * s_mod[1024 + cb + j];
+                                xv[j] = fmaxf(fmaf(xn, 1.f + v[j], v[8 + j]), 0.f);
+                            }
+                            store8(dst + m * p.ldd + cb, xv);
+                        }
+                        return;
                     }
                     const bool full = n0 + 16 <= p.Cout;
                     if (res && valid) {

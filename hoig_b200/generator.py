@@ -229,7 +229,8 @@ class GeneratorB200(nn.Module):
 
     def _gb(self, prefix: str):
         ps = [self._p(prefix + n) for n in ("mlp_gamma.weight", "mlp_gamma.bias", "mlp_beta.weight", "mlp_beta.bias")]
-        return self._cached(prefix + "#gb", ps, lambda: pack_spade_gamma_beta(*ps, self.compute_dtype))
+        return self._cached(prefix + "#gb", ps,
+                            lambda: pack_spade_gamma_beta(*ps, self.compute_dtype, interleave=self.compute_dtype != torch.float32))
 
     # ---------------------------------------------------------------- building blocks
     def _new(self, n, h, w, c):
@@ -291,9 +292,13 @@ class GeneratorB200(nn.Module):
             s = self._seg(seg_nchw, h, seg_cache)
             actv, _ = self._conv(s, prefix + "mlp_shared.0.weight", NHIDDEN, 3, bias=prefix + "mlp_shared.0.bias", act=ops.ACT_RELU)
         wgb, bgb = self._gb(prefix)
+        dst = x if out is None else out
+        if self.compute_dtype != torch.float32:
+            # normalise + modulate + ReLU in the epilogue of the (gamma, beta) GEMM: the 2C-wide tensor never reaches memory
+            ops.conv2d(actv, wgb, dst, kh=3, kw=3, stride=1, pad=1, bias=bgb, act=ops.ACT_RELU, cout=2 * c, spade_x=x, spade_stats=stats)
+            return dst
         gb = self._new(n, h, w, 2 * c)
         ops.conv2d(actv, wgb, gb, kh=3, kw=3, stride=1, pad=1, bias=bgb)
-        dst = x if out is None else out
         ops.instnorm_apply(x, stats, dst, gb=gb, relu=True)
         return dst
 

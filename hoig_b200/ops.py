@@ -143,8 +143,10 @@ def conv2d(x0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, *, kh: int
            pad: int = 0, pad_w: Optional[int] = None, mode: int = CONV, x1: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
            act: int = ACT_NONE, residual: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
            flow: Optional[torch.Tensor] = None, cout: Optional[int] = None, simt: bool = False,
-           act_table: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Implicit-GEMM convolution; see ``hoigConvDesc``.  ``weight`` is the packed matrix
+           act_table: Optional[torch.Tensor] = None, spade_x: Optional[torch.Tensor] = None,
+           spade_stats: Optional[torch.Tensor] = None, eps: float = 1e-5) -> torch.Tensor:
+    """Implicit-GEMM convolution; see ``hoigConvDesc``.  With ``spade_x`` the GEMM produces interleaved (gamma, beta) and the
+    epilogue writes relu(norm(spade_x) * (1 + gamma) + beta) into ``out`` (cout // 2 channels; pass ``cout``).  ``weight`` is the packed matrix
     from :func:`hoig_b200.packing.pack_conv_weight`; ``out`` is an NHWC view."""
     d = ConvDesc()
     d.dtype, d.mode = _dt(x0), mode
@@ -175,6 +177,15 @@ def conv2d(x0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, *, kh: int
     else:
         d.residual, d.ldr = None, 0
     d.dst, d.ldd = _nhwc(out, "out")
+    if spade_x is not None:
+        if spade_stats is None or spade_stats.dtype != torch.float64 or spade_stats.numel() != N * (d.Cout // 2) * 2:
+            raise ValueError("conv2d: spade_stats must be float64 [N, Cout/2, 2]")
+        if spade_x.shape != (N, OH, OW, d.Cout // 2) or spade_x.dtype != x0.dtype or Co < d.Cout // 2:
+            raise ValueError("conv2d: spade_x / out must be (N,OH,OW,Cout/2) of the input dtype")
+        d.spade_x, d.ld_spade_x = _nhwc(spade_x, "spade_x")
+        d.spade_stats, d.spade_eps = spade_stats.data_ptr(), eps
+    else:
+        d.spade_x, d.ld_spade_x, d.spade_stats, d.spade_eps = None, 0, None, 0.0
     d.stats = stats.data_ptr() if stats is not None else None
     if stats is not None and (stats.dtype != torch.float64 or stats.numel() != N * d.Cout * 2):
         raise ValueError("conv2d: stats must be float64 [N, Cout, 2]")

@@ -56,9 +56,18 @@ def pack_unfolded3_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return out.to(dtype).contiguous()
 
 
-def pack_spade_gamma_beta(wg, bg, wb, bb, dtype):
-    """mlp_gamma / mlp_beta (spade.py:22-23) fused into one GEMM with N = 2C:
-    rows [0,C) produce gamma, rows [C,2C) beta."""
+def pack_spade_gamma_beta(wg, bg, wb, bb, dtype, interleave: bool = False):
+    """mlp_gamma / mlp_beta (spade.py:22-23) fused into one GEMM with N = 2C.
+
+    ``interleave=False``: rows [0,C) produce gamma, rows [C,2C) beta (separate ``instnorm_apply``).
+    ``interleave=True``: blocks of 8 channels [g0..g7 b0..b7], the layout of the SPADE-modulating conv epilogue
+    (``hoigConvDesc::spade_x``), where one thread holds gamma and beta of the same channels."""
     w = torch.cat([wg, wb], 0)
-    b = torch.cat([bg, bb], 0).detach().float().contiguous()
-    return pack_conv_weight(w, dtype), b
+    b = torch.cat([bg, bb], 0).detach().float()
+    if interleave:
+        c = wg.shape[0]
+        assert c % 8 == 0
+        idx = torch.arange(c, device=w.device).view(c // 8, 1, 8)
+        perm = torch.cat([idx, idx + c], 1).reshape(-1)          # row order g-block, b-block, g-block, ...
+        w, b = w[perm], b[perm]
+    return pack_conv_weight(w, dtype), b.contiguous()

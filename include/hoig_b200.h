@@ -122,6 +122,15 @@ typedef struct {
     const float *flow;  /* HOIG_CONV_LOCAL_ATTN only: (N,H,W,2) pixel-unit offsets (x,y) */
     const int *act_table; /* NULL or [Cout] device array of hoigAct codes overriding `act` per output channel */
     int pad_w;          /* horizontal padding (set equal to pad for square kernels) */
+    /* SPADE-modulating epilogue (spade.py:33-38 fused into the gamma/beta GEMM; 16-bit dtypes only).  When spade_x is
+     * non-NULL the GEMM's Cout = 2*C columns are (gamma, beta) in blocks of 8 channels [g0..g7 b0..b7] (weights and bias
+     * packed that way) and the kernel writes C channels:
+     *   dst[pixel][c] = relu( (x[pixel][c] - mean_c) * rstd_c * (1 + gamma_c) + beta_c ),
+     * x = spade_x (N,OH,OW,C) with pixel stride ld_spade_x, mean/rstd per (image, channel) from spade_stats ([N][C][2] sum /
+     * sum of squares) and spade_eps.  The gamma/beta tensor never reaches memory.  stats, residual, act_table must be NULL. */
+    const void *spade_x; int64_t ld_spade_x;
+    const double *spade_stats;
+    float spade_eps;
 } hoigConvDesc;
 
 /* Rows / columns of the packed weight matrix for a given problem.  Conv / local attention: rows = Cout padded

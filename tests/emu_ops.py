@@ -41,7 +41,7 @@ def unpack_transposed(wp, cout, kh, kw, cin_p, pad):
 
 
 def conv2d(x0, weight, out, *, kh, kw, stride=1, pad=0, pad_w=None, mode=0, x1=None, bias=None, act=0, residual=None, stats=None,
-           flow=None, cout=None, simt=False, act_table=None):
+           flow=None, cout=None, simt=False, act_table=None, spade_x=None, spade_stats=None, eps=1e-5):
     x = x0 if x1 is None else torch.cat([x0, x1], 3)
     cin_p = x.shape[3]
     cout = out.shape[3] if cout is None else cout
@@ -65,6 +65,20 @@ def conv2d(x0, weight, out, *, kh, kw, stride=1, pad=0, pad_w=None, mode=0, x1=N
     if bias is not None:
         y = y + bias.view(1, -1, 1, 1)
     y = y.permute(0, 2, 3, 1)
+    if spade_x is not None:
+        # hoigConvDesc::spade_x: columns are (gamma, beta) in blocks of 8 channels; write relu(norm(x) * (1 + gamma) + beta)
+        n, h, w_, c2 = y.shape
+        c = c2 // 2
+        gb = y.reshape(n, h, w_, c // 8, 2, 8)
+        gamma, beta = gb[..., 0, :].reshape(n, h, w_, c), gb[..., 1, :].reshape(n, h, w_, c)
+        st = spade_stats.view(n, c, 2)
+        mean = st[..., 0] / (h * w_)
+        var = (st[..., 1] / (h * w_) - mean * mean).clamp_min(0)
+        rstd = 1.0 / torch.sqrt(var.float() + eps)
+        xn_ = (spade_x.float() - mean.float().view(n, 1, 1, c)) * rstd.view(n, 1, 1, c)
+        res_ = torch.relu(xn_ * (1 + gamma) + beta)
+        out[..., :c] = _q(res_, out)
+        return out
     if residual is not None:
         y = y + residual[..., :cout].float()
     if act_table is not None:

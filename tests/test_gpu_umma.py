@@ -147,3 +147,36 @@ def test_dual_issue_pipelines_equal_single(case, pair):
     assert torch.equal(outs[0][0], outs[1][0])
     if outs[0][1] is not None:
         assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(2, 32, 128, 512), (1, 128, 128, 128), (3, 16, 128, 64)], ids=["c512_32", "c128_128", "c64_16_gather_tiles"])
+def test_spade_modulating_epilogue(shape, dtype):
+    """(gamma, beta) GEMM with the SPADE apply fused into its epilogue == separate GEMM + instnorm_apply (spade.py:33-38)."""
+    from hoig_b200.packing import pack_spade_gamma_beta
+    n, h, cin, c = shape
+    g = torch.Generator().manual_seed(17)
+    actv = _rand(g, n, h, h, cin).to(dtype)
+    x = (_rand(g, n, h, h, c) * 2.0 + 0.5).to(dtype)
+    wg, wb = _rand(g, c, cin, 3, 3, scale=0.03), _rand(g, c, cin, 3, 3, scale=0.03)
+    bg, bb = _rand(g, c, scale=0.1), _rand(g, c, scale=0.1)
+    xf = x.double()
+    stats = torch.stack([xf.sum((1, 2)), (xf * xf).sum((1, 2))], 2).reshape(-1).contiguous()
+    # fused
+    wi, bi = pack_spade_gamma_beta(wg, bg, wb, bb, dtype, interleave=True)
+    fused = torch.empty(n, h, h, c, dtype=dtype, device="cuda")
+    ops.conv2d(actv.cuda(), wi.cuda(), fused, kh=3, kw=3, stride=1, pad=1, bias=bi.cuda(), act=ops.ACT_RELU, cout=2 * c,
+               spade_x=x.cuda(), spade_stats=stats.cuda())
+    # contract (CPU emulation of the same descriptor) and the two-kernel formulation on the GPU
+    ref = emu_ops.conv2d(actv, wi, torch.empty(n, h, h, c, dtype=dtype), kh=3, kw=3, stride=1, pad=1, bias=bi, act=ops.ACT_RELU,
+                         cout=2 * c, spade_x=x, spade_stats=stats)
+    ws, bs = pack_spade_gamma_beta(wg, bg, wb, bb, dtype)
+    gb = torch.empty(n, h, h, 2 * c, dtype=dtype, device="cuda")
+    ops.conv2d(actv.cuda(), ws.cuda(), gb, kh=3, kw=3, stride=1, pad=1, bias=bs.cuda())
+    two = ops.instnorm_apply(x.cuda(), stats.cuda(), torch.empty(n, h, h, c, dtype=dtype, device="cuda"), gb=gb, relu=True)
+    torch.cuda.synchronize()
+    tol = 4e-2 if dtype == torch.bfloat16 else 5e-3
+    d1 = (fused.cpu().float() - ref.float()).abs().max().item()
+    d2 = (fused.cpu().float() - two.cpu().float()).abs().max().item()
+    print(f"spade epilogue {shape} {dtype}: vs contract {d1:.3e}, vs two-kernel {d2:.3e}")
+    assert d1 <= tol and d2 <= tol
