@@ -58,6 +58,9 @@ struct UmmaParams {
     int prefetch_tiles;  // TMA-A: L2-prefetch the activation boxes this many tile rounds ahead (0 = off)
     int tpi_shift;       // log2(tiles_per_image) when it is a power of two, else -1
     int contig;          // 1: contiguous tile range per CTA, 0: tiles strided by the grid size
+    int bres;            // 1: the whole packed weight matrix (k_blocks tiles of BN x 64) stays RESIDENT in shared memory, loaded
+                         //    once per CTA; the ring then carries activations only.  For the narrow high-resolution convs the
+                         //    L2->SM path (~42 B/clk/SM), not the tensor pipe, is the bound, and weights are 1/3 of that traffic.
     int dual;            // 1: two independent pipelines per CTA (narrow N): tiles alternate between two MMA-issuing warps,
                          //    each with its own half of the smem ring and two of the four TMEM accumulator stages
     int debug;           // timing knock-outs (HOIG_UMMA_DEBUG, results are garbage): 1 = epilogue only drains TMEM, 2 = A tile loaded once per tile
@@ -77,6 +80,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
 {
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[4], tempty_bar[4];
+    __shared__ __align__(8) uint64_t bres_bar;
     __shared__ uint32_t tmem_base_smem;
     __shared__ float s_stats[4][2][256];   // per TMEM lane quadrant: plain += by its owning warps, no shared atomics
     __shared__ __align__(16) float s_bias[256 + 32];
@@ -84,7 +88,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
     const ConvParams &p = P.c;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int BN = P.BN;
-    const int stage_bytes = A_STAGE_BYTES + (BN / NCTA) * BK * 2;
+    const int stage_bytes = P.bres ? A_STAGE_BYTES : A_STAGE_BYTES + (BN / NCTA) * BK * 2;
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     const uint32_t stg_base = smem_u32(smem);                  // epilogue staging first (1024-aligned)
     const uint32_t smem_base = stg_base + STG_BYTES;           // then the operand ring
@@ -100,7 +104,9 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
     const int tile_step = P.contig ? 1 : tile_units;
 
     if (threadIdx.x == 0) {
-        const uint32_t full_count = P.tma_a ? 2u : (uint32_t)(PROD_WARPS * 32 + 1);   // TMA-A: one arrive.expect_tx per producer thread
+        // TMA-A: one arrive.expect_tx per producer thread (only the activation thread when the weights are resident)
+        const uint32_t full_count = P.tma_a ? (P.bres ? 1u : 2u) : (uint32_t)(PROD_WARPS * 32 + 1);
+        mbar_init(smem_u32(&bres_bar), 1);
         for (int s = 0; s < P.stages; ++s) {
             mbar_init(smem_u32(&full_bar[s]), full_count);
             mbar_init(smem_u32(&empty_bar[s]), 1);
@@ -259,7 +265,16 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
         // Gather mode: TMA_WARP streams the weight tiles, WB_WARP has nothing to do.
         const bool do_a = P.tma_a && warp == TMA_WARP;
         const bool do_b = P.tma_a ? warp == WB_WARP : warp == TMA_WARP;
-        if (do_a || do_b) {   // whole warp runs the loop; one elected lane issues
+        const uint32_t bres_base = smem_base + (uint32_t)P.stages * (uint32_t)stage_bytes;   // resident weights follow the ring
+        if (do_b && P.bres) {
+            // resident weights: all k-block tiles once, one barrier
+            if (elect_one()) {
+                mbar_arrive_expect_tx(smem_u32(&bres_bar), (uint32_t)P.k_blocks * (uint32_t)(BN * BK * 2));
+                for (int kb = 0; kb < P.k_blocks; ++kb)
+                    tma_load_2d(bres_base + (uint32_t)kb * (uint32_t)(BN * BK * 2), &map_w, smem_u32(&bres_bar), kb * BK, 0);
+            }
+            __syncwarp();
+        } else if (do_a || do_b) {   // whole warp runs the loop; one elected lane issues
             const CUtensorMap *maps[4] = {&map_a0, &map_a1, &map_a2, &map_a3};
             // NP pipelines (1, or 2 in dual mode): pipeline w owns ring stages w, w+NP, ... and the CTA's tiles w, w+NP, ...
             const int NP = P.dual ? 2 : 1;
@@ -339,6 +354,8 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
             const uint64_t desc0 = umma_desc(smem_base);             // + (byte offset >> 4) addresses any tile of the ring
             const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
             // i = index of the tile in this CTA's sequence; TMEM accumulator stage i % (2*NP), used for the (i / (2*NP))-th time
+            const uint64_t bres_desc = desc0 + (uint64_t)(((uint32_t)P.stages * (uint32_t)stage_bytes) >> 4);
+            if (P.bres) { mbar_wait(smem_u32(&bres_bar), 0); tc_fence_after(); }
             for (uint32_t i = (uint32_t)w; tile0 + (int)i * tile_step < total_tiles; i += (uint32_t)NP) {
                 const uint32_t acc = i % (uint32_t)(2 * NP), use = i / (uint32_t)(2 * NP);
                 mbar_wait(smem_u32(&tempty_bar[acc]), (use & 1) ^ 1);
@@ -349,7 +366,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                     mbar_wait(full0 + 8u * st, ph);
                     tc_fence_after();
                     const uint64_t da = desc0 + (uint64_t)(st * stage16);
-                    const uint64_t db = da + (uint64_t)(A_STAGE_BYTES >> 4);
+                    const uint64_t db = P.bres ? bres_desc + (uint64_t)((uint32_t)kb * (uint32_t)(BN * 8)) : da + (uint64_t)(A_STAGE_BYTES >> 4);
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
@@ -575,6 +592,7 @@ int g_umma_debug = 0;
 int g_prefetch_tiles = 0;   // kept for HOIG_UMMA_PREFETCH_TILES compatibility; L2 prefetch of future tiles was measured to hurt and is gone   // measured: L2 prefetch of future tiles HURTS (the streaming convs are L2->SM bandwidth bound, not latency bound)
 
 int g_contig_mode = 1;      // HOIG_UMMA_CONTIG
+int g_bres_mode = 1;        // HOIG_UMMA_BRES: resident weights for small weight matrices
 int g_dual_mode = 1;        // 1: narrow-N TMA convs run two MMA issue pipelines per CTA (HOIG_UMMA_DUAL=0 disables)
 int g_pair_mode = 1;        // 0: one CTA per tile; 1: CTA pairs (cta_group::2) where they pay off; 2: pairs wherever legal (tests)
 
@@ -630,9 +648,13 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     // Short reductions stay on single CTAs: a pair pays cluster-scope barrier latency per tile, measured to cost more than
     // the halved weight traffic saves below ~12 k-blocks (7x1 stems, 64->128 stride-2, 128->64 transposed).
     const bool pair_ok = P.tma_a && P.m_tiles % 2 == 0 && P.BN % 32 == 0 && p.Npad % P.BN == 0;
-    const int ncta = (pair_ok && (g_pair_mode == 2 || (g_pair_mode == 1 && P.k_blocks >= 12))) ? 2 : 1;
-    const int stage_bytes = A_STAGE_BYTES + (P.BN / ncta) * BK * 2;
-    P.stages = RING_BUDGET / stage_bytes;
+    int ncta = (pair_ok && (g_pair_mode == 2 || (g_pair_mode == 1 && P.k_blocks >= 12))) ? 2 : 1;
+    // Resident weights (single-CTA tiles, one n-tile): worth it when the whole matrix fits beside >= 4 activation stages
+    const size_t w_bytes = (size_t)P.k_blocks * P.BN * BK * 2;
+    // (not when the conv would run on CTA pairs: measured slower for 128->64 @256^2, whose 147 KB of weights leave 4 stages)
+    P.bres = (g_bres_mode && P.tma_a && P.n_tiles == 1 && ncta == 1 && w_bytes + 4 * (size_t)A_STAGE_BYTES <= (size_t)RING_BUDGET) ? 1 : 0;
+    const int stage_bytes = P.bres ? A_STAGE_BYTES : A_STAGE_BYTES + (P.BN / ncta) * BK * 2;
+    P.stages = (int)((RING_BUDGET - (P.bres ? w_bytes : 0)) / stage_bytes);
     if (P.stages > MAX_STAGES) P.stages = MAX_STAGES;
     // Narrow tiles (N <= 128): one thread cannot issue 128 x N x 16 MMAs as fast as the tensor pipe retires them
     // (scripts/probes/mma_probe.cu: ~65-100 cycles of issue overhead vs 48-64 cycles of execution), so two warps
@@ -679,7 +701,7 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     const int total = (P.m_tiles / ncta) * P.n_tiles;
     const int units = num_sms / ncta;                       // CTAs or CTA pairs that fit the GPU
     const int grid = (total < units ? total : units) * ncta;
-    const size_t smem = (size_t)STG_BYTES + (size_t)P.stages * stage_bytes + 1024;
+    const size_t smem = (size_t)STG_BYTES + (size_t)P.stages * stage_bytes + (P.bres ? w_bytes : 0) + 1024;
     if (dtype == HOIG_F16)
         return ncta == 2 ? launch_kernel<__half, 2>(P, map_w, map_a, grid, smem, stream) : launch_kernel<__half, 1>(P, map_w, map_a, grid, smem, stream);
     return ncta == 2 ? launch_kernel<__nv_bfloat16, 2>(P, map_w, map_a, grid, smem, stream)
@@ -700,6 +722,8 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
         g_force_gather = (e && e[0] == '1') ? 1 : 0;
         const char *pf = getenv("HOIG_UMMA_PREFETCH_TILES");
         if (pf) g_prefetch_tiles = atoi(pf);
+        const char *bm = getenv("HOIG_UMMA_BRES");
+        if (bm) g_bres_mode = atoi(bm);
         const char *cm = getenv("HOIG_UMMA_CONTIG");
         if (cm) g_contig_mode = atoi(cm);
         const char *dm = getenv("HOIG_UMMA_DUAL");
@@ -723,5 +747,7 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
 extern "C" void hoig_set_umma_gather_only(int on) { hoig::g_force_gather = on ? 1 : 0; }
 // Diagnostic switch: 0 = one CTA per tile, 1 = CTA pairs (cta_group::2) where they pay off (default), 2 = wherever legal.
 extern "C" void hoig_set_umma_pair_mode(int on) { hoig::g_pair_mode = on; }
+// Diagnostic switch: 1 = small weight matrices stay resident in shared memory (default), 0 = always streamed.
+extern "C" void hoig_set_umma_bres_mode(int on) { hoig::g_bres_mode = on ? 1 : 0; }
 // Diagnostic switch: 1 = two MMA issue pipelines per CTA for narrow-N tiles (default), 0 = one.
 extern "C" void hoig_set_umma_dual_mode(int on) { hoig::g_dual_mode = on ? 1 : 0; }

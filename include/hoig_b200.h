@@ -152,6 +152,8 @@ void hoig_set_umma_gather_only(int on);
 void hoig_set_umma_pair_mode(int on);
 /* Test hook: 1 (default) = narrow-N tensor-core convs run two MMA issue pipelines per CTA, 0 = one. */
 void hoig_set_umma_dual_mode(int on);
+/* Test hook: 1 (default) = weight matrices that fit stay resident in shared memory, 0 = always streamed through the ring. */
+void hoig_set_umma_bres_mode(int on);
 /* Tuning hook: pixels per rasterizer band (256..16384; the band's 64-bit key buffer lives in shared memory). */
 void hoig_set_rasterizer_band_pixels(int n);
 

@@ -180,3 +180,23 @@ def test_spade_modulating_epilogue(shape, dtype):
     d2 = (fused.cpu().float() - two.cpu().float()).abs().max().item()
     print(f"spade epilogue {shape} {dtype}: vs contract {d1:.3e}, vs two-kernel {d2:.3e}")
     assert d1 <= tol and d2 <= tol
+
+
+@pytest.mark.parametrize("dual", [0, 1], ids=["one_pipeline", "dual_pipelines"])
+@pytest.mark.parametrize("case", DUAL_CASES, ids=[c[0] for c in DUAL_CASES])
+def test_resident_weights_equal_streamed(case, dual):
+    """Weights resident in shared memory vs streamed through the ring: same MMAs in the same order, bit-identical."""
+    import hoig_b200._lib as L
+    outs = []
+    L.lib().hoig_set_umma_dual_mode(dual)
+    try:
+        for mode in (0, 1):
+            L.lib().hoig_set_umma_bres_mode(mode)
+            out, ref, st, st_ref = _run_conv(case, torch.bfloat16)
+            outs.append((out.cpu(), None if st is None else st.cpu()))
+    finally:
+        L.lib().hoig_set_umma_bres_mode(1)
+        L.lib().hoig_set_umma_dual_mode(1)
+    assert torch.equal(outs[0][0], outs[1][0])
+    if outs[0][1] is not None:
+        assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-3)
