@@ -89,6 +89,7 @@ _SIGNATURES = {
     "hoig_set_umma_pair_mode": (None, [c_int]),
     "hoig_set_umma_dual_mode": (None, [c_int]),
     "hoig_set_umma_bres_mode": (None, [c_int]),
+    "hoig_set_umma_halo_mode": (None, [c_int]),
     "hoig_attn_combine": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "hoig_grid_sample": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int,

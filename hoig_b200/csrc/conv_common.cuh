@@ -58,6 +58,7 @@ struct ConvParams {
     const float *flow;
     int KH;                 // local attention: kernel size (5)
     int tiles_per_image;
+    int kh, kw, pad_h, pad_w;   // regular stride-1 tap grid (tap (r,s) = offset (r - pad_h, s - pad_w) of view 0), else kw = 0
     const void *spade_x; int64_t ld_spade_x;   // SPADE-modulating epilogue (hoigConvDesc::spade_x), else NULL
     const double *spade_stats;
     float spade_eps;

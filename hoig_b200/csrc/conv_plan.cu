@@ -101,6 +101,7 @@ int plan_conv(const hoigConvDesc *d, int bm, ConvPlan *plan)
             p.nviews = 4;
         } else {
             p.stride = d->stride;
+            if (d->stride == 1) { p.kh = d->KH; p.kw = d->KW; p.pad_h = d->pad; p.pad_w = d->pad_w; }
         }
         for (int r = 0; r < d->KH; ++r)
             for (int s = 0; s < d->KW; ++s) {

@@ -36,6 +36,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int A_HALO_BYTES = 17 * 1024;   // (128 + up to 7 halo pixels) x 128 B, rounded up to the 1024 B swizzle period
 constexpr int EPI_WARPS = 8, PROD_WARPS = 4;    // epilogue warp w: TMEM lane quadrant w % 4, 16-column chunks of parity w / 4
 constexpr int EPI_END = 16;                     // warps 12-15: a further epilogue group
 constexpr int TMA_WARP = 16, MMA_WARP = 17, WB_WARP = 18, MMA2_WARP = 19;   // MMA2: second issue stream (dual mode)   // WB: weight-tile TMA producer in TMA-A mode
@@ -58,6 +59,10 @@ struct UmmaParams {
     int prefetch_tiles;  // TMA-A: L2-prefetch the activation boxes this many tile rounds ahead (0 = off)
     int tpi_shift;       // log2(tiles_per_image) when it is a power of two, else -1
     int contig;          // 1: contiguous tile range per CTA, 0: tiles strided by the grid size
+    int halo;            // 1: regular kh x kw stride-1 conv whose tiles are 128 consecutive pixels of ONE image row: a stage holds one
+                         //    activation box of 128 + kw - 1 pixels per (kernel row, 64 channels) and the kw taps read it through
+                         //    descriptors shifted by one pixel row (128 B) each -- L2->SM activation traffic / kw (see conv_halo.cu)
+    int k_steps;         // halo: kh * Cin / 64 pipeline steps of kw taps each
     int bres;            // 1: the whole packed weight matrix (k_blocks tiles of BN x 64) stays RESIDENT in shared memory, loaded
                          //    once per CTA; the ring then carries activations only.  For the narrow high-resolution convs the
                          //    L2->SM path (~42 B/clk/SM), not the tensor pipe, is the bound, and weights are 1/3 of that traffic.
@@ -88,7 +93,11 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
     const ConvParams &p = P.c;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int BN = P.BN;
-    const int stage_bytes = P.bres ? A_STAGE_BYTES : A_STAGE_BYTES + (BN / NCTA) * BK * 2;
+    const int TPS = P.halo ? p.kw : 1;                                  // taps per pipeline step
+    const int a_bytes = P.halo ? A_HALO_BYTES : A_STAGE_BYTES;          // activation region of a stage
+    const int b_tile = (BN / NCTA) * BK * 2;                            // one tap's weight tile (this CTA's share)
+    const int stage_bytes = P.bres ? a_bytes : a_bytes + TPS * b_tile;
+    const int n_steps = P.halo ? P.k_steps : P.k_blocks;
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     const uint32_t stg_base = smem_u32(smem);                  // epilogue staging first (1024-aligned)
     const uint32_t smem_base = stg_base + STG_BYTES;           // then the operand ring
@@ -300,43 +309,89 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                     gy0[w] = pix0 / p.GW; gx0[w] = pix0 % p.GW;
                 }
                 int tap = 0, c = 0;
-                for (int kb = 0; kb < P.k_blocks; ++kb) {
-                    const int tt = tap < p.ntaps ? tap : p.ntaps - 1;   // K padding blocks: any finite data (weights are zero)
-                    for (int w = 0; w < NP; ++w) {
-                        if (!live[w]) continue;
-                        // ring position / phase kept incrementally: a runtime division per k-block on this single
-                        // thread costs more than the MMAs of a short k-block
-                        const uint32_t st = q[w] * (uint32_t)NP + (uint32_t)w;
-                        mbar_wait(empty0 + 8u * st, ph[w] ^ 1u);
-                        const uint32_t bar = full0 + 8u * st;
-                        const uint32_t a_dst = smem_base + st * (uint32_t)stage_bytes;
-                        if (do_a) {
-                            const bool skip_a = NCTA == 1 && (P.debug & 2) && kb > 0;
-                            if (elect_one()) {
-                                if (skip_a) {
-                                    mbar_arrive(bar);
-                                } else if (NCTA == 2) {
-                                    if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[0]) + 8u * st, 2u * (uint32_t)A_STAGE_BYTES);
-                                    tma_load_4d_2sm(a_dst, maps[p.tap_map[tt]], bar, c, gx0[w] + p.tap_dx[tt], gy0[w] + p.tap_dy[tt], n_img[w]);
+                if (!P.halo) {
+                    for (int kb = 0; kb < P.k_blocks; ++kb) {
+                        const int tt = tap < p.ntaps ? tap : p.ntaps - 1;   // K padding blocks: any finite data (weights are zero)
+                        for (int w = 0; w < NP; ++w) {
+                            if (!live[w]) continue;
+                            // ring position / phase kept incrementally: a runtime division per k-block on this single
+                            // thread costs more than the MMAs of a short k-block
+                            const uint32_t st = q[w] * (uint32_t)NP + (uint32_t)w;
+                            mbar_wait(empty0 + 8u * st, ph[w] ^ 1u);
+                            const uint32_t bar = full0 + 8u * st;
+                            const uint32_t a_dst = smem_base + st * (uint32_t)stage_bytes;
+                            if (do_a) {
+                                const bool skip_a = NCTA == 1 && (P.debug & 2) && kb > 0;
+                                if (elect_one()) {
+                                    if (skip_a) {
+                                        mbar_arrive(bar);
+                                    } else if (NCTA == 2) {
+                                        if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[0]) + 8u * st, 2u * (uint32_t)A_STAGE_BYTES);
+                                        tma_load_4d_2sm(a_dst, maps[p.tap_map[tt]], bar, c, gx0[w] + p.tap_dx[tt], gy0[w] + p.tap_dy[tt], n_img[w]);
+                                    } else {
+                                        mbar_arrive_expect_tx(bar, (uint32_t)A_STAGE_BYTES);
+                                        tma_load_4d(a_dst, maps[p.tap_map[tt]], bar, c, gx0[w] + p.tap_dx[tt], gy0[w] + p.tap_dy[tt], n_img[w]);
+                                    }
+                                }
+                            } else if (elect_one()) {
+                                if (NCTA == 2) {
+                                    if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[0]) + 8u * st, b_bytes);
+                                    tma_load_2d_2sm(a_dst + A_STAGE_BYTES, &map_w, bar, kb * BK, nt[w] * BN + (int)(rank * b_rows));
                                 } else {
-                                    mbar_arrive_expect_tx(bar, (uint32_t)A_STAGE_BYTES);
-                                    tma_load_4d(a_dst, maps[p.tap_map[tt]], bar, c, gx0[w] + p.tap_dx[tt], gy0[w] + p.tap_dy[tt], n_img[w]);
+                                    mbar_arrive_expect_tx(bar, b_bytes);
+                                    tma_load_2d(a_dst + A_STAGE_BYTES, &map_w, bar, kb * BK, nt[w] * BN);
                                 }
                             }
-                        } else if (elect_one()) {
-                            if (NCTA == 2) {
-                                if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[0]) + 8u * st, b_bytes);
-                                tma_load_2d_2sm(a_dst + A_STAGE_BYTES, &map_w, bar, kb * BK, nt[w] * BN + (int)(rank * b_rows));
-                            } else {
-                                mbar_arrive_expect_tx(bar, b_bytes);
-                                tma_load_2d(a_dst + A_STAGE_BYTES, &map_w, bar, kb * BK, nt[w] * BN);
-                            }
+                            __syncwarp();
+                            if (++q[w] == sp) { q[w] = 0; ph[w] ^= 1u; }
                         }
-                        __syncwarp();
-                        if (++q[w] == sp) { q[w] = 0; ph[w] ^= 1u; }
+                        c += BK;
+                        if (c >= p.Cin) { c = 0; ++tap; }
                     }
-                    c += BK;
-                    if (c >= p.Cin) { c = 0; ++tap; }
+                } else {
+                    // row-halo mode: step = (kernel row `tap`, channel block c): ONE activation box of 128 + kw - 1 pixels starting
+                    // pad_w pixels left of the tile, and the kw weight tiles of that kernel row
+                    const uint32_t a_tx = (uint32_t)(BM + TPS - 1) * 128u;
+                    for (int kb = 0; kb < P.k_steps; ++kb) {
+                        for (int w = 0; w < NP; ++w) {
+                            if (!live[w]) continue;
+                            const uint32_t st = q[w] * (uint32_t)NP + (uint32_t)w;
+                            mbar_wait(empty0 + 8u * st, ph[w] ^ 1u);
+                            const uint32_t bar = full0 + 8u * st;
+                            const uint32_t a_dst = smem_base + st * (uint32_t)stage_bytes;
+                            if (do_a) {
+                                if (elect_one()) {
+                                    if (NCTA == 2) {
+                                        if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[0]) + 8u * st, 2u * a_tx);
+                                        tma_load_4d_2sm(a_dst, &map_a0, bar, c, gx0[w] - p.pad_w, gy0[w] + tap - p.pad_h, n_img[w]);
+                                    } else {
+                                        mbar_arrive_expect_tx(bar, a_tx);
+                                        tma_load_4d(a_dst, &map_a0, bar, c, gx0[w] - p.pad_w, gy0[w] + tap - p.pad_h, n_img[w]);
+                                    }
+                                }
+                            } else {
+                                if (elect_one()) {
+                                    if (NCTA == 2) {
+                                        if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[0]) + 8u * st, (uint32_t)TPS * b_bytes);
+                                    } else {
+                                        mbar_arrive_expect_tx(bar, (uint32_t)TPS * b_bytes);
+                                    }
+                                }
+                                for (int sft = 0; sft < TPS; ++sft) {      // warp-uniform loop, one elected lane issues each load
+                                    const int kcol = (tap * TPS + sft) * p.Cin + c;
+                                    const uint32_t b_dst = a_dst + (uint32_t)A_HALO_BYTES + (uint32_t)(sft * b_tile);
+                                    if (elect_one()) {
+                                        if (NCTA == 2) tma_load_2d_2sm(b_dst, &map_w, bar, kcol, nt[w] * BN + (int)(rank * b_rows));
+                                        else tma_load_2d(b_dst, &map_w, bar, kcol, nt[w] * BN);
+                                    }
+                                }
+                            }
+                            __syncwarp();
+                            if (++q[w] == sp) { q[w] = 0; ph[w] ^= 1u; }
+                        }
+                        c += BK;
+                        if (c >= p.Cin) { c = 0; ++tap; }
+                    }
                 }
             }
         }
@@ -361,24 +416,52 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                 mbar_wait(smem_u32(&tempty_bar[acc]), (use & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)BN;
-                for (int kb = 0; kb < P.k_blocks; ++kb) {
-                    const uint32_t st = q * (uint32_t)NP + (uint32_t)w;
-                    mbar_wait(full0 + 8u * st, ph);
-                    tc_fence_after();
-                    const uint64_t da = desc0 + (uint64_t)(st * stage16);
-                    const uint64_t db = P.bres ? bres_desc + (uint64_t)((uint32_t)kb * (uint32_t)(BN * 8)) : da + (uint64_t)(A_STAGE_BYTES >> 4);
-                    if (elect_one()) {
+                if (!P.halo) {
+                    for (int kb = 0; kb < P.k_blocks; ++kb) {
+                        const uint32_t st = q * (uint32_t)NP + (uint32_t)w;
+                        mbar_wait(full0 + 8u * st, ph);
+                        tc_fence_after();
+                        const uint64_t da = desc0 + (uint64_t)(st * stage16);
+                        const uint64_t db = P.bres ? bres_desc + (uint64_t)((uint32_t)kb * (uint32_t)(BN * 8)) : da + (uint64_t)(A_STAGE_BYTES >> 4);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {
-                            if (NCTA == 2) umma_bf16_2sm(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-                            else umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                            for (int k = 0; k < BK / 16; ++k) {
+                                if (NCTA == 2) umma_bf16_2sm(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                                else umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                            }
+                            // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+                            if (NCTA == 2) umma_commit_2sm(empty0 + 8u * st);
+                            else umma_commit(empty0 + 8u * st);
                         }
-                        // frees the smem stage (in both CTAs of a pair) when these MMAs retire
-                        if (NCTA == 2) umma_commit_2sm(empty0 + 8u * st);
-                        else umma_commit(empty0 + 8u * st);
+                        __syncwarp();
+                        if (++q == sp) { q = 0; ph ^= 1u; }
                     }
-                    __syncwarp();
-                    if (++q == sp) { q = 0; ph ^= 1u; }
+                } else {
+                    for (int kb = 0; kb < P.k_steps; ++kb) {
+                        const uint32_t st = q * (uint32_t)NP + (uint32_t)w;
+                        mbar_wait(full0 + 8u * st, ph);
+                        tc_fence_after();
+                        const uint64_t da = desc0 + (uint64_t)(st * stage16);
+                        const uint64_t db = da + (uint64_t)(A_HALO_BYTES >> 4);
+                        // tap s reads the shared activation box s pixel rows (128 B) further on and its own weight tile
+                        for (int sft = 0; sft < TPS; ++sft) {       // warp-uniform loop, one elected lane issues
+                            const uint64_t das = da + (uint64_t)(sft * 8), dbs = db + (uint64_t)(sft * (b_tile >> 4));
+                            if (elect_one()) {
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k) {
+                                    const uint32_t accum = (kb | sft | k) ? 1u : 0u;
+                                    if (NCTA == 2) umma_bf16_2sm(d_tmem, das + (uint64_t)(2 * k), dbs + (uint64_t)(2 * k), idesc, accum);
+                                    else umma_bf16(d_tmem, das + (uint64_t)(2 * k), dbs + (uint64_t)(2 * k), idesc, accum);
+                                }
+                                if (sft == TPS - 1) {
+                                    if (NCTA == 2) umma_commit_2sm(empty0 + 8u * st);
+                                    else umma_commit(empty0 + 8u * st);
+                                }
+                            }
+                            __syncwarp();
+                        }
+                        if (++q == sp) { q = 0; ph ^= 1u; }
+                    }
                 }
                 if (elect_one()) {   // accumulator complete (signalled in both CTAs of a pair)
                     if (NCTA == 2) umma_commit_2sm(smem_u32(&tfull_bar[acc]));
@@ -592,6 +675,7 @@ int g_umma_debug = 0;
 int g_prefetch_tiles = 0;   // kept for HOIG_UMMA_PREFETCH_TILES compatibility; L2 prefetch of future tiles was measured to hurt and is gone   // measured: L2 prefetch of future tiles HURTS (the streaming convs are L2->SM bandwidth bound, not latency bound)
 
 int g_contig_mode = 1;      // HOIG_UMMA_CONTIG
+int g_halo_mode = 1;        // HOIG_UMMA_HALO: row-halo activation reuse for full-row tiles
 int g_bres_mode = 1;        // HOIG_UMMA_BRES: resident weights for small weight matrices
 int g_dual_mode = 1;        // 1: narrow-N TMA convs run two MMA issue pipelines per CTA (HOIG_UMMA_DUAL=0 disables)
 int g_pair_mode = 1;        // 0: one CTA per tile; 1: CTA pairs (cta_group::2) where they pay off; 2: pairs wherever legal (tests)
@@ -650,10 +734,15 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     const bool pair_ok = P.tma_a && P.m_tiles % 2 == 0 && P.BN % 32 == 0 && p.Npad % P.BN == 0;
     int ncta = (pair_ok && (g_pair_mode == 2 || (g_pair_mode == 1 && P.k_blocks >= 12))) ? 2 : 1;
     // Resident weights (single-CTA tiles, one n-tile): worth it when the whole matrix fits beside >= 4 activation stages
+    // Row-halo mode: regular stride-1 kh x kw conv, tiles = 128 consecutive pixels of one image row
+    P.halo = (g_halo_mode && P.tma_a && p.nviews == 1 && p.kw >= 2 && p.kw <= 7 && p.GW % BM == 0 && p.Cin % BK == 0) ? 1 : 0;
+    if (P.halo && RING_BUDGET / (A_HALO_BYTES + p.kw * (P.BN / ncta) * BK * 2) < 3) P.halo = 0;   // needs >= 3 stages of kw weight tiles
+    P.k_steps = P.halo ? p.kh * (p.Cin / BK) : 0;
     const size_t w_bytes = (size_t)P.k_blocks * P.BN * BK * 2;
     // (not when the conv would run on CTA pairs: measured slower for 128->64 @256^2, whose 147 KB of weights leave 4 stages)
-    P.bres = (g_bres_mode && P.tma_a && P.n_tiles == 1 && ncta == 1 && w_bytes + 4 * (size_t)A_STAGE_BYTES <= (size_t)RING_BUDGET) ? 1 : 0;
-    const int stage_bytes = P.bres ? A_STAGE_BYTES : A_STAGE_BYTES + (P.BN / ncta) * BK * 2;
+    P.bres = (g_bres_mode && !P.halo && P.tma_a && P.n_tiles == 1 && ncta == 1 && w_bytes + 4 * (size_t)A_STAGE_BYTES <= (size_t)RING_BUDGET) ? 1 : 0;
+    const int stage_bytes = P.bres ? A_STAGE_BYTES
+                                   : (P.halo ? A_HALO_BYTES + p.kw * (P.BN / ncta) * BK * 2 : A_STAGE_BYTES + (P.BN / ncta) * BK * 2);
     P.stages = (int)((RING_BUDGET - (P.bres ? w_bytes : 0)) / stage_bytes);
     if (P.stages > MAX_STAGES) P.stages = MAX_STAGES;
     // Narrow tiles (N <= 128): one thread cannot issue 128 x N x 16 MMAs as fast as the tensor pipe retires them
@@ -662,7 +751,7 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     P.contig = g_contig_mode;
     P.dual = (g_dual_mode && P.tma_a && P.BN <= 128 && P.stages >= 4) ? 1 : 0;
     if (P.dual) P.stages &= ~1;
-    HOIG_REQUIRE(P.stages >= LOOKAHEAD + 1, "conv2d: not enough shared memory stages");
+    HOIG_REQUIRE(P.stages >= (P.tma_a ? 2 : LOOKAHEAD + 1), "conv2d: not enough shared memory stages");
 
     P.debug = g_umma_debug;
     P.tpi_shift = -1;
@@ -680,8 +769,8 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     }
     for (int v = 0; v < 4; ++v) map_a[v] = map_w;
     if (P.tma_a) {
-        const int bw = p.GW < BM ? p.GW : BM;
-        const int bh = BM / bw;
+        const int bw = P.halo ? BM + p.kw - 1 : (p.GW < BM ? p.GW : BM);
+        const int bh = P.halo ? 1 : BM / bw;
         const cuuint32_t box[4] = {BK, (cuuint32_t)bw, (cuuint32_t)bh, 1};
         for (int v = 0; v < p.nviews; ++v) {
             const InputView &vw = p.view[v];
@@ -722,6 +811,8 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
         g_force_gather = (e && e[0] == '1') ? 1 : 0;
         const char *pf = getenv("HOIG_UMMA_PREFETCH_TILES");
         if (pf) g_prefetch_tiles = atoi(pf);
+        const char *hm = getenv("HOIG_UMMA_HALO");
+        if (hm) g_halo_mode = atoi(hm);
         const char *bm = getenv("HOIG_UMMA_BRES");
         if (bm) g_bres_mode = atoi(bm);
         const char *cm = getenv("HOIG_UMMA_CONTIG");
@@ -747,6 +838,8 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
 extern "C" void hoig_set_umma_gather_only(int on) { hoig::g_force_gather = on ? 1 : 0; }
 // Diagnostic switch: 0 = one CTA per tile, 1 = CTA pairs (cta_group::2) where they pay off (default), 2 = wherever legal.
 extern "C" void hoig_set_umma_pair_mode(int on) { hoig::g_pair_mode = on; }
+// Diagnostic switch: 1 = full-row tiles of regular stride-1 convs share one activation box per kernel row (default), 0 = one box per tap.
+extern "C" void hoig_set_umma_halo_mode(int on) { hoig::g_halo_mode = on ? 1 : 0; }
 // Diagnostic switch: 1 = small weight matrices stay resident in shared memory (default), 0 = always streamed.
 extern "C" void hoig_set_umma_bres_mode(int on) { hoig::g_bres_mode = on ? 1 : 0; }
 // Diagnostic switch: 1 = two MMA issue pipelines per CTA for narrow-N tiles (default), 0 = one.

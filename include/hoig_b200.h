@@ -154,6 +154,8 @@ void hoig_set_umma_pair_mode(int on);
 void hoig_set_umma_dual_mode(int on);
 /* Test hook: 1 (default) = weight matrices that fit stay resident in shared memory, 0 = always streamed through the ring. */
 void hoig_set_umma_bres_mode(int on);
+/* Test hook: 1 (default) = full-row tiles of regular stride-1 convs load one activation box per kernel row, 0 = one per tap. */
+void hoig_set_umma_halo_mode(int on);
 /* Tuning hook: pixels per rasterizer band (256..16384; the band's 64-bit key buffer lives in shared memory). */
 void hoig_set_rasterizer_band_pixels(int n);
 

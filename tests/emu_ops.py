@@ -85,12 +85,11 @@ def conv2d(x0, weight, out, *, kh, kw, stride=1, pad=0, pad_w=None, mode=0, x1=N
         y = torch.stack([ACT[int(a)](y[..., i]) for i, a in enumerate(act_table.tolist())], -1)
     else:
         y = ACT[act](y)
-    y = _q(y, out)
-    out[..., :cout] = y
     if stats is not None:
-        yf = y.double()
+        yf = y.double()      # statistics of the fp32 values, before the 16-bit store rounding (conv_umma.cu epilogue)
         st = torch.stack([yf.sum((1, 2)), (yf * yf).sum((1, 2))], 2)  # (N, C, 2)
         stats += st.reshape(-1)
+    out[..., :cout] = _q(y, out)
     return out
 
 

@@ -200,3 +200,35 @@ def test_resident_weights_equal_streamed(case, dual):
     assert torch.equal(outs[0][0], outs[1][0])
     if outs[0][1] is not None:
         assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-3)
+
+
+HALO_CASES = [
+    ("3x3_w256_c64_n64_stats", 2, 256, 64, 64, 3, 1, "conv", dict(stats=True)),
+    ("3x3_w128_c128_n256_bias", 1, 128, 128, 256, 3, 1, "conv", dict(bias=True, stats=True)),
+    ("3x3_w128_c256_n128_res", 2, 128, 256, 128, 3, 1, "conv", dict(residual=True, stats=True)),
+    ("3x3_w256_c128_n64", 1, 256, 128, 64, 3, 1, "conv", dict(stats=True, act=1)),
+    ("5x5_w128_c64_n32", 1, 128, 64, 32, 5, 1, "conv", dict(bias=True)),
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES, ids=[c[0] for c in HALO_CASES])
+def test_row_halo_equals_box_per_tap(case):
+    """Full-row tiles: one activation box per kernel row with shifted descriptors vs one box per tap; also against the contract."""
+    import hoig_b200._lib as L
+    outs = []
+    for mode in (0, 1):
+        L.lib().hoig_set_umma_halo_mode(mode)
+        try:
+            out, ref, st, st_ref = _run_conv(case, torch.bfloat16)
+        finally:
+            L.lib().hoig_set_umma_halo_mode(1)
+        outs.append((out.cpu(), None if st is None else st.cpu()))
+    Cout = case[4]
+    ok, rel = _report("halo-mode " + case[0], outs[1][0][..., :Cout], ref[..., :Cout], 2e-2, 2e-2)
+    assert ok and rel < 1e-2
+    # same products; the fp32 accumulation order differs ((row, channel block, tap) instead of (tap, channel block)):
+    # at most one 16-bit ulp apart
+    a, b = outs[0][0].float(), outs[1][0].float()
+    assert ((a - b).abs() <= 2.0 ** -7 * b.abs() + 1e-3).all()
+    if outs[0][1] is not None:
+        assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-3)
