@@ -63,6 +63,7 @@ struct UmmaParams {
                          //    activation box of 128 + kw - 1 pixels per (kernel row, 64 channels) and the kw taps read it through
                          //    descriptors shifted by one pixel row (128 B) each -- L2->SM activation traffic / kw (see conv_halo.cu)
     int k_steps;         // halo: kh * Cin / 64 pipeline steps of kw taps each
+    int mma_stats;       // 1: per-plane statistics reduced with warp-level MMAs (colsum16), 0: shuffle transpose-reduce
     int bres;            // 1: the whole packed weight matrix (k_blocks tiles of BN x 64) stays RESIDENT in shared memory, loaded
                          //    once per CTA; the ring then carries activations only.  For the narrow high-resolution convs the
                          //    L2->SM path (~42 B/clk/SM), not the tensor pipe, is the bound, and weights are 1/3 of that traffic.
@@ -489,6 +490,9 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
         uint32_t tcount = 0;
         const uint32_t tempty0 = NCTA == 2 ? mapa(smem_u32(&tempty_bar[0]), 0) : smem_u32(&tempty_bar[0]);   // in the leader CTA
         int cur_img = -1, cur_nt = -1;
+        uint32_t e_sel[4], e_sel_bf[4];      // 0/1 selection fragments of colsum16 in the operand type / in bf16 (squares)
+        colsum_select<std::is_same<T, __half>::value>(lane, e_sel);
+        colsum_select<false>(lane, e_sel_bf);
         const bool spade = p.spade_x != nullptr;
         float *s_mod = &s_stats[0][0][0];   // SPADE epilogue: mean[1024] | rstd[1024] (the statistics buffer is idle in that mode)
         // per-plane sum / sum of squares of the tiles since the last flush: one atomicAdd(double) per column
@@ -617,8 +621,29 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                         }
                     }
                     if (p.stats) {
-                        // Statistics of the fp32 values (before the 16-bit store rounding, i.e. closer to the reference's fp32
-                        // activations); rows past the end of the plane contribute nothing.
+                        if (P.mma_stats) {
+                            // Column sums of the stored 16-bit values and of their squares (rounded to bf16) on the warp-level
+                            // tensor-core path (umma_common.cuh colsum16): ~60 instructions instead of ~140 per chunk.
+                            constexpr bool kF16 = std::is_same<T, __half>::value;
+                            uint32_t sq[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                if (!all_valid && !valid) pk[j] = 0u;
+                                float lo, hi;
+                                unpack2<T>(pk[j], lo, hi);
+                                sq[j] = pack2<__nv_bfloat16>(lo * lo, hi * hi);
+                            }
+                            float s_lo, s_hi, q_lo, q_hi;
+                            colsum16<kF16>(pk, e_sel, s_lo, s_hi);
+                            colsum16<false>(sq, e_sel_bf, q_lo, q_hi);
+                            if ((lane & 3) == 0) {      // (quad, column) is touched by this warp only
+                                const int col = c0 + (lane >> 2);
+                                s_stats[quad][0][col] += s_lo; s_stats[quad][0][col + 8] += s_hi;
+                                s_stats[quad][1][col] += q_lo; s_stats[quad][1][col + 8] += q_hi;
+                            }
+                        } else {
+                        // Statistics of the fp32 values (before the 16-bit store rounding); rows past the end of the plane
+                        // contribute nothing.
                         float q[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
@@ -631,6 +656,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                             const int col = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
                             s_stats[quad][0][col] += cs;   // (quad, column) is touched by this warp only
                             s_stats[quad][1][col] += cq;
+                        }
                         }
                     }
             };
@@ -675,6 +701,7 @@ int g_umma_debug = 0;
 int g_prefetch_tiles = 0;   // kept for HOIG_UMMA_PREFETCH_TILES compatibility; L2 prefetch of future tiles was measured to hurt and is gone   // measured: L2 prefetch of future tiles HURTS (the streaming convs are L2->SM bandwidth bound, not latency bound)
 
 int g_contig_mode = 1;      // HOIG_UMMA_CONTIG
+int g_mma_stats = 1;        // HOIG_UMMA_MMA_STATS
 int g_halo_mode = 1;        // HOIG_UMMA_HALO: row-halo activation reuse for full-row tiles
 int g_bres_mode = 1;        // HOIG_UMMA_BRES: resident weights for small weight matrices
 int g_dual_mode = 1;        // 1: narrow-N TMA convs run two MMA issue pipelines per CTA (HOIG_UMMA_DUAL=0 disables)
@@ -749,6 +776,7 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     // (scripts/probes/mma_probe.cu: ~65-100 cycles of issue overhead vs 48-64 cycles of execution), so two warps
     // issue, each driving its own pipeline (half of the ring, two of four accumulator stages, alternate tiles).
     P.contig = g_contig_mode;
+    P.mma_stats = g_mma_stats;
     P.dual = (g_dual_mode && P.tma_a && P.BN <= 128 && P.stages >= 4) ? 1 : 0;
     if (P.dual) P.stages &= ~1;
     HOIG_REQUIRE(P.stages >= (P.tma_a ? 2 : LOOKAHEAD + 1), "conv2d: not enough shared memory stages");
@@ -811,6 +839,8 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
         g_force_gather = (e && e[0] == '1') ? 1 : 0;
         const char *pf = getenv("HOIG_UMMA_PREFETCH_TILES");
         if (pf) g_prefetch_tiles = atoi(pf);
+        const char *ms = getenv("HOIG_UMMA_MMA_STATS");
+        if (ms) g_mma_stats = atoi(ms);
         const char *hm = getenv("HOIG_UMMA_HALO");
         if (hm) g_halo_mode = atoi(hm);
         const char *bm = getenv("HOIG_UMMA_BRES");

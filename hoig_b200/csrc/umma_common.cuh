@@ -242,5 +242,45 @@ int make_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t *dim
     return HOIG_OK;
 }
 
+
+// ---- column sums of a 32-row x 16-column block held one row per lane (the epilogue's register layout) on the legacy
+// warp-level tensor-core path.  Each lane passes its own row's packed 16-bit pairs as the B fragment of m16n8k16
+// (k slots (2t, 2t+1, 2t+8, 2t+9) of column n = lane / 4 are the row's four values), and A is a 0/1 selection matrix that
+// routes slot s of MMA j to output row 4*j + s, so D[m][n] = sum over the four rows 4n..4n+3 of column m.  Adding the two D
+// values of a lane and reducing over the four lanes of a group leaves, on every lane, the totals of columns lane/4 and
+// lane/4 + 8: 4 MMAs + 4 shuffles instead of a 31-shuffle transpose-reduce.
+template <bool F16>
+__device__ __forceinline__ void hmma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    if (F16)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// e[i] = (lane/4 == 2i ? 1 : 0, lane/4 == 2i+1 ? 1 : 0) as a packed 16-bit pair of the operand type
+template <bool F16>
+__device__ __forceinline__ void colsum_select(int lane, uint32_t (&e)[4])
+{
+    const uint32_t one = F16 ? 0x3C00u : 0x3F80u;
+    const int g = lane >> 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) e[i] = (g == 2 * i ? one : 0u) | (g == 2 * i + 1 ? one << 16 : 0u);
+}
+template <bool F16>
+__device__ __forceinline__ void colsum16(const uint32_t (&pk)[8], const uint32_t (&e)[4], float &lo, float &hi)
+{
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    hmma_16816<F16>(d, e[0], 0u, e[1], 0u, pk[0], pk[1]);   // columns 0-3   -> D rows 0-3
+    hmma_16816<F16>(d, e[2], 0u, e[3], 0u, pk[2], pk[3]);   // columns 4-7   -> D rows 4-7
+    hmma_16816<F16>(d, 0u, e[0], 0u, e[1], pk[4], pk[5]);   // columns 8-11  -> D rows 8-11
+    hmma_16816<F16>(d, 0u, e[2], 0u, e[3], pk[6], pk[7]);   // columns 12-15 -> D rows 12-15
+    lo = d[0] + d[1];
+    hi = d[2] + d[3];
+    lo += __shfl_xor_sync(0xffffffffu, lo, 1); hi += __shfl_xor_sync(0xffffffffu, hi, 1);
+    lo += __shfl_xor_sync(0xffffffffu, lo, 2); hi += __shfl_xor_sync(0xffffffffu, hi, 2);
+}
+
 }  // namespace
 }  // namespace hoig
