@@ -1,4 +1,5 @@
 // mma_probe.cu -- how long does one tcgen05.mma (128 x N x 16, kind::f16, operands in smem) take as a function of N,
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o mma_probe mma_probe.cu -lcuda
 // the number of accumulators the issue stream rotates over, and the commit cadence?  One CTA per SM, no TMA traffic.
 #include <cuda.h>
 #include <cuda_runtime.h>
