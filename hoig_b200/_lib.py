@@ -82,6 +82,10 @@ _SIGNATURES = {
                                  c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_void_p]),
     "hoig_attn_unfold": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                  c_int, c_int, c_void_p]),
+    "hoig_uv_backward_warp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "hoig_sample_texture_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "hoig_grid_sample_nchw": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "hoig_uv_texture_compose": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "hoig_seg_unfold3": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
     "hoig_replicate_pad": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "hoig_conv2d_halo": (c_int, [c_int, c_int, c_int, c_int, POINTER(HaloConvSeg), c_int, c_void_p]),

@@ -538,6 +538,119 @@ __global__ void erode_kernel(const float *__restrict__ in, float *__restrict__ o
 }
 
 }  // namespace
+
+// ------------------------------------------------------------------ stage R8: UV-texture warp
+// utils/nmr.py:973-1040 (get_texture_backward_warp, first half), one thread per (sample, atlas pixel).
+__global__ void uv_backward_warp_kernel(const float *__restrict__ src_faces, const int32_t *__restrict__ fim_uv,
+                                        const float *__restrict__ wim_uv, const int32_t *__restrict__ src_fim, int64_t n, int hw_uv,
+                                        int F, int is, float *__restrict__ T, float *__restrict__ O)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int b = (int)(i / hw_uv), p = (int)(i % hw_uv);
+    const int f = fim_uv[p];
+    float tx = -2.f, ty = -2.f, o = 0.f;
+    if (f != -1) {
+        const float *fv = src_faces + ((size_t)b * F + f) * 9;
+        const float w0 = wim_uv[3 * p], w1 = wim_uv[3 * p + 1], w2 = wim_uv[3 * p + 2];
+        // (f2pts * w[:, :, None]).sum(dim=1): products rounded, summed in vertex order; y negated as trainer.py:67-68
+        tx = __fadd_rn(__fadd_rn(__fmul_rn(fv[0], w0), __fmul_rn(fv[3], w1)), __fmul_rn(fv[6], w2));
+        ty = __fadd_rn(__fadd_rn(__fmul_rn(-fv[1], w0), __fmul_rn(-fv[4], w1)), __fmul_rn(-fv[7], w2));
+        // ((T + 1) / 2.0 * 255.0).long().clamp(0, 255): truncation toward zero, the literal 255 of nmr.py:1014
+        const float lim = (float)(is - 1);
+        const int cx = min(max((int)__fmul_rn(__fdiv_rn(__fadd_rn(tx, 1.f), 2.f), lim), 0), is - 1);
+        const int cy = min(max((int)__fmul_rn(__fdiv_rn(__fadd_rn(ty, 1.f), 2.f), lim), 0), is - 1);
+        const int32_t *sf = src_fim + (size_t)b * is * is;
+        bool vis = false;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int x = min(max(cx + dx, 0), is - 1), y = min(max(cy + dy, 0), is - 1);
+                vis |= sf[y * is + x] == f;
+            }
+        o = vis ? 0.f : 1.f;
+    }
+    T[2 * i] = tx;
+    T[2 * i + 1] = ty;
+    O[i] = o;
+}
+
+// utils/nmr.py:1068-1100 sample_from_texture_dense: uv_coord (F,3,2) shared by the batch
+__global__ void sample_texture_dense_kernel(const float *__restrict__ uv_coord, const int32_t *__restrict__ fim,
+                                            const float *__restrict__ wim, int64_t n, float *__restrict__ T)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int f = fim[i];
+    float tx = -2.f, ty = -2.f;
+    if (f != -1) {
+        const float *uv = uv_coord + (size_t)f * 6;
+        const float w0 = wim[3 * i], w1 = wim[3 * i + 1], w2 = wim[3 * i + 2];
+        tx = __fadd_rn(__fadd_rn(__fmul_rn(uv[0], w0), __fmul_rn(uv[2], w1)), __fmul_rn(uv[4], w2));
+        ty = __fadd_rn(__fadd_rn(__fmul_rn(uv[1], w0), __fmul_rn(uv[3], w1)), __fmul_rn(uv[5], w2));
+    }
+    T[2 * i] = tx;
+    T[2 * i + 1] = ty;
+}
+
+// F.grid_sample(im, grid, 'bilinear', 'zeros', align_corners) on NCHW f32 (aten GridSampler.cuh semantics: unnormalise,
+// floor, the four corner weights as products of the distances to the opposite corner, out-of-range corners contribute 0)
+__global__ void grid_sample_nchw_kernel(const float *__restrict__ im, int B, int C, int Hi, int Wi, const float *__restrict__ grid,
+                                        int Ho, int Wo, int align, float *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * Ho * Wo) return;
+    const int b = (int)(i / ((int64_t)Ho * Wo));
+    const int64_t p = i % ((int64_t)Ho * Wo);
+    const float gx = grid[2 * i], gy = grid[2 * i + 1];
+    const float ix = align ? (gx + 1.f) / 2.f * (float)(Wi - 1) : ((gx + 1.f) * (float)Wi - 1.f) / 2.f;
+    const float iy = align ? (gy + 1.f) / 2.f * (float)(Hi - 1) : ((gy + 1.f) * (float)Hi - 1.f) / 2.f;
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+    const float nw = (x1 - ix) * (y1 - iy), ne = (ix - x0) * (y1 - iy), sw = (x1 - ix) * (iy - y0), se = (ix - x0) * (iy - y0);
+    const bool vx0 = x0 >= 0 && x0 < Wi, vx1 = x1 >= 0 && x1 < Wi, vy0 = y0 >= 0 && y0 < Hi, vy1 = y1 >= 0 && y1 < Hi;
+    for (int c = 0; c < C; ++c) {
+        const float *pl = im + ((size_t)b * C + c) * Hi * Wi;
+        float acc = 0.f;
+        if (vy0 && vx0) acc += pl[(size_t)y0 * Wi + x0] * nw;
+        if (vy0 && vx1) acc += pl[(size_t)y0 * Wi + x1] * ne;
+        if (vy1 && vx0) acc += pl[(size_t)y1 * Wi + x0] * sw;
+        if (vy1 && vx1) acc += pl[(size_t)y1 * Wi + x1] * se;
+        out[((size_t)b * C + c) * Ho * Wo + p] = acc;
+    }
+}
+
+// utils/nmr.py:1049-1056: O <- 1 - erode3(1 - erode3(O)) (util.morph, pad value 1), syn = syn*(1-O) + O, then the stock object
+// texture over columns >= x0
+__global__ void uv_texture_compose_kernel(float *__restrict__ syn, const float *__restrict__ O, const float *__restrict__ preload,
+                                          int B, int C, int Hu, int Wu, int x0)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * Hu * Wu) return;
+    const int b = (int)(i / ((int64_t)Hu * Wu));
+    const int y = (int)((i / Wu) % Hu), x = (int)(i % Wu);
+    const float *Ob = O + (size_t)b * Hu * Wu;
+    float open = 0.f;   // dilate3(erode3(O)): any in-image neighbour q whose whole (pad-1) 3x3 window is 1
+    for (int dy = -1; dy <= 1 && open == 0.f; ++dy)
+        for (int dx = -1; dx <= 1 && open == 0.f; ++dx) {
+            const int qy = y + dy, qx = x + dx;
+            if (qy < 0 || qy >= Hu || qx < 0 || qx >= Wu) continue;
+            float s = 0.f;
+            for (int ey = -1; ey <= 1; ++ey)
+                for (int ex = -1; ex <= 1; ++ex) {
+                    const int ry = qy + ey, rx = qx + ex;
+                    s += (ry < 0 || ry >= Hu || rx < 0 || rx >= Wu) ? 1.f : Ob[(size_t)ry * Wu + rx];
+                }
+            if (s == 9.f) open = 1.f;
+        }
+    for (int c = 0; c < C; ++c) {
+        float *v = syn + (((size_t)b * C + c) * Hu + y) * Wu + x;
+        if (preload && x >= x0) *v = preload[((size_t)y * (Wu - x0) + (x - x0)) * C + c];
+        else *v = *v * (1.f - open) + 1.0f * open;
+    }
+}
+
 }  // namespace hoig
 
 using namespace hoig;
@@ -635,4 +748,44 @@ extern "C" int hoig_erode(const float *in, float *out, int B, int H, int W, int 
     if (n == 0) return HOIG_OK;
     erode_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(in, out, B, H, W, ks);
     return check_launch("erode_kernel");
+}
+
+extern "C" int hoig_uv_backward_warp(const float *src_faces, const int32_t *fim_uv, const float *wim_uv, const int32_t *src_fim,
+                                     int B, int F, int Hu, int Wu, int image_size, float *T, float *O, hoigStream_t stream)
+{
+    HOIG_REQUIRE(src_faces && fim_uv && wim_uv && src_fim && T && O && image_size > 0, "uv_backward_warp: bad argument");
+    const int64_t n = (int64_t)B * Hu * Wu;
+    if (n == 0) return HOIG_OK;
+    uv_backward_warp_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(src_faces, fim_uv, wim_uv, src_fim, n, Hu * Wu, F, image_size, T, O);
+    return check_launch("uv_backward_warp_kernel");
+}
+
+extern "C" int hoig_sample_texture_dense(const float *uv_coord, const int32_t *fim, const float *wim, int B, int H, int W, float *T,
+                                         hoigStream_t stream)
+{
+    HOIG_REQUIRE(uv_coord && fim && wim && T, "sample_texture_dense: null pointer");
+    const int64_t n = (int64_t)B * H * W;
+    if (n == 0) return HOIG_OK;
+    sample_texture_dense_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(uv_coord, fim, wim, n, T);
+    return check_launch("sample_texture_dense_kernel");
+}
+
+extern "C" int hoig_grid_sample_nchw(const float *im, int B, int C, int Hi, int Wi, const float *grid, int Ho, int Wo, int align_corners,
+                                     float *out, hoigStream_t stream)
+{
+    HOIG_REQUIRE(im && grid && out && C > 0 && Hi > 0 && Wi > 0, "grid_sample_nchw: bad argument");
+    const int64_t n = (int64_t)B * Ho * Wo;
+    if (n == 0) return HOIG_OK;
+    grid_sample_nchw_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(im, B, C, Hi, Wi, grid, Ho, Wo, align_corners, out);
+    return check_launch("grid_sample_nchw_kernel");
+}
+
+extern "C" int hoig_uv_texture_compose(float *syn, const float *O, const float *preload, int B, int C, int Hu, int Wu, int x0,
+                                       hoigStream_t stream)
+{
+    HOIG_REQUIRE(syn && O && x0 >= 0 && x0 <= Wu, "uv_texture_compose: bad argument");
+    const int64_t n = (int64_t)B * Hu * Wu;
+    if (n == 0) return HOIG_OK;
+    uv_texture_compose_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(syn, O, preload, B, C, Hu, Wu, x0);
+    return check_launch("uv_texture_compose_kernel");
 }

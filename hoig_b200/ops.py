@@ -118,6 +118,53 @@ def erode(mask: torch.Tensor, ks: int) -> torch.Tensor:
     return out
 
 
+def uv_backward_warp(src_faces: torch.Tensor, fim_uv: torch.Tensor, wim_uv: torch.Tensor, src_fim: torch.Tensor):
+    """utils/nmr.py:973-1040: (T (B,Hu,Wu,2), O (B,1,Hu,Wu)) of the atlas pixels, see ``hoig_uv_backward_warp``."""
+    B, F = src_faces.shape[:2]
+    Hu, Wu = fim_uv.shape[-2:]
+    if fim_uv.dtype != torch.int32 or src_fim.dtype != torch.int32 or not fim_uv.is_contiguous() or not src_fim.is_contiguous():
+        raise ValueError("uv_backward_warp: face-index maps must be contiguous int32")
+    T = torch.empty(B, Hu, Wu, 2, dtype=torch.float32, device=src_faces.device)
+    O = torch.empty(B, 1, Hu, Wu, dtype=torch.float32, device=src_faces.device)
+    _lib.check(_lib.lib().hoig_uv_backward_warp(_f32c(src_faces, "src_faces"), fim_uv.data_ptr(), _f32c(wim_uv, "wim_uv"),
+                                                src_fim.data_ptr(), B, F, Hu, Wu, src_fim.shape[-1], T.data_ptr(), O.data_ptr(),
+                                                _stream()), "uv_backward_warp")
+    return T, O
+
+
+def sample_texture_dense(uv_coord: torch.Tensor, fim: torch.Tensor, wim: torch.Tensor) -> torch.Tensor:
+    """utils/nmr.py:1068-1100: T (B,H,W,2) = barycentric blend of the per-face UV coordinates, -2 off the mesh."""
+    B, H, W = fim.shape
+    if fim.dtype != torch.int32 or not fim.is_contiguous():
+        raise ValueError("sample_texture_dense: fim must be contiguous int32")
+    T = torch.empty(B, H, W, 2, dtype=torch.float32, device=fim.device)
+    _lib.check(_lib.lib().hoig_sample_texture_dense(_f32c(uv_coord, "uv_coord"), fim.data_ptr(), _f32c(wim, "wim"), B, H, W,
+                                                    T.data_ptr(), _stream()), "sample_texture_dense")
+    return T
+
+
+def grid_sample_nchw(im: torch.Tensor, grid: torch.Tensor, align_corners: bool) -> torch.Tensor:
+    """F.grid_sample(im, grid, 'bilinear', 'zeros', align_corners) for NCHW f32 images."""
+    B, C, Hi, Wi = im.shape
+    _, Ho, Wo, two = grid.shape
+    if two != 2 or grid.shape[0] != B:
+        raise ValueError("grid_sample_nchw: grid must be (B,Ho,Wo,2)")
+    out = torch.empty(B, C, Ho, Wo, dtype=torch.float32, device=im.device)
+    _lib.check(_lib.lib().hoig_grid_sample_nchw(_f32c(im, "im"), B, C, Hi, Wi, _f32c(grid, "grid"), Ho, Wo, int(align_corners),
+                                                out.data_ptr(), _stream()), "grid_sample_nchw")
+    return out
+
+
+def uv_texture_compose(syn: torch.Tensor, O: torch.Tensor, preload: Optional[torch.Tensor] = None, x0: int = 384) -> torch.Tensor:
+    """utils/nmr.py:1049-1056 in place on ``syn`` (B,C,Hu,Wu): open3(O) blend towards 1, then the stock object texture."""
+    B, C, Hu, Wu = syn.shape
+    if preload is not None and tuple(preload.shape) != (Hu, Wu - x0, C):
+        raise ValueError(f"uv_texture_compose: preload must be ({Hu},{Wu - x0},{C}) HWC")
+    _lib.check(_lib.lib().hoig_uv_texture_compose(_f32c(syn, "syn"), _f32c(O, "O"), _f32c(preload, "preload") if preload is not None else None,
+                                                  B, C, Hu, Wu, x0 if preload is not None else Wu, _stream()), "uv_texture_compose")
+    return syn
+
+
 # ------------------------------------------------------- reference op boundary
 def block_extract(source: torch.Tensor, flow: torch.Tensor, out: torch.Tensor, k: int) -> torch.Tensor:
     B, C, Hs, Ws = source.shape

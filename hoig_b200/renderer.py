@@ -72,3 +72,25 @@ def condition_inputs(src_img, faces_src, fim_src, fim_ref, wim_ref, map_fn, sem_
     out["T"] = T_hand
     masks = dict(src_mask_bg=s["m_bg"], ref_mask_bg=r["m_bg"], src_mask_hand=s["m_hand"], ref_mask_hand=r["m_hand"])
     return out, masks
+
+
+# ------------------------------------------------------------------ stage R8: UV-texture warp
+def texture_backward_warp(im, src_faces, src_fim, fim_uv, wim_uv, obj_tex=None, x0: int = 384):
+    """``MANORenderer.get_texture_backward_warp`` (utils/nmr.py:973-1058), batched.
+
+    im (B,3,256,256) source images; src_faces (B,F,3,3) projected source faces (``hoig_project_faces`` layout; the y flip of
+    trainer.py:67-68 happens inside); src_fim (B,256,256) int32; fim_uv / wim_uv the object's UV atlas maps (Hu,Wu) / (Hu,Wu,3);
+    obj_tex the stock object texture (Hu, Wu-x0, 3) or None (``pre_load=False``).  Returns the texture atlas (B,3,Hu,Wu)."""
+    T, O = ops.uv_backward_warp(src_faces, fim_uv, wim_uv, src_fim)
+    syn = ops.grid_sample_nchw(im, T, align_corners=False)               # nmr.py:1047 (torch default)
+    return ops.uv_texture_compose(syn, O, obj_tex, x0)                    # nmr.py:1049-1056
+
+
+def sample_from_texture_dense(fim, wim, faces_uv_coord):
+    """``MANORenderer.sample_from_texture_dense`` (utils/nmr.py:1068-1100), batched: T (B,H,W,2)."""
+    return ops.sample_texture_dense(faces_uv_coord, fim, wim)
+
+
+def render_from_texture(texture, fim, wim, faces_uv_coord):
+    """models/trainer.py:84-87: re-render the texture atlas at a pose given its face-index / weight maps."""
+    return ops.grid_sample_nchw(texture, sample_from_texture_dense(fim, wim, faces_uv_coord), align_corners=True)

@@ -89,6 +89,26 @@ int hoig_bc_transform(const float *src_faces, const int32_t *fim_ref, const floa
 /* R6 utils/util.py:142-153 erode (pad value 1, all-ones ks x ks window). in/out (B,1,H,W) f32. */
 int hoig_erode(const float *in, float *out, int B, int H, int W, int ks, hoigStream_t stream);
 
+/* ---- stage R8: UV-texture warp (utils/nmr.py:973-1100, models/trainer.py:83-87)
+ * hoig_uv_backward_warp: nmr.py:973-1040.  For every atlas pixel p with fim_uv[p] != -1 (fim_uv (Hu,Wu) int32, wim_uv (Hu,Wu,3),
+ * shared by the batch):  T[b,p] = sum_k src_faces[b][fim_uv[p]][k].xy (y negated, trainer.py:67-68) * wim_uv[p][k], else -2;
+ * O[b,p] = 1 - [one of the 3x3 neighbours (clamped) of trunc((T+1)/2*(is-1)) in src_fim[b] (is x is) equals fim_uv[p]], else 0.
+ * src_faces (B,F,3,3) f32 as produced by hoig_project_faces; T (B,Hu,Wu,2), O (B,1,Hu,Wu) f32. */
+int hoig_uv_backward_warp(const float *src_faces, const int32_t *fim_uv, const float *wim_uv, const int32_t *src_fim,
+                          int B, int F, int Hu, int Wu, int image_size, float *T, float *O, hoigStream_t stream);
+/* nmr.py:1068-1100 sample_from_texture_dense: T[b,p] = sum_k uv_coord[fim[b,p]][k] * wim[b,p][k], -2 where fim == -1;
+ * uv_coord (F,3,2) f32 shared by the batch; fim (B,H,W) int32; wim (B,H,W,3); T (B,H,W,2). */
+int hoig_sample_texture_dense(const float *uv_coord, const int32_t *fim, const float *wim, int B, int H, int W, float *T,
+                              hoigStream_t stream);
+/* F.grid_sample(im, grid, mode='bilinear', padding_mode='zeros', align_corners) on NCHW f32 images:
+ * im (B,C,Hi,Wi), grid (B,Ho,Wo,2) -> out (B,C,Ho,Wo)  (nmr.py:1047 uses align_corners=False, trainer.py:85,87 True). */
+int hoig_grid_sample_nchw(const float *im, int B, int C, int Hi, int Wi, const float *grid, int Ho, int Wo, int align_corners,
+                          float *out, hoigStream_t stream);
+/* nmr.py:1049-1056: O <- 1 - erode3(1 - erode3(O)); syn <- syn*(1-O) + O; columns >= x0 of syn are replaced by the stock object
+ * texture `preload` ((Hu, Wu-x0, C) HWC f32) when it is non-NULL.  syn (B,C,Hu,Wu) in place, O (B,1,Hu,Wu). */
+int hoig_uv_texture_compose(float *syn, const float *O, const float *preload, int B, int C, int Hu, int Wu, int x0,
+                            hoigStream_t stream);
+
 /* ------------------------------------------------- reference op boundary B2
  * thirdparty/block_extractor/block_extractor_cuda.cc:5-16 (forward):
  *   source (B,C,Hs,Ws), flow (B,2,Hf,Wf), out (B,C,k*Hf,k*Wf), all NCHW f32. */

@@ -126,3 +126,57 @@ def condition_maps(faces_src, fim_src, fim_ref, wim_ref, map_fn, sem_full, n_han
     out["T"] = T
     out["T_hand"] = T * (mh == 0) + (-2) * torch.ones_like(T) * (mh == 1)
     return out
+
+
+# ------------------------------------------------------------------ stage R8: UV-texture warp (test infrastructure)
+def texture_backward_warp(im, src_f2verts, src_fims, fim_uv, wim_uv, obj_tex=None, x0=384):
+    """utils/nmr.py:973-1058 restated for CPU tensors, same loops and op order.  src_f2verts (B,F,3,2) are the projected source
+    face vertices AFTER trainer.py:67-68 (xy only, y negated); fim_uv (Hu,Wu) long/int, wim_uv (Hu,Wu,3); src_fims (B,is,is)."""
+    import torch.nn.functional as F
+    bs = src_f2verts.shape[0]
+    hu, wu = fim_uv.shape
+    size = src_fims.shape[-1]
+    T = -2 * torch.ones((bs, hu * wu, 2), dtype=torch.float32)
+    O = torch.zeros((bs, hu * wu, 1), dtype=torch.float32)
+    for i in range(bs):
+        to_fim = fim_uv.long().reshape(-1)
+        to_wim = wim_uv.reshape(-1, 3)
+        exist = to_fim != -1
+        face_idx = to_fim[exist]
+        weights = to_wim[exist]
+        smpl_T = (src_f2verts[i][face_idx] * weights[:, :, None]).sum(dim=1)
+        T[i, exist] = smpl_T
+        from_fim = src_fims[i].long().reshape(-1)
+        t11 = ((smpl_T + 1) / 2.0 * float(size - 1)).long().clamp(0, size - 1)
+        visible = torch.zeros_like(face_idx, dtype=torch.bool)
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                t = (t11 + torch.tensor([dx, dy])).clamp(0, size - 1)
+                visible |= from_fim[t[:, 1] * size + t[:, 0]] == face_idx
+        O[i, exist, 0] = 1 - visible.float()
+    T = T.view(bs, hu, wu, 2)
+    O = O.view(bs, hu, wu, 1).permute(0, 3, 1, 2)
+    syn = F.grid_sample(im, T, align_corners=False)
+    O = erode(O, 3)
+    O = 1 - erode(1 - O, 3)
+    syn = syn * (1 - O) + 1.0 * torch.ones_like(syn) * O
+    if obj_tex is not None:
+        syn[:, :, :, x0:] = obj_tex.permute(2, 0, 1)[None]
+    return syn, T, O
+
+
+def sample_from_texture_dense(fim, wim, faces_uv_coord):
+    """utils/nmr.py:1068-1100."""
+    bs, h, w = fim.shape
+    T = -2 * torch.ones((bs, h * w, 2), dtype=torch.float32)
+    for i in range(bs):
+        f = fim[i].long().reshape(-1)
+        exist = f != -1
+        T[i, exist] = (faces_uv_coord[f[exist]] * wim[i].reshape(-1, 3)[exist][:, :, None]).sum(dim=1)
+    return T.view(bs, h, w, 2)
+
+
+def render_from_texture(texture, fim, wim, faces_uv_coord):
+    """models/trainer.py:84-87."""
+    import torch.nn.functional as F
+    return F.grid_sample(texture, sample_from_texture_dense(fim, wim, faces_uv_coord), align_corners=True)

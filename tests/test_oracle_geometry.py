@@ -109,3 +109,34 @@ def test_scene_rasterizes_both_parts_and_T_roundtrip():
     # pixel (row y, col x) of the flipped map sits at ndc ((2x+1-256)/256, -(2(255-y)+1-256)/256) in image coords
     assert np.abs(t[:, 0] - (2 * xs + 1 - 256) / 256).max() < 2e-2
     assert np.abs(t[:, 1] - (2 * ys + 1 - 256) / 256).max() < 2e-2
+
+
+def test_texture_warp_oracle_identity_atlas_resamples_the_image():
+    """nmr.py:973-1058 with one source triangle covering the whole image, everything visible, and an atlas whose barycentric
+    weights reproduce the atlas pixel centres: the texture is the bilinear resize of the image (grid_sample, align_corners=False)."""
+    import torch.nn.functional as F
+    size, hu, wu = 32, 24, 40
+    g = torch.Generator().manual_seed(2)
+    im = torch.rand(2, 3, size, size, generator=g)
+    tri = torch.tensor([[-3.0, -3.0], [5.0, -3.0], [-3.0, 5.0]])          # covers [-1,1]^2
+    f2v = tri[None, None].repeat(2, 1, 1, 1)                                # (B, F=1, 3, 2), already y-flipped coordinates
+    ys = (torch.arange(hu) * 2 + 1) / hu - 1
+    xs = (torch.arange(wu) * 2 + 1) / wu - 1
+    py, px = torch.meshgrid(ys, xs, indexing="ij")
+    w1, w2 = (px + 3) / 8, (py + 3) / 8                                     # p = v0 + w1 (v1 - v0) + w2 (v2 - v0)
+    wim_uv = torch.stack([1 - w1 - w2, w1, w2], -1)
+    fim_uv = torch.zeros(hu, wu, dtype=torch.int32)
+    src_fim = torch.zeros(2, size, size, dtype=torch.int32)
+    syn, T, O = geo.texture_backward_warp(im, f2v, src_fim, fim_uv, wim_uv)
+    assert O.abs().max().item() == 0
+    assert (T[0, ..., 0] - px).abs().max().item() <= 1e-6 and (T[0, ..., 1] - py).abs().max().item() <= 1e-6
+    ref = F.interpolate(im, size=(hu, wu), mode="bilinear", align_corners=False)
+    assert (syn - ref)[:, :, 2:-2, 2:-2].abs().max().item() <= 1e-5     # the rim differs: zeros padding vs interpolate's clamping
+    # nothing visible -> occluded everywhere -> the opened mask paints the texture white
+    syn2, _, O2 = geo.texture_backward_warp(im, f2v, src_fim - 1, fim_uv, wim_uv)
+    assert O2.min().item() == 1 and (syn2 - 1).abs().max().item() == 0
+    # off-mesh pixels of a pose sample to -2 and render as zeros (grid_sample zeros padding)
+    fim = torch.full((1, 8, 8), -1, dtype=torch.int32)
+    Td = geo.sample_from_texture_dense(fim, torch.ones(1, 8, 8, 3) / 3, torch.zeros(1, 3, 2))
+    assert (Td == -2).all()
+    assert geo.render_from_texture(syn[:1], fim, torch.ones(1, 8, 8, 3) / 3, torch.zeros(1, 3, 2)).abs().max().item() == 0
