@@ -43,6 +43,15 @@ class ConvDesc(Structure):
     ]
 
 
+class CondInputsDesc(Structure):
+    """Mirror of ``hoigCondInputsDesc``."""
+    _fields_ = ([(n, c_void_p) for n in ("fim_src", "fim_ref", "wim_ref", "src_faces", "src_img", "render_src", "render_ref", "map_fn",
+                                         "sem_full", "bg_inputs", "src_obj_inputs", "src_obj_conds", "src_hand_inputs", "src_hand_conds",
+                                         "tsf_obj_inputs", "tsf_obj_conds", "tsf_hand_inputs", "tsf_hand_conds", "T", "src_mask_bg",
+                                         "ref_mask_bg", "src_mask_hand", "ref_mask_hand")]
+                + [(n, c_int) for n in ("B", "F", "image_size", "n_hand_faces", "bg_erode_ks")])
+
+
 class HaloConvSeg(Structure):
     """Mirror of ``hoigHaloConvSeg``."""
     _fields_ = [("src", c_void_p), ("ld", c_int64), ("N", c_int), ("Hp", c_int), ("Wp", c_int), ("C", c_int),
@@ -82,6 +91,7 @@ _SIGNATURES = {
                                  c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_void_p]),
     "hoig_attn_unfold": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                  c_int, c_int, c_void_p]),
+    "hoig_condition_inputs": (c_int, [POINTER(CondInputsDesc), c_void_p]),
     "hoig_uv_backward_warp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "hoig_sample_texture_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hoig_grid_sample_nchw": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -651,6 +651,136 @@ __global__ void uv_texture_compose_kernel(float *__restrict__ syn, const float *
     }
 }
 
+
+// ------------------------------------------------------------------ row N1: HandRecoveryFlow tail in one pass
+// models/trainer.py:66-145 for the whole batch: everything the generator consumes, straight from the two face-index maps.
+// One thread per (sample, pixel).  The erosions (utils/util.py:142-153: pad value 1, ks x ks window sum == ks^2) are evaluated
+// from the face-index map itself, so no intermediate mask tensor is written and read back.
+struct CondSide {
+    const int32_t *fim;       // (B,is,is)
+    const float *render;      // (B,3,is,is) UV re-rendering at this pose (stage R8)
+    float *obj_inputs, *obj_conds, *hand_inputs, *hand_conds, *mask_bg, *mask_hand;
+};
+struct CondArgs {
+    CondSide side[2];         // 0 = src, 1 = ref/tsf
+    const float *src_img;     // (B,3,is,is)
+    const float *src_faces;   // (B,F,3,3)
+    const float *wim_ref;     // (B,is,is,3)
+    const float *map_fn, *sem_full;
+    float *bg_inputs, *T;
+    int B, F, is, n_hand, bg_ks;
+};
+
+// value of the erosion inputs at (y, x) of one face-index map; outside the image util.morph pads with 1
+__device__ __forceinline__ void mask_values(const CondArgs &a, const int32_t *fim, int y, int x, float &bg, float &not_hand)
+{
+    if (y < 0 || y >= a.is || x < 0 || x >= a.is) { bg = 1.f; not_hand = 1.f; return; }
+    const int f = fim[y * a.is + x];
+    bg = a.map_fn[(size_t)(f < 0 ? a.F : f) * 3 + 2];
+    not_hand = 1.f - ((f != -1 && f < a.n_hand) ? 1.f : 0.f);
+}
+
+constexpr int CT_W = 32, CT_H = 8, CT_R = 7;       // tile and the largest supported erosion radius (ks <= 15)
+
+// 2-D tiles: the erosion inputs of a tile and its halo are gathered once into shared memory (face index -> table lookups are
+// the expensive part), the 15 x 15 erosion is evaluated separably (row sums, then column sums).
+__global__ void __launch_bounds__(CT_W * CT_H) condition_inputs_kernel(const CondArgs a)
+{
+    __shared__ float s_bg[2][CT_H + 2 * CT_R][CT_W + 2 * CT_R];    // [side]: background channel of cond (side 1 only needs halo 1)
+    __shared__ float s_nh[2][CT_H + 2][CT_W + 2];                  // not_hand, halo 1
+    __shared__ float s_row[CT_H + 2 * CT_R][CT_W];                 // horizontal sums of the source background window
+    const int hw = a.is * a.is;
+    const int b = blockIdx.z, x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * CT_W + tx;
+    const int r = a.bg_ks / 2;
+    const int32_t *fim_s = a.side[0].fim + (size_t)b * hw, *fim_r = a.side[1].fim + (size_t)b * hw;
+    for (int i = tid; i < (CT_H + 2 * CT_R) * (CT_W + 2 * CT_R); i += CT_W * CT_H) {
+        const int yy = i / (CT_W + 2 * CT_R), xx = i % (CT_W + 2 * CT_R);
+        float bg, nh;
+        mask_values(a, fim_s, y0 + yy - CT_R, x0 + xx - CT_R, bg, nh);
+        s_bg[0][yy][xx] = bg;
+        const int hy = yy - (CT_R - 1), hx = xx - (CT_R - 1);                       // position inside the halo-1 tiles
+        if (hy >= 0 && hy < CT_H + 2 && hx >= 0 && hx < CT_W + 2) {
+            s_nh[0][hy][hx] = nh;
+            mask_values(a, fim_r, y0 + yy - CT_R, x0 + xx - CT_R, bg, nh);
+            s_bg[1][yy][xx] = bg;
+            s_nh[1][hy][hx] = nh;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < (CT_H + 2 * CT_R) * CT_W; i += CT_W * CT_H) {              // row sums over [x - r, x + r]
+        const int yy = i / CT_W, xx = i % CT_W;
+        float sacc = 0.f;
+        for (int dx = -r; dx <= r; ++dx) sacc += s_bg[0][yy][xx + CT_R + dx];
+        s_row[yy][xx] = sacc;
+    }
+    __syncthreads();
+    const int x = x0 + tx, y = y0 + ty;
+    if (x >= a.is || y >= a.is) return;
+    const int p = y * a.is + x;
+    const int64_t i = (int64_t)b * hw + p;
+    float bgm;
+    {
+        float sacc = 0.f;
+        for (int dy = -r; dy <= r; ++dy) sacc += s_row[ty + CT_R + dy][tx];
+        bgm = sacc == (float)(a.bg_ks * a.bg_ks) ? 1.f : 0.f;
+    }
+    float m_hand_ref = 0.f;
+#pragma unroll
+    for (int sd = 0; sd < 2; ++sd) {
+        const CondSide &S = a.side[sd];
+        const int f = (sd == 0 ? fim_s : fim_r)[p];
+        const int row = f < 0 ? a.F : f;
+        const float c0 = a.map_fn[(size_t)row * 3], c1 = a.map_fn[(size_t)row * 3 + 1], c2 = a.map_fn[(size_t)row * 3 + 2];
+        const float sem = a.sem_full[row];
+        // erode3 of not_hand and of the background channel of cond (trainer.py:72,109-110)
+        float s_hand = 0.f, s_bgsum = 0.f;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                s_hand += s_nh[sd][ty + 1 + dy][tx + 1 + dx];
+                s_bgsum += s_bg[sd][ty + CT_R + dy][tx + CT_R + dx];
+            }
+        const float m_hand = s_hand == 9.f ? 1.f : 0.f, m_bg = s_bgsum == 9.f ? 1.f : 0.f;
+        if (sd == 1) m_hand_ref = m_hand;
+        const float hm = c0 < 1.5f ? 1.f : 0.f, om = c0 > 1.5f ? 1.f : 0.f;           // trainer.py:112-124
+        const size_t p3 = (size_t)b * 3 * hw + p, p12 = (size_t)b * 12 * hw + p;
+        S.hand_conds[p3] = hm * c0; S.hand_conds[p3 + hw] = hm * c1; S.hand_conds[p3 + 2 * (size_t)hw] = c2 + 1.f - hm;
+        S.obj_conds[p12] = om * c0; S.obj_conds[p12 + hw] = om * c1; S.obj_conds[p12 + 2 * (size_t)hw] = c2 + 1.f - om;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) S.obj_conds[p12 + (size_t)(3 + c) * hw] = (sem == (float)(c + 7)) ? 1.f : 0.f;   // seg[:, 6:]
+        const float *hand_rgb = sd == 0 ? a.src_img : S.render;                       // trainer.py:128 vs 132
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            S.obj_inputs[p3 + (size_t)c * hw] = S.render[p3 + (size_t)c * hw] * (m_hand - m_bg);        // trainer.py:127,131
+            S.hand_inputs[p3 + (size_t)c * hw] = hand_rgb[p3 + (size_t)c * hw] * (1.f - m_hand);
+        }
+        S.mask_bg[i] = m_bg;
+        S.mask_hand[i] = m_hand;
+    }
+    // bg_inputs = [src_img * erode_ks(cond_src[:, -1:]), erode_ks(...)]   (trainer.py:135-136, ks = 15)
+    {
+        const size_t p3 = (size_t)b * 3 * hw + p, p4 = (size_t)b * 4 * hw + p;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a.bg_inputs[p4 + (size_t)c * hw] = a.src_img[p3 + (size_t)c * hw] * bgm;
+        a.bg_inputs[p4 + 3 * (size_t)hw] = bgm;
+    }
+    // T = cal_bc_transform (nmr.py:874-925), masked to the hand region of the target pose (trainer.py:80-81)
+    {
+        const int f = fim_r[p];
+        float tx_ = -2.f, ty_ = -2.f;
+        if (f != -1 && m_hand_ref != 1.f) {
+            const float *fv = a.src_faces + ((size_t)b * a.F + f) * 9;
+            const float w0 = a.wim_ref[3 * i], w1 = a.wim_ref[3 * i + 1], w2 = a.wim_ref[3 * i + 2];
+            tx_ = __fadd_rn(__fadd_rn(__fmul_rn(fv[0], w0), __fmul_rn(fv[3], w1)), __fmul_rn(fv[6], w2));
+            ty_ = __fadd_rn(__fadd_rn(__fmul_rn(-fv[1], w0), __fmul_rn(-fv[4], w1)), __fmul_rn(-fv[7], w2));
+        }
+        a.T[2 * i] = tx_;
+        a.T[2 * i + 1] = ty_;
+    }
+}
+
 }  // namespace hoig
 
 using namespace hoig;
@@ -788,4 +918,26 @@ extern "C" int hoig_uv_texture_compose(float *syn, const float *O, const float *
     if (n == 0) return HOIG_OK;
     uv_texture_compose_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(syn, O, preload, B, C, Hu, Wu, x0);
     return check_launch("uv_texture_compose_kernel");
+}
+
+extern "C" int hoig_condition_inputs(const hoigCondInputsDesc *d, hoigStream_t stream)
+{
+    HOIG_REQUIRE(d, "condition_inputs: null descriptor");
+    HOIG_REQUIRE(d->fim_src && d->fim_ref && d->wim_ref && d->src_faces && d->src_img && d->render_src && d->render_ref && d->map_fn &&
+                     d->sem_full, "condition_inputs: null input");
+    HOIG_REQUIRE(d->bg_inputs && d->src_obj_inputs && d->src_obj_conds && d->src_hand_inputs && d->src_hand_conds && d->tsf_obj_inputs &&
+                     d->tsf_obj_conds && d->tsf_hand_inputs && d->tsf_hand_conds && d->T && d->src_mask_bg && d->ref_mask_bg &&
+                     d->src_mask_hand && d->ref_mask_hand, "condition_inputs: null output");
+    HOIG_REQUIRE(d->B >= 0 && d->F > 0 && d->image_size > 0 && d->bg_erode_ks >= 1 && (d->bg_erode_ks & 1), "condition_inputs: bad shape");
+    CondArgs a;
+    a.side[0] = {d->fim_src, d->render_src, d->src_obj_inputs, d->src_obj_conds, d->src_hand_inputs, d->src_hand_conds, d->src_mask_bg, d->src_mask_hand};
+    a.side[1] = {d->fim_ref, d->render_ref, d->tsf_obj_inputs, d->tsf_obj_conds, d->tsf_hand_inputs, d->tsf_hand_conds, d->ref_mask_bg, d->ref_mask_hand};
+    a.src_img = d->src_img; a.src_faces = d->src_faces; a.wim_ref = d->wim_ref; a.map_fn = d->map_fn; a.sem_full = d->sem_full;
+    a.bg_inputs = d->bg_inputs; a.T = d->T;
+    a.B = d->B; a.F = d->F; a.is = d->image_size; a.n_hand = d->n_hand_faces; a.bg_ks = d->bg_erode_ks;
+    HOIG_REQUIRE(d->bg_erode_ks <= 2 * CT_R + 1, "condition_inputs: erosion size %d not supported (<= %d)", d->bg_erode_ks, 2 * CT_R + 1);
+    if (d->B == 0) return HOIG_OK;
+    const dim3 grid((unsigned)ceil_div(d->image_size, CT_W), (unsigned)ceil_div(d->image_size, CT_H), (unsigned)d->B);
+    condition_inputs_kernel<<<grid, dim3(CT_W, CT_H), 0, as_stream(stream)>>>(a);
+    return check_launch("condition_inputs_kernel");
 }

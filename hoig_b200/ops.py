@@ -118,6 +118,35 @@ def erode(mask: torch.Tensor, ks: int) -> torch.Tensor:
     return out
 
 
+def condition_inputs(src_img, src_faces, fim_src, fim_ref, wim_ref, map_fn, sem_full, render_src, render_ref,
+                     n_hand_faces: int, bg_erode_ks: int = 15):
+    """``hoig_condition_inputs``: every Generator.forward input and the four masks in one launch (models/trainer.py:66-145)."""
+    B, H, _ = fim_src.shape
+    F = map_fn.shape[0] - 1
+    dev = fim_src.device
+    for t in (fim_src, fim_ref):
+        if t.dtype != torch.int32 or not t.is_contiguous():
+            raise ValueError("condition_inputs: face-index maps must be contiguous int32")
+
+    def new(c):
+        return torch.empty(B, c, H, H, dtype=torch.float32, device=dev)
+
+    out = dict(bg_inputs=new(4), src_obj_inputs=new(3), src_obj_conds=new(12), src_hand_inputs=new(3), src_hand_conds=new(3),
+               tsf_obj_inputs=new(3), tsf_obj_conds=new(12), tsf_hand_inputs=new(3), tsf_hand_conds=new(3),
+               T=torch.empty(B, H, H, 2, dtype=torch.float32, device=dev))
+    masks = dict(src_mask_bg=new(1), ref_mask_bg=new(1), src_mask_hand=new(1), ref_mask_hand=new(1))
+    d = _lib.CondInputsDesc()
+    d.fim_src, d.fim_ref = fim_src.data_ptr(), fim_ref.data_ptr()
+    d.wim_ref, d.src_faces, d.src_img = _f32c(wim_ref, "wim_ref"), _f32c(src_faces, "src_faces"), _f32c(src_img, "src_img")
+    d.render_src, d.render_ref = _f32c(render_src, "render_src"), _f32c(render_ref, "render_ref")
+    d.map_fn, d.sem_full = _f32c(map_fn, "map_fn"), _f32c(sem_full.reshape(-1), "sem_full")
+    for k, v in {**out, **masks}.items():
+        setattr(d, k, v.data_ptr())
+    d.B, d.F, d.image_size, d.n_hand_faces, d.bg_erode_ks = B, F, H, n_hand_faces, bg_erode_ks
+    _lib.check(_lib.lib().hoig_condition_inputs(ctypes.byref(d), _stream()), "condition_inputs")
+    return out, masks
+
+
 def uv_backward_warp(src_faces: torch.Tensor, fim_uv: torch.Tensor, wim_uv: torch.Tensor, src_fim: torch.Tensor):
     """utils/nmr.py:973-1040: (T (B,Hu,Wu,2), O (B,1,Hu,Wu)) of the atlas pixels, see ``hoig_uv_backward_warp``."""
     B, F = src_faces.shape[:2]

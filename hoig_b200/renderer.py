@@ -35,6 +35,15 @@ def render_fim_wim_batched(cam: torch.Tensor, vertices: torch.Tensor, faces_idx:
     return faces, fim, wim
 
 
+def condition_inputs_fused(src_img, faces_src, fim_src, fim_ref, wim_ref, map_fn, sem_full, render_img_src=None,
+                           render_img_ref=None, n_hand_faces: int = N_HAND_FACES):
+    """Same result as :func:`condition_inputs` from ONE kernel launch (``hoig_condition_inputs``, row N1 of SURVEY 8f)."""
+    r_src = src_img if render_img_src is None else render_img_src
+    r_ref = src_img if render_img_ref is None else render_img_ref
+    return ops.condition_inputs(src_img.contiguous(), faces_src, fim_src, fim_ref, wim_ref, map_fn, sem_full, r_src.contiguous(),
+                                r_ref.contiguous(), n_hand_faces)
+
+
 def condition_inputs(src_img, faces_src, fim_src, fim_ref, wim_ref, map_fn, sem_full, render_img_src=None,
                      render_img_ref=None, n_hand_faces: int = N_HAND_FACES):
     """Batched ``HandRecoveryFlow.forward`` tail (models/trainer.py:66-145) given the rasterizer outputs.

@@ -89,6 +89,24 @@ int hoig_bc_transform(const float *src_faces, const int32_t *fim_ref, const floa
 /* R6 utils/util.py:142-153 erode (pad value 1, all-ones ks x ks window). in/out (B,1,H,W) f32. */
 int hoig_erode(const float *in, float *out, int B, int H, int W, int ks, hoigStream_t stream);
 
+/* ---- row N1: the tail of HandRecoveryFlow.forward (models/trainer.py:66-145) for the whole batch in ONE launch: condition
+ * tables, one-hot segmentation, hand / background masks (3x3 erosions, the 15x15 erosion of the source background), the dense
+ * correspondence T masked to the target hand region, and the assembly of every Generator.forward input.  All tensors NCHW f32
+ * unless noted; the 1 + 8 erosion windows are evaluated from the face-index maps, nothing intermediate touches memory.
+ *   in : fim_src, fim_ref (B,is,is) int32; wim_ref (B,is,is,3); src_faces (B,F,3,3) (hoig_project_faces); src_img (B,3,is,is);
+ *        render_src / render_ref (B,3,is,is) (stage R8); map_fn (F+1,3), sem_full (F+1) with the background row last.
+ *   out: bg_inputs (B,4), {src,tsf}_obj_inputs (B,3), {src,tsf}_obj_conds (B,12), {src,tsf}_hand_inputs (B,3),
+ *        {src,tsf}_hand_conds (B,3), T (B,is,is,2), {src,ref}_mask_bg, {src,ref}_mask_hand (B,1). */
+typedef struct hoigCondInputsDesc {
+    const int32_t *fim_src, *fim_ref;
+    const float *wim_ref, *src_faces, *src_img, *render_src, *render_ref, *map_fn, *sem_full;
+    float *bg_inputs, *src_obj_inputs, *src_obj_conds, *src_hand_inputs, *src_hand_conds;
+    float *tsf_obj_inputs, *tsf_obj_conds, *tsf_hand_inputs, *tsf_hand_conds, *T;
+    float *src_mask_bg, *ref_mask_bg, *src_mask_hand, *ref_mask_hand;
+    int B, F, image_size, n_hand_faces, bg_erode_ks;
+} hoigCondInputsDesc;
+int hoig_condition_inputs(const hoigCondInputsDesc *desc, hoigStream_t stream);
+
 /* ---- stage R8: UV-texture warp (utils/nmr.py:973-1100, models/trainer.py:83-87)
  * hoig_uv_backward_warp: nmr.py:973-1040.  For every atlas pixel p with fim_uv[p] != -1 (fim_uv (Hu,Wu) int32, wim_uv (Hu,Wu,3),
  * shared by the batch):  T[b,p] = sum_k src_faces[b][fim_uv[p]][k].xy (y negated, trainer.py:67-68) * wim_uv[p][k], else -2;

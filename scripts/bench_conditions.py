@@ -75,8 +75,8 @@ def main():
                     lambda: renderer.texture_backward_warp(src_img, fs, fim_s, fim_uv, wim_uv, obj_tex))
         r_ref = timed("R8 re-render (ref pose)", lambda: renderer.render_from_texture(tex, fim_r, wim_r, coord))
         r_src = timed("R8 re-render (src pose)", lambda: renderer.render_from_texture(tex, fim_s, wim_s, coord))
-        return timed("R4-R7 condition maps, masks, T, input assembly",
-                     lambda: renderer.condition_inputs(src_img, fs, fim_s, fim_r, wim_r, map_fn, sem, r_src, r_ref))
+        return timed("R4-R7 condition maps, masks, T, input assembly (one launch)",
+                     lambda: renderer.condition_inputs_fused(src_img, fs, fim_s, fim_r, wim_r, map_fn, sem, r_src, r_ref))
 
     for _ in range(3):
         step()

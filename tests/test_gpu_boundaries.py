@@ -72,3 +72,26 @@ def test_batched_condition_inputs_match_oracle():
     assert torch.allclose(inp["bg_inputs"].cpu(), torch.cat([src_img.cpu() * bgm, bgm], 1))
     assert inp["src_obj_inputs"].shape == (B, 3, 256, 256) and inp["src_obj_conds"].shape == (B, 12, 256, 256)
     assert inp["src_hand_inputs"].shape == (B, 3, 256, 256) and inp["T"].shape == (B, 256, 256, 2)
+
+
+def test_fused_condition_inputs_equal_the_stepwise_glue():
+    """Row N1: ``hoig_condition_inputs`` (one launch) reproduces ``renderer.condition_inputs`` (C-ABI kernels + torch glue, gated
+    against the oracle above) bit for bit, with distinct re-rendered images on both sides."""
+    B = 3
+    sc = synth.make_scene(B, seed=7, obj_faces=3000)
+    nv = sc.n_verts
+    cam, fidx = sc.cam.cuda(), sc.faces_idx.cuda()
+    faces_s, fim_s, wim_s = renderer.render_fim_wim_batched(cam, sc.verts_src[:, :nv].contiguous().cuda(), fidx)
+    faces_r, fim_r, wim_r = renderer.render_fim_wim_batched(cam, sc.verts_ref[:, :nv].contiguous().cuda(), fidx)
+    g = torch.Generator().manual_seed(3)
+    src_img, r_src, r_ref = [(torch.rand(B, 3, 256, 256, generator=g) * 2 - 1).cuda() for _ in range(3)]
+    args = (src_img, faces_s, fim_s, fim_r, wim_r, sc.map_fn.cuda(), sc.sem_full.cuda(), r_src, r_ref)
+    a, ma = renderer.condition_inputs(*args)
+    b, mb = renderer.condition_inputs_fused(*args)
+    torch.cuda.synchronize()
+    assert set(a) == set(b) and set(ma) == set(mb)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    for k in ma:
+        assert torch.equal(ma[k], mb[k]), k
+    assert 0 < mb["ref_mask_hand"].mean().item() < 1 and (b["T"][..., 0] > -1.5).any()
