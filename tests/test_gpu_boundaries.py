@@ -95,3 +95,36 @@ def test_fused_condition_inputs_equal_the_stepwise_glue():
     for k in ma:
         assert torch.equal(ma[k], mb[k]), k
     assert 0 < mb["ref_mask_hand"].mean().item() < 1 and (b["T"][..., 0] > -1.5).any()
+
+
+def test_meshes_to_image_end_to_end():
+    """The whole hot path on device: meshes + source image -> condition stage (R0-R8, N1) -> generator -> composite.  Checks the
+    plumbing between the stages (shapes, dtypes, value ranges, no NaN), each stage being gated against its oracle elsewhere."""
+    from hoig_b200.generator import composite, create
+    B = 2
+    sc = synth.make_scene(B, seed=11, obj_faces=3000)
+    nv = sc.n_verts
+    cam, fidx = sc.cam.cuda(), sc.faces_idx.cuda()
+    faces_s, fim_s, wim_s = renderer.render_fim_wim_batched(cam, sc.verts_src[:, :nv].contiguous().cuda(), fidx)
+    _, fim_r, wim_r = renderer.render_fim_wim_batched(cam, sc.verts_ref[:, :nv].contiguous().cuda(), fidx)
+    g = torch.Generator().manual_seed(0)
+    src_img = (torch.rand(B, 3, 256, 256, generator=g) * 2 - 1).cuda()
+    F = fidx.shape[0]
+    fim_uv = torch.randint(-1, F, (256, 640), generator=g, dtype=torch.int32).cuda()
+    w = torch.rand(256, 640, 3, generator=g) + 0.05
+    wim_uv = (w / w.sum(-1, keepdim=True)).cuda()
+    uv_coord = (torch.rand(F, 3, 2, generator=g) * 2 - 1).cuda()
+    tex = renderer.texture_backward_warp(src_img, faces_s, fim_s, fim_uv, wim_uv, torch.rand(256, 256, 3, generator=g).cuda())
+    r_src = renderer.render_from_texture(tex, fim_s, wim_s, uv_coord)
+    r_ref = renderer.render_from_texture(tex, fim_r, wim_r, uv_coord)
+    inputs, masks = renderer.condition_inputs_fused(src_img, faces_s, fim_s, fim_r, wim_r, sc.map_fn.cuda(), sc.sem_full.cuda(), r_src, r_ref)
+    net = create("generator_spade_attn", dtype=torch.float16, bg_dim=8, img_dim=3, obj_dim=3, img_cond_dim=3, obj_cond_dim=12,
+                 conv_dim=16, repeat_num=2)
+    net.init_weights()
+    net = net.cuda().eval()
+    outs = net(**inputs, src_armask=torch.zeros(B, 1, 256, 256).cuda(), tsf_armask=torch.zeros(B, 1, 256, 256).cuda())
+    img = composite(outs[1], outs[6], outs[7], outs[8], outs[9])
+    torch.cuda.synchronize()
+    assert img.shape == (B, 3, 256, 256) and torch.isfinite(img).all()
+    assert img.abs().max().item() <= 1.0 + 1e-5            # tanh images blended by sigmoid masks
+    assert all(torch.isfinite(o).all() for o in outs)
