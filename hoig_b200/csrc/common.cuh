@@ -38,7 +38,12 @@ template <> struct DT<__nv_bfloat16> {
 
 template <> struct DT<__half> {
     static __device__ __forceinline__ float ld(const __half *p) { return __half2float(*p); }
-    static __device__ __forceinline__ void st(__half *p, float v) { *p = __float2half_rn(v); }
+    static __device__ __forceinline__ void st(__half *p, float v)
+    {
+        unsigned short r;
+        asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+        *reinterpret_cast<unsigned short *>(p) = r;
+    }
 };
 
 // two 16-bit storage values <-> two floats
@@ -48,10 +53,13 @@ template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, f
     __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&t);
 }
+// fp16 storage saturates at +-65504 instead of overflowing to inf (one F2FP.SATFINITE either way): an out-of-range activation
+// then stays finite through the following normalisation instead of turning a whole plane into NaN
 template <> __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi)
 {
-    __half2 t = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t *>(&t);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 template <typename T> __device__ __forceinline__ void unpack2(uint32_t w, float &lo, float &hi);
 template <> __device__ __forceinline__ void unpack2<__nv_bfloat16>(uint32_t w, float &lo, float &hi)

@@ -191,6 +191,15 @@ def test_seg_unfold3_matches_contract(dtype, C, hi, ho):
     assert torch.equal(a.cpu(), b)
 
 
+def test_fp16_storage_saturates_instead_of_overflowing():
+    """Values beyond the fp16 range are stored as +-65504, not inf (layout kernel and conv epilogue share the conversion)."""
+    x = torch.tensor([1e6, -1e6, 3.0, 70000.0, -65504.0, 0.5, 1e38, -1e38]).view(1, 8, 1, 1)
+    out = ops.nchw_to_nhwc(x.cuda(), torch.empty(1, 1, 1, 8, dtype=torch.float16, device="cuda"))
+    got = out.cpu().float().view(-1)
+    assert torch.isfinite(got).all()
+    assert got.tolist() == [65504.0, -65504.0, 3.0, 65504.0, -65504.0, 0.5, 65504.0, -65504.0]
+
+
 # --------------------------------------------------------------------------- convolution
 CONV_CASES = [
     # name, N, H, Cin, Cout, k, stride, mode, extras
