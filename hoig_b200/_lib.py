@@ -91,6 +91,8 @@ _SIGNATURES = {
                                  c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_void_p]),
     "hoig_attn_unfold": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                  c_int, c_int, c_void_p]),
+    "hoig_block_extract_backward_f32": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
+    "hoig_local_attn_reshape_backward_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "hoig_condition_inputs": (c_int, [POINTER(CondInputsDesc), c_void_p]),
     "hoig_uv_backward_warp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "hoig_sample_texture_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

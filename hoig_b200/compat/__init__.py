@@ -30,7 +30,8 @@ class block_extractor_cuda:  # noqa: N801 - mirrors the extension module name
 
     @staticmethod
     def backward(source, flow_field, grad_output, grad_source, grad_flow_field, kernel_size):
-        raise NotImplementedError("hoig_b200: BlockExtractor backward is a training ('next') row, SURVEY.md 8f N3")
+        ops.block_extract_backward(source, flow_field, grad_output, grad_source, grad_flow_field, kernel_size)
+        return 1
 
 
 class local_attn_reshape_cuda:  # noqa: N801
@@ -43,7 +44,8 @@ class local_attn_reshape_cuda:  # noqa: N801
 
     @staticmethod
     def backward(inputs, grad_output, grad_inputs, kernel_size):
-        raise NotImplementedError("hoig_b200: LocalAttnReshape backward is a training ('next') row, SURVEY.md 8f N3")
+        ops.local_attn_reshape_backward(grad_output, grad_inputs, kernel_size)
+        return 1
 
 
 class rasterize:  # noqa: N801

@@ -455,6 +455,71 @@ __global__ void local_attn_reshape_kernel(const float *__restrict__ in, float *_
     out[i] = in[(((int64_t)b * k * k + (y % k) * k + x % k) * H + y / k) * W + x / k];
 }
 
+// ---------------------------------------------------------------- backward of the two reference ops (boundary B2, row N3)
+// block_extractor_kernel.cu:86-166.  Source gradient: one thread per output element scatters to its four taps (atomicAdd, as
+// the reference).  Flow gradient: the reference issues 2 atomics per output element onto the same (b, yf, xf) cell, C*k*k
+// colliding updates per cell; here one warp owns a cell, accumulates over channels and taps in registers and writes once.
+__global__ void block_extract_bwd_src_kernel(const float *__restrict__ flow, const float *__restrict__ gout, float *__restrict__ gsrc,
+                                             int64_t n, int C, int Hs, int Ws, int Hf, int Wf, int k)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int Wo = k * Wf, Ho = k * Hf;
+    const int x = (int)(i % Wo), y = (int)((i / Wo) % Ho);
+    const int c = (int)((i / ((int64_t)Wo * Ho)) % C), b = (int)(i / ((int64_t)Wo * Ho * C));
+    const int yf = y / k, xf = x / k;
+    const float fx = flow[(((int64_t)b * 2 + 0) * Hf + yf) * Wf + xf];
+    const float fy = flow[(((int64_t)b * 2 + 1) * Hf + yf) * Wf + xf];
+    const BETap t = be_tap(fx, fy, yf, xf, y % k, x % k, k, Hs, Ws);
+    float *gs = gsrc + ((int64_t)b * C + c) * Hs * Ws;
+    const float g = gout[i];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) atomicAdd(gs + t.idx[q], g * t.w[q]);   // w = xP * yP, :152-155
+}
+
+__global__ void __launch_bounds__(128)
+block_extract_bwd_flow_kernel(const float *__restrict__ src, const float *__restrict__ flow, const float *__restrict__ gout,
+                              float *__restrict__ gflow, int64_t ncells, int C, int Hs, int Ws, int Hf, int Wf, int k)
+{
+    const int lane = threadIdx.x % 32;
+    const int64_t cell = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+    if (cell >= ncells) return;                       // whole warp exits together
+    const int xf = (int)(cell % Wf), yf = (int)((cell / Wf) % Hf), b = (int)(cell / ((int64_t)Wf * Hf));
+    const int Wo = k * Wf, Ho = k * Hf;
+    const float fx = flow[(((int64_t)b * 2 + 0) * Hf + yf) * Wf + xf];
+    const float fy = flow[(((int64_t)b * 2 + 1) * Hf + yf) * Wf + xf];
+    float gx = 0.f, gy = 0.f;
+    for (int j = lane; j < C * k * k; j += 32) {
+        const int c = j / (k * k), tap = j % (k * k), ky = tap / k, kx = tap % k;
+        const float dy = __fadd_rn(__fadd_rn(fy, (float)(ky - k / 2)), (float)yf), dx = __fadd_rn(__fadd_rn(fx, (float)(kx - k / 2)), (float)xf);
+        const float fdx = floorf(dx), fdy = floorf(dy);
+        const int xL = max(min((int)fdx, Ws - 1), 0), xR = max(min((int)(fdx + 1.f), Ws - 1), 0);
+        const int yT = max(min((int)fdy, Hs - 1), 0), yB = max(min((int)(fdy + 1.f), Hs - 1), 0);
+        const float xLp = 1.f - (dx - fdx), xRp = dx - fdx, yTp = 1.f - (dy - fdy), yBp = dy - fdy;
+        const float *s = src + ((int64_t)b * C + c) * Hs * Ws;
+        const float vLT = s[yT * Ws + xL], vRT = s[yT * Ws + xR], vLB = s[yB * Ws + xL], vRB = s[yB * Ws + xR];
+        const float g = gout[(((int64_t)b * C + c) * Ho + yf * k + ky) * Wo + xf * k + kx];
+        gy += g * (-xLp * vLT - xRp * vRT + xLp * vLB + xRp * vRB);       // :157
+        gx += g * (-yTp * vLT - yBp * vLB + yTp * vRT + yBp * vRB);       // :158
+    }
+    gx = warp_sum(gx);
+    gy = warp_sum(gy);
+    if (lane == 0) {
+        gflow[(((int64_t)b * 2 + 0) * Hf + yf) * Wf + xf] += gx;
+        gflow[(((int64_t)b * 2 + 1) * Hf + yf) * Wf + xf] += gy;
+    }
+}
+
+// local_attn_reshape_kernel.cu:62-104: the forward is a permutation, so is the backward (no atomics needed)
+__global__ void local_attn_reshape_bwd_kernel(const float *__restrict__ gout, float *__restrict__ gin, int64_t n, int k, int H, int W)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int Wo = k * W, Ho = k * H;
+    const int x = (int)(i % Wo), y = (int)((i / Wo) % Ho), b = (int)(i / ((int64_t)Wo * Ho));
+    gin[(((int64_t)b * k * k + (y % k) * k + x % k) * H + y / k) * W + x / k] += gout[i];
+}
+
 // extract_attn.py:24-25 materialised for the tensor-core path: U[pix][t*2C + c] = BlockExtractor(tgt, 0) tap t
 // for c < C and BlockExtractor(src, flow) tap t for c >= C (block_extractor_kernel.cu:52-84, same float op
 // order as the fused gather), so the k x k stride-k conv over cat[block_target, block_source] becomes a plain
@@ -1095,4 +1160,25 @@ extern "C" int hoig_seg_unfold3(const float *seg, int B, int C, int Hi, int Wi, 
             seg_unfold3_kernel<T><<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>(seg, B, C, Hi, Wi, (T *)dst, ldd, Kpad, Ho, Wo);
         return check_launch("seg_unfold3_kernel");
     });
+}
+
+extern "C" int hoig_block_extract_backward_f32(const float *source, const float *flow, const float *grad_out, float *grad_source,
+                                               float *grad_flow, int B, int C, int Hs, int Ws, int Hf, int Wf, int k, hoigStream_t stream)
+{
+    HOIG_REQUIRE(source && flow && grad_out && grad_source && grad_flow && k >= 1, "block_extract_backward: bad argument");
+    const int64_t n = (int64_t)B * C * k * Hf * k * Wf, ncells = (int64_t)B * Hf * Wf;
+    if (n == 0) return HOIG_OK;
+    block_extract_bwd_src_kernel<<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>(flow, grad_out, grad_source, n, C, Hs, Ws, Hf, Wf, k);
+    block_extract_bwd_flow_kernel<<<ceil_div(ncells * 32, 128), 128, 0, as_stream(stream)>>>(source, flow, grad_out, grad_flow, ncells, C, Hs, Ws,
+                                                                                          Hf, Wf, k);
+    return check_launch("block_extract_backward");
+}
+
+extern "C" int hoig_local_attn_reshape_backward_f32(const float *grad_out, float *grad_in, int B, int k, int H, int W, hoigStream_t stream)
+{
+    HOIG_REQUIRE(grad_out && grad_in && k >= 1, "local_attn_reshape_backward: bad argument");
+    const int64_t n = (int64_t)B * k * H * k * W;
+    if (n == 0) return HOIG_OK;
+    local_attn_reshape_bwd_kernel<<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>(grad_out, grad_in, n, k, H, W);
+    return check_launch("local_attn_reshape_bwd_kernel");
 }

@@ -205,6 +205,27 @@ def block_extract(source: torch.Tensor, flow: torch.Tensor, out: torch.Tensor, k
     return out
 
 
+def block_extract_backward(source, flow, grad_out, grad_source, grad_flow, k: int):
+    """Adds the BlockExtractor gradients into ``grad_source`` / ``grad_flow`` (block_extractor_kernel.cu:86-166)."""
+    B, C, Hs, Ws = source.shape
+    _, two, Hf, Wf = flow.shape
+    if two != 2 or grad_out.shape != (B, C, k * Hf, k * Wf) or grad_source.shape != source.shape or grad_flow.shape != flow.shape:
+        raise ValueError("block_extract_backward: shape mismatch")
+    _lib.check(_lib.lib().hoig_block_extract_backward_f32(_f32c(source, "source"), _f32c(flow, "flow"), _f32c(grad_out, "grad_output"),
+                                                          _f32c(grad_source, "grad_source"), _f32c(grad_flow, "grad_flow_field"),
+                                                          B, C, Hs, Ws, Hf, Wf, k, _stream()), "block_extract_backward_f32")
+    return grad_source, grad_flow
+
+
+def local_attn_reshape_backward(grad_out: torch.Tensor, grad_in: torch.Tensor, k: int) -> torch.Tensor:
+    B, kk, H, W = grad_in.shape
+    if kk != k * k or grad_out.shape != (B, 1, k * H, k * W):
+        raise ValueError("local_attn_reshape_backward: shape mismatch")
+    _lib.check(_lib.lib().hoig_local_attn_reshape_backward_f32(_f32c(grad_out, "grad_output"), _f32c(grad_in, "grad_inputs"), B, k, H, W,
+                                                               _stream()), "local_attn_reshape_backward_f32")
+    return grad_in
+
+
 def local_attn_reshape(inputs: torch.Tensor, out: torch.Tensor, k: int) -> torch.Tensor:
     B, kk, H, W = inputs.shape
     if kk != k * k or out.shape != (B, 1, k * H, k * W):

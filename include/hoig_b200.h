@@ -135,6 +135,13 @@ int hoig_block_extract_f32(const float *source, const float *flow, float *out, i
 /* thirdparty/local_attn_reshape/local_attn_reshape_cuda.cc:5-13 (forward):
  *   in (B,k*k,H,W) -> out (B,1,k*H,k*W). */
 int hoig_local_attn_reshape_f32(const float *in, float *out, int B, int k, int H, int W, hoigStream_t stream);
+/* Backward of the two ops (row N3; thirdparty/block_extractor/block_extractor_cuda.cc:18-33, block_extractor_kernel.cu:86-166 and
+ * thirdparty/local_attn_reshape/local_attn_reshape_cuda.cc:17-29, local_attn_reshape_kernel.cu:62-104).  Like the reference
+ * kernels they ADD into grad_source / grad_flow / grad_in, which the reference autograd Functions pass zero-filled.
+ * grad_out (B,C,k*Hf,k*Wf) resp. (B,1,k*H,k*W); grad_source like source; grad_flow like flow; grad_in (B,k*k,H,W). */
+int hoig_block_extract_backward_f32(const float *source, const float *flow, const float *grad_out, float *grad_source,
+                                    float *grad_flow, int B, int C, int Hs, int Ws, int Hf, int Wf, int k, hoigStream_t stream);
+int hoig_local_attn_reshape_backward_f32(const float *grad_out, float *grad_in, int B, int k, int H, int W, hoigStream_t stream);
 
 /* ----------------------------------------------------------------- stage G
  * Building blocks of Generator.forward (models/networks/generator.py:347-491,

@@ -50,6 +50,10 @@ def lib() -> ctypes.CDLL:
         L.oracle_block_extract.restype = None
         L.oracle_local_attn_reshape.argtypes = [f32p, f32p] + [ctypes.c_int] * 4
         L.oracle_local_attn_reshape.restype = None
+        L.oracle_block_extract_backward.argtypes = [f32p] * 5 + [ctypes.c_int] * 7
+        L.oracle_block_extract_backward.restype = None
+        L.oracle_local_attn_reshape_backward.argtypes = [f32p, f32p] + [ctypes.c_int] * 4
+        L.oracle_local_attn_reshape_backward.restype = None
         L.oracle_num_threads.restype = ctypes.c_int
         _LIB = L
     return _LIB
@@ -84,6 +88,26 @@ def block_extract(src: np.ndarray, flow: np.ndarray, k: int) -> np.ndarray:
     out = np.empty((B, C, k * Hf, k * Wf), np.float32)
     lib().oracle_block_extract(src, flow, out, B, C, Hs, Ws, Hf, Wf, k)
     return out
+
+
+def block_extract_backward(src: np.ndarray, flow: np.ndarray, grad_out: np.ndarray, k: int):
+    """block_extractor_kernel.cu:86-166 -> (grad_src, grad_flow), starting from zeros like block_extractor.py:36-37."""
+    src = np.ascontiguousarray(src, np.float32)
+    flow = np.ascontiguousarray(flow, np.float32)
+    grad_out = np.ascontiguousarray(grad_out, np.float32)
+    B, C, Hs, Ws = src.shape
+    _, _, Hf, Wf = flow.shape
+    gs, gf = np.zeros_like(src), np.zeros_like(flow)
+    lib().oracle_block_extract_backward(src, flow, grad_out, gs, gf, B, C, Hs, Ws, Hf, Wf, k)
+    return gs, gf
+
+
+def local_attn_reshape_backward(grad_out: np.ndarray, k: int) -> np.ndarray:
+    grad_out = np.ascontiguousarray(grad_out, np.float32)
+    B, _, Ho, Wo = grad_out.shape
+    gin = np.zeros((B, k * k, Ho // k, Wo // k), np.float32)
+    lib().oracle_local_attn_reshape_backward(grad_out, gin, B, k, Ho // k, Wo // k)
+    return gin
 
 
 def local_attn_reshape(x: np.ndarray, k: int) -> np.ndarray:

@@ -234,3 +234,55 @@ void oracle_local_attn_reshape(const float *in, float *out, int B, int k, int H,
             }
 }
 
+
+/* block_extractor/block_extractor_kernel.cu:86-166 (kernel_block_extractor_backward), sequential: for every output element
+ * its gradient is scattered to the four source taps with the forward's bilinear weights, and the flow gradient of the
+ * (yf, xf) cell accumulates grad * d(sample)/d(flow) over channels and the k x k taps.  grad_src / grad_flow are ADDED to
+ * (the reference's autograd Function passes zero-filled tensors, block_extractor.py:36-37). */
+void oracle_block_extract_backward(const float *src, const float *flow, const float *gout, float *gsrc, float *gflow,
+                                   int B, int C, int Hs, int Ws, int Hf, int Wf, int k)
+{
+    const int Ho = k * Hf, Wo = k * Wf;
+    for (int b = 0; b < B; ++b)
+        for (int c = 0; c < C; ++c) {
+            const float *s = src + ((size_t)b * C + c) * Hs * Ws;
+            float *gs = gsrc + ((size_t)b * C + c) * Hs * Ws;
+            const float *go = gout + ((size_t)b * C + c) * Ho * Wo;
+            for (int y = 0; y < Ho; ++y)
+                for (int x = 0; x < Wo; ++x) {
+                    const int yf = y / k, xf = x / k;
+                    const int yo = y % k - k / 2, xo = x % k - k / 2;
+                    const float fy = flow[(((size_t)b * 2 + 1) * Hf + yf) * Wf + xf] + (float)yo;
+                    const float fx = flow[(((size_t)b * 2 + 0) * Hf + yf) * Wf + xf] + (float)xo;
+                    const float dy = fy + (float)yf, dx = fx + (float)xf;
+                    const float fdx = floorf(dx), fdy = floorf(dy);
+                    const int xL = clampi((int)fdx, 0, Ws - 1), xR = clampi((int)(fdx + 1.f), 0, Ws - 1);
+                    const int yT = clampi((int)fdy, 0, Hs - 1), yB = clampi((int)(fdy + 1.f), 0, Hs - 1);
+                    const float xLp = 1.f - (dx - fdx), xRp = dx - fdx;
+                    const float yTp = 1.f - (dy - fdy), yBp = dy - fdy;
+                    const float vLT = s[yT * Ws + xL], vRT = s[yT * Ws + xR], vLB = s[yB * Ws + xL], vRB = s[yB * Ws + xR];
+                    const float g = go[(size_t)y * Wo + x];
+                    gs[yT * Ws + xL] += g * xLp * yTp;                       /* :152-155 */
+                    gs[yT * Ws + xR] += g * xRp * yTp;
+                    gs[yB * Ws + xL] += g * xLp * yBp;
+                    gs[yB * Ws + xR] += g * xRp * yBp;
+                    const float gy = g * (-xLp * vLT - xRp * vRT + xLp * vLB + xRp * vRB);     /* :157-158 */
+                    const float gx = g * (-yTp * vLT - yBp * vLB + yTp * vRT + yBp * vRB);
+                    gflow[(((size_t)b * 2 + 1) * Hf + yf) * Wf + xf] += gy;  /* :161-162 */
+                    gflow[(((size_t)b * 2 + 0) * Hf + yf) * Wf + xf] += gx;
+                }
+        }
+}
+
+/* local_attn_reshape/local_attn_reshape_kernel.cu:62-104 (kernel_local_attn_reshape_backward): the forward is a permutation,
+ * so grad_in[b, (y%k)*k + x%k, y/k, x/k] += grad_out[b, 0, y, x]. */
+void oracle_local_attn_reshape_backward(const float *gout, float *gin, int B, int k, int H, int W)
+{
+    const int Ho = k * H, Wo = k * W;
+    for (int b = 0; b < B; ++b)
+        for (int y = 0; y < Ho; ++y)
+            for (int x = 0; x < Wo; ++x) {
+                const int ch = (y % k) * k + (x % k);
+                gin[(((size_t)b * k * k + ch) * H + y / k) * W + x / k] += gout[((size_t)b * Ho + y) * Wo + x];
+            }
+}

@@ -23,8 +23,11 @@ def test_compat_modules_follow_the_reference_calling_convention():
     out = flow.new(2, 6, 70, 50).zero_()
     assert be.forward(src, flow, out, 5) == 1
     assert torch.equal(out.cpu(), torch.from_numpy(oracle.block_extract(src.cpu().numpy(), flow.cpu().numpy(), 5)))
-    with pytest.raises(NotImplementedError):
-        be.backward(src, flow, out, src, flow, 5)
+    # block_extractor.py:34-42: backward adds into caller-provided zero-filled gradients and returns int
+    gs, gf = torch.zeros_like(src), torch.zeros_like(flow)
+    assert be.backward(src, flow, torch.ones_like(out), gs, gf, 5) == 1
+    rs, rf = oracle.block_extract_backward(src.cpu().numpy(), flow.cpu().numpy(), np.ones((2, 6, 70, 50), np.float32), 5)
+    assert np.abs(gs.cpu().numpy() - rs).max() <= 1e-3 and np.abs(gf.cpu().numpy() - rf).max() <= 1e-3
     x = torch.rand(4, 9, 14, 10, generator=g).cuda()
     o = x.new(4, 1, 42, 30).zero_()
     assert la.forward(x, o, 3) == 1

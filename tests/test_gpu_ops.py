@@ -77,6 +77,63 @@ def test_local_attn_reshape_vs_oracle_and_reference():
         assert torch.equal(o2, out)
 
 
+def test_block_extract_and_reshape_backward_vs_oracle_and_reference():
+    """Row N3 (boundary B2 backward entry points): gradients of BlockExtractor / LocalAttnReshape against the C oracle and the
+    reference's own backward kernels compiled from /root/reference (atomic summation order differs: tolerance, not bit-equality)."""
+    g = torch.Generator().manual_seed(4)
+    B, C, H, W, k = 2, 6, 14, 10, 5
+    src, flow = torch.randn(B, C, H, W, generator=g), torch.randn(B, 2, H, W, generator=g) * 3.0
+    flow[0, :, 0, 0] = torch.tensor([-40.0, 33.0])                   # taps clamped at the border
+    gout = torch.randn(B, C, k * H, k * W, generator=g)
+    gs = torch.zeros_like(src).cuda()
+    gf = torch.zeros_like(flow).cuda()
+    ops.block_extract_backward(src.cuda(), flow.cuda(), gout.cuda(), gs, gf, k)
+    rs, rf = oracle.block_extract_backward(src.numpy(), flow.numpy(), gout.numpy(), k)
+    assert np.abs(gs.cpu().numpy() - rs).max() <= 1e-4 * max(1.0, np.abs(rs).max())
+    assert np.abs(gf.cpu().numpy() - rf).max() <= 1e-4 * max(1.0, np.abs(rf).max())
+    mod = _load_ref("ref_block_extractor_cuda")
+    if mod is not None:
+        g2, f2 = torch.zeros_like(src).cuda(), torch.zeros_like(flow).cuda()
+        mod.backward(src.cuda(), flow.cuda(), gout.cuda(), g2, f2, k)
+        torch.cuda.synchronize()
+        print("block_extract backward vs reference kernel: grad_source maxabs", (g2 - gs).abs().max().item(), "grad_flow maxabs",
+              (f2 - gf).abs().max().item())
+        assert (g2 - gs).abs().max().item() <= 1e-4 * max(1.0, g2.abs().max().item())
+        assert (f2 - gf).abs().max().item() <= 1e-4 * max(1.0, f2.abs().max().item())
+    # accumulate semantics: a second call doubles the result
+    ops.block_extract_backward(src.cuda(), flow.cuda(), gout.cuda(), gs, gf, k)
+    assert np.abs(gs.cpu().numpy() - 2 * rs).max() <= 2e-4 * max(1.0, np.abs(rs).max())
+    x = torch.rand(4, 9, 14, 10)
+    go = torch.randn(4, 1, 42, 30, generator=g)
+    gi = ops.local_attn_reshape_backward(go.cuda(), torch.zeros_like(x).cuda(), 3)
+    assert np.array_equal(gi.cpu().numpy(), oracle.local_attn_reshape_backward(go.numpy(), 3))
+    mod = _load_ref("ref_local_attn_reshape_cuda")
+    if mod is not None:
+        gi2 = torch.zeros_like(x).cuda()
+        mod.backward(x.cuda(), go.cuda(), gi2, 3)
+        torch.cuda.synchronize()
+        assert torch.equal(gi2, gi)
+
+
+def test_compat_autograd_functions_run_forward_and_backward():
+    """The reference's autograd Functions (block_extractor.py:6-42, local_attn_reshape.py:6-37) call `forward` / `backward` of the
+    extension modules; the stand-ins must support both so `loss.backward()` through the unmodified wrappers works."""
+    import hoig_b200.compat as compat
+    be, lar, _ = compat.install()
+    g = torch.Generator().manual_seed(2)
+    src = torch.randn(1, 4, 8, 8, generator=g).cuda()
+    flow = (torch.randn(1, 2, 8, 8, generator=g) * 2).cuda()
+    out = torch.zeros(1, 4, 24, 24, device="cuda")
+    assert be.forward(src, flow, out, 3) == 1
+    gs, gf = torch.zeros_like(src), torch.zeros_like(flow)
+    assert be.backward(src, flow, torch.ones_like(out), gs, gf, 3) == 1
+    # d(sum of all samples)/d(source) sums the bilinear weights landing on each source pixel: total = number of samples
+    assert abs(gs.sum().item() - out.numel()) <= 1e-2
+    gi = torch.zeros(1, 9, 8, 8, device="cuda")
+    assert lar.backward(torch.zeros(1, 9, 8, 8, device="cuda"), torch.ones(1, 1, 24, 24, device="cuda"), gi, 3) == 1
+    assert torch.equal(gi, torch.ones_like(gi))
+
+
 # ------------------------------------------------------------------------ elementwise
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 def test_layout_and_norm_ops(dtype):

@@ -73,3 +73,24 @@ def test_local_attn_reshape_kat():
     assert out.shape == (1, 1, 42, 30)
     assert np.array_equal(out[0, 0, :3, :3], np.arange(9, dtype=np.float32).reshape(3, 3))
     assert np.array_equal(out, gr.local_attn_reshape(torch.from_numpy(x), 3).numpy())
+
+
+def test_oracle_block_extract_backward_matches_autograd():
+    """The C restatement of kernel_block_extractor_backward (block_extractor_kernel.cu:86-166) against torch autograd through the
+    torch restatement of the forward (whose bilinear weights are differentiable in the flow exactly the way the kernel's analytic
+    formula is), and the LocalAttnReshape backward against the autograd of pixel_shuffle."""
+    import oracle
+    g = torch.Generator().manual_seed(0)
+    B, C, H, W, k = 2, 3, 7, 6, 5
+    src = torch.randn(B, C, H, W, generator=g, dtype=torch.float64, requires_grad=True)
+    flow = (torch.randn(B, 2, H, W, generator=g, dtype=torch.float64) * 2.5).requires_grad_(True)
+    gout = torch.randn(B, C, k * H, k * W, generator=g, dtype=torch.float64)
+    out = gr.block_extract(src, flow, k)
+    out.backward(gout)
+    gs, gf = oracle.block_extract_backward(src.detach().float().numpy(), flow.detach().float().numpy(), gout.float().numpy(), k)
+    assert np.abs(gs - src.grad.numpy()).max() <= 2e-4 * max(1.0, np.abs(src.grad.numpy()).max())
+    assert np.abs(gf - flow.grad.numpy()).max() <= 2e-4 * max(1.0, np.abs(flow.grad.numpy()).max())
+    x = torch.randn(2, k * k, 4, 3, generator=g, requires_grad=True)
+    go = torch.randn(2, 1, 4 * k, 3 * k, generator=g)
+    gr.local_attn_reshape(x, k).backward(go)
+    assert np.array_equal(oracle.local_attn_reshape_backward(go.numpy(), k), x.grad.numpy())
