@@ -1,26 +1,25 @@
-// conv_umma.cu -- bf16 implicit-GEMM convolution on 5th-gen tensor cores (sm_100a).
+// conv_umma.cu -- 16-bit (bf16 / fp16) implicit-GEMM convolution on 5th-gen tensor cores (sm_100a).
 //
-// D[128 pixels][BN channels] (fp32, TMEM) += A[128][64] (bf16, smem) * W[BN][64]^T (bf16, smem)
-// per k-block, tcgen05.mma.cta_group::1.kind::f16, UMMA 128 x BN x 16, BN <= 256.
+// D[128 pixels][BN channels] (fp32, TMEM) += A[128][64] (smem) * W[BN][64]^T (smem) per k-block,
+// tcgen05.mma.kind::f16, UMMA 128 x BN x 16 (cta_group::1) or 256 x BN x 16 over a CTA pair (cta_group::2), BN <= 256.
 //
-// Persistent, warp-specialised CTA (one per SM, 448 threads):
-//   warps 0-7   epilogue (warp w: TMEM lane quadrant w % 4, 16-column chunks of parity w / 4):
-//               tcgen05.ld (next chunk in flight while the current one is finalised) -> +bias (smem)
-//               (+residual) -> activation -> bf16 -> 32-byte row-segment stores; per-plane
-//               sum / sum-of-squares (instance-norm statistics) by warp-transpose reduction.
-//               Overlaps the next tile's main loop (two TMEM accumulator stages).
-//   warps 8-11  A producers in "gather" mode: one output pixel (A row) per thread, 16-byte
-//               cp.async chunks written straight into the 128B-swizzled K-major layout the
-//               UMMA descriptor expects (zero-fill = padding); in local-attention mode the
-//               BlockExtractor bilinear taps are blended in registers and stored to smem.
-//   warp  12    TMA producer: weights (2D map, always) and, in "TMA-A" mode, the activation tile
-//               itself as one 4D box per (tap, 64 channels) of the tap's input view; out-of-bounds
-//               box rows are zero-filled by TMA == conv padding.  Stride-2 convs and the four
-//               transposed-conv phases are stride-1 problems over strided views (conv_common.cuh),
-//               so they take this path too.
-//   warp  13    TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit -> mbarriers
-//
-// smem: ring of STAGES x (A 16 KB + B BN*128 B), 1024-byte aligned for SWIZZLE_128B.
+// Persistent, warp-specialised CTA (one per SM, 640 threads), each walking a contiguous range of tiles:
+//   warps 0-15  epilogue, four groups of four warps (warp w: TMEM lane quadrant w % 4, group w / 4; the groups share the
+//               16-column chunks round-robin): tcgen05.ld (next chunk in flight while the current one is finalised) -> +bias
+//               (smem) (+residual) -> activation, or SPADE modulation of a second tensor -> 16-bit 32-byte row-segment stores;
+//               per-plane sum / sum of squares (instance-norm statistics) by warp-level MMA column sums, flushed per image.
+//               Overlaps the next tile's main loop (2 TMEM accumulator stages, 4 in dual mode).
+//   warps 8-11  double as A producers in "gather" mode (< 64 input channels, fp32-style flow gathers): one output pixel per
+//               thread, 16-byte cp.async chunks written straight into the 128B-swizzled K-major layout the UMMA descriptor
+//               expects (zero-fill = padding); in local-attention mode the BlockExtractor taps are blended in registers.
+//   warp  16    TMA producer, activations: one 4-D box per (tap, 64 channels) of the tap's input view, out-of-bounds rows
+//               zero-filled by TMA == conv padding (stride-2 convs and the transposed conv are stride-1 problems over strided
+//               views, conv_common.cuh); in row-halo mode one box of 128 + kw - 1 pixels per (kernel row, 64 channels).
+//   warp  18    TMA producer, weights (in gather mode warp 16 does this); resident-weights mode loads the matrix once.
+//   warps 17,19 TMEM allocation + tcgen05.mma issue (one elected lane each; the second only in dual mode, where two pipelines
+//               with their own ring halves and accumulator stages process alternate tiles), tcgen05.commit -> mbarriers.
+// Modes chosen per launch on the host (launch_one): tma_a, halo, bres, dual, CTA pairs; DESIGN.md 3.1 has the measurements
+// behind each.  smem: ring of `stages` x (A 16/17 KB + weight tiles), 1024-byte aligned for SWIZZLE_128B.
 #include <cuda.h>
 
 #include <string.h>
@@ -39,7 +38,7 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int A_HALO_BYTES = 17 * 1024;   // (128 + up to 7 halo pixels) x 128 B, rounded up to the 1024 B swizzle period
 constexpr int EPI_WARPS = 8, PROD_WARPS = 4;    // epilogue warp w: TMEM lane quadrant w % 4, 16-column chunks of parity w / 4
 constexpr int EPI_END = 16;                     // warps 12-15: a further epilogue group
-constexpr int TMA_WARP = 16, MMA_WARP = 17, WB_WARP = 18, MMA2_WARP = 19;   // MMA2: second issue stream (dual mode)   // WB: weight-tile TMA producer in TMA-A mode
+constexpr int TMA_WARP = 16, MMA_WARP = 17, WB_WARP = 18, MMA2_WARP = 19;   // WB: weight-tile producer (TMA-A mode), MMA2: second issue stream (dual mode)
 constexpr int THREADS = 640;
 constexpr int MAX_STAGES = 8;
 constexpr int LOOKAHEAD = 3;           // cp.async groups in flight per producer thread
