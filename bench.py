@@ -190,6 +190,22 @@ def run_ours(args):
     per_kernel = _lib.recorder.summary()
     _lib.recorder.reset(timing=False)
 
+    graph_value = None
+    if args.cuda_graph:
+        # the same step as one graph replay (forward + composite captured once for this shape)
+        run = g.graphed(dev, with_composite=True)
+        for _ in range(2):
+            run(**dev)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            run(**dev)
+        g1.record()
+        barrier()
+        (ms_graph,) = dist_utils.reduce_max([g0.elapsed_time(g1)], "cuda")
+        graph_value = dist_utils.throughput(B, world, args.steps, ms_graph)
+
     # ---- timed region 2: end to end through the public module API with host buffers ----
     # Every step copies ITS inputs host->device (pinned memory) and reads its composite back; the copies run on
     # side streams so step i+1's upload and step i-1's download overlap step i's kernels (double buffering).
@@ -262,6 +278,8 @@ def run_ours(args):
                          "flops_per_image": GFLOP_PER_IMAGE * 1e9, "traffic": _conv_traffic(B),
                          "traffic_note": "mean DRAM read+write bytes per conv launch, ncu capture under profiles/ (bf16, batch 64)"},
             "kernel_time_share": shares}
+    if graph_value is not None:
+        line["graph_value"] = graph_value
     if args.cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         times = _oracle_forward_time(1, 1, cores)
@@ -281,6 +299,8 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step (BASELINE config: 64)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16", "f32"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="also time the step as ONE captured CUDA graph (GeneratorB200.graphed) and report it as graph_value")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

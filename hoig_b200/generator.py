@@ -510,6 +510,43 @@ class GeneratorB200(nn.Module):
             h, st = self._resnet(net, i, h, st, seg, seg_cache, want_stats=nxt)
         return self._decode(net, h, cats, seg, seg_cache, final_out)
 
+    # ------------------------------------------------------------------ CUDA graph
+    @torch.no_grad()
+    def graphed(self, example_inputs: Dict[str, torch.Tensor], with_composite: bool = False, warmup: int = 2):
+        """Capture ``forward`` (and optionally the target composite, models/trainer.py:400-401) for the shapes of
+        ``example_inputs`` into one CUDA graph: ~360 kernel launches become one replay.
+
+        Returns ``run(**inputs) -> (outputs_tuple, composite_or_None)``; inputs are copied into the graph's static buffers, the
+        returned tensors are the graph's static outputs (overwritten by the next replay).  Weights are read through the packed
+        caches that exist at capture time: re-capture after ``load_state_dict`` / parameter updates.
+        """
+        static_in = {k: v.clone() for k, v in example_inputs.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                 # warm-up off the capture stream: packs weights, sets kernel attributes
+            for _ in range(max(1, warmup)):
+                o = self.forward(**static_in)
+                if with_composite:
+                    composite(o[1], o[6], o[7], o[8], o[9])
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            outs = self.forward(**static_in)
+            img = composite(outs[1], outs[6], outs[7], outs[8], outs[9]) if with_composite else None
+
+        def run(**inputs):
+            if set(inputs) != set(static_in):
+                raise ValueError("graphed generator: the captured call had inputs " + ", ".join(sorted(static_in)))
+            for k, v in inputs.items():
+                if v.shape != static_in[k].shape:
+                    raise ValueError(f"graphed generator: {k} has shape {tuple(v.shape)}, captured {tuple(static_in[k].shape)}")
+                static_in[k].copy_(v, non_blocking=True)
+            graph.replay()
+            return outs, img
+
+        run.graph = graph
+        return run
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, bg_inputs, src_obj_inputs, tsf_obj_inputs, src_hand_inputs, tsf_hand_inputs, T,

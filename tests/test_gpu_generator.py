@@ -124,3 +124,26 @@ def test_batch_slot_isolation_bf16():
     o4, o1 = g(**inp4), g(**inp1)
     for a, b in zip(o4, o1):
         assert (a[2:3] - b).abs().max().item() <= 2e-2
+
+
+def test_cuda_graph_replay_equals_eager():
+    """``GeneratorB200.graphed``: one captured graph per input shape; replays with new inputs reproduce the eager forward (the
+    per-plane statistics are summed with atomics, so allow the last-ulp differences that summation order causes)."""
+    cfg = dict(SMALL, conv_dim=64)
+    sd = gr.init_state_dict(seed=0, jitter=0.05, **cfg, **TABLE["generator_spade_attn"])
+    g = create("generator_spade_attn", dtype=torch.float16, **cfg)
+    g.load_state_dict(sd)
+    g = g.cuda().eval()
+    a = {k: v.cuda() for k, v in synth.generator_inputs(2, seed=1, size=128).items()}
+    b = {k: v.cuda() for k, v in synth.generator_inputs(2, seed=2, size=128).items()}
+    run = g.graphed(a, with_composite=True)
+    for inp in (b, a, b):
+        eager = [o.clone() for o in g(**inp)]
+        img_e = composite(eager[1], eager[6], eager[7], eager[8], eager[9]).clone()
+        outs, img = run(**inp)
+        torch.cuda.synchronize()
+        for x, y in zip(outs, eager):
+            assert (x - y).abs().max().item() <= 2e-3
+        assert (img - img_e).abs().max().item() <= 2e-3
+    with pytest.raises(ValueError):
+        run(**{k: v[:1] for k, v in a.items()})
