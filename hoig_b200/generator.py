@@ -520,7 +520,7 @@ class GeneratorB200(nn.Module):
         returned tensors are the graph's static outputs (overwritten by the next replay).  Weights are read through the packed
         caches that exist at capture time: re-capture after ``load_state_dict`` / parameter updates.
         """
-        static_in = {k: v.clone() for k, v in example_inputs.items()}
+        static_in = {k: v.clone() for k, v in example_inputs.items() if v is not None}   # optional inputs left out stay None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                 # warm-up off the capture stream: packs weights, sets kernel attributes
@@ -535,6 +535,7 @@ class GeneratorB200(nn.Module):
             img = composite(outs[1], outs[6], outs[7], outs[8], outs[9]) if with_composite else None
 
         def run(**inputs):
+            inputs = {k: v for k, v in inputs.items() if v is not None}
             if set(inputs) != set(static_in):
                 raise ValueError("graphed generator: the captured call had inputs " + ", ".join(sorted(static_in)))
             for k, v in inputs.items():
