@@ -175,6 +175,7 @@ class GeneratorB200(nn.Module):
             top, rest = name.split(".", 1)
             self._modules[top].add(rest, shape)
         self._pcache: Dict[str, tuple] = {}
+        self._ptable: Dict[str, torch.Tensor] = {}     # name -> Parameter, see _p()
         self.reset_parameters()
 
     # ------------------------------------------------------------ nn.Module API
@@ -207,11 +208,21 @@ class GeneratorB200(nn.Module):
                     prm.zero_()
 
     def _p(self, name: str) -> torch.Tensor:
-        return self.get_parameter(name)
+        # name -> Parameter lookups walk the module tree (~6 us each, ~600 per forward); Parameter objects are stable across
+        # load_state_dict / .to() (their .data is swapped in place), and _apply() drops the table in case they are not
+        try:
+            return self._ptable[name]
+        except KeyError:
+            prm = self._ptable[name] = self.get_parameter(name)
+            return prm
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.setdefault("_ptable", {}).clear()
+        return super()._apply(fn, *args, **kwargs)
 
     # packed-weight cache, keyed by parameter identity and version
     def _cached(self, key: str, params: Sequence[torch.Tensor], build):
-        sig = tuple((p.data_ptr(), p._version, str(p.device)) for p in params) + (self.compute_dtype,)
+        sig = tuple((p.data_ptr(), p._version) for p in params) + (self.compute_dtype,)   # data_ptr changes with the device
         hit = self._pcache.get(key)
         if hit is not None and hit[0] == sig:
             return hit[1]
