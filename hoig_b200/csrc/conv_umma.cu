@@ -55,7 +55,6 @@ struct UmmaParams {
     int stages;
     int tma_a;       // 1: activations by TMA boxes, 0: cp.async / register gather
     int cpt_shift;   // log2(Cin / 8) when Cin < 64 (chunk -> tap by shift), -1: generic division
-    int prefetch_tiles;  // TMA-A: L2-prefetch the activation boxes this many tile rounds ahead (0 = off)
     int tpi_shift;       // log2(tiles_per_image) when it is a power of two, else -1
     int contig;          // 1: contiguous tile range per CTA, 0: tiles strided by the grid size
     int halo;            // 1: regular kh x kw stride-1 conv whose tiles are 128 consecutive pixels of ONE image row: a stage holds one
@@ -697,7 +696,6 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
 }
 
 int g_umma_debug = 0;
-int g_prefetch_tiles = 0;   // kept for HOIG_UMMA_PREFETCH_TILES compatibility; L2 prefetch of future tiles was measured to hurt and is gone   // measured: L2 prefetch of future tiles HURTS (the streaming convs are L2->SM bandwidth bound, not latency bound)
 
 int g_contig_mode = 1;      // HOIG_UMMA_CONTIG
 int g_mma_stats = 1;        // HOIG_UMMA_MMA_STATS
@@ -783,7 +781,6 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     P.debug = g_umma_debug;
     P.tpi_shift = -1;
     if ((p.tiles_per_image & (p.tiles_per_image - 1)) == 0) { P.tpi_shift = 0; while ((1 << P.tpi_shift) < p.tiles_per_image) ++P.tpi_shift; }
-    P.prefetch_tiles = 0;
 
     CUtensorMap map_w, map_a[4];
     int st;
@@ -836,8 +833,6 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
     if (g_force_gather < 0) {
         const char *e = getenv("HOIG_UMMA_GATHER_ONLY");
         g_force_gather = (e && e[0] == '1') ? 1 : 0;
-        const char *pf = getenv("HOIG_UMMA_PREFETCH_TILES");
-        if (pf) g_prefetch_tiles = atoi(pf);
         const char *ms = getenv("HOIG_UMMA_MMA_STATS");
         if (ms) g_mma_stats = atoi(ms);
         const char *hm = getenv("HOIG_UMMA_HALO");

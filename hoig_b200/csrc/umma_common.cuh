@@ -52,12 +52,6 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
-// L2 prefetch of a box (no smem destination, no barrier): hides HBM latency that the smem ring alone cannot
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *map, int c0, int c1, int c2, int c3)
-{
-    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
-                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src, uint32_t src_bytes)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
