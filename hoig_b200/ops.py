@@ -47,10 +47,17 @@ def _f32c(t: torch.Tensor, name: str) -> int:
     return t.data_ptr()
 
 
+_PACKED_DIMS: dict = {}
+
+
 def packed_dims(cout: int, kh: int, kw: int, cin: int, mode: int = CONV, stride: int = 1, pad: int = 0):
-    r, c = ctypes.c_int(), ctypes.c_int()
-    _lib.load().hoig_conv_packed_dims(mode, cout, kh, kw, cin, stride, pad, ctypes.byref(r), ctypes.byref(c))
-    return r.value, c.value
+    key = (cout, kh, kw, cin, mode, stride, pad)
+    hit = _PACKED_DIMS.get(key)                # a pure function of the geometry: one C call per distinct conv
+    if hit is None:
+        r, c = ctypes.c_int(), ctypes.c_int()
+        _lib.load().hoig_conv_packed_dims(mode, cout, kh, kw, cin, stride, pad, ctypes.byref(r), ctypes.byref(c))
+        hit = _PACKED_DIMS[key] = (r.value, c.value)
+    return hit
 
 
 # ------------------------------------------------------------------ stage R
