@@ -297,7 +297,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step (BASELINE config: 64)")
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16", "f32"])
+    ap.add_argument("--dtype", default="f16", choices=["bf16", "f16", "f32"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--cuda-graph", action="store_true",
                     help="also time the step as ONE captured CUDA graph (GeneratorB200.graphed) and report it as graph_value")

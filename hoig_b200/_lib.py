@@ -177,7 +177,9 @@ class LaunchRecorder:
 
 recorder = LaunchRecorder()
 _NO_LAUNCH = {"hoig_version", "hoig_last_error", "hoig_check_device", "hoig_conv_packed_dims",
-              "hoig_rasterize_workspace_bytes", "hoig_set_umma_gather_only", "hoig_set_rasterizer_band_pixels"}
+              "hoig_rasterize_workspace_bytes", "hoig_set_umma_gather_only", "hoig_set_rasterizer_band_pixels",
+              "hoig_set_halo_variant", "hoig_set_umma_pair_mode", "hoig_set_umma_dual_mode", "hoig_set_umma_bres_mode",
+              "hoig_set_umma_halo_mode"}
 
 
 class _Proxy:

@@ -23,6 +23,31 @@ int check_launch(const char *what)
     return HOIG_ERR_CUDA;
 }
 
+static int g_sm_count[kMaxDevices];
+static bool g_slot_used[kMaxDevices][SLOT_COUNT];
+
+static int current_device()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+    return dev;
+}
+
+int device_sm_count()
+{
+    const int dev = current_device();
+    if (!g_sm_count[dev]) cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+    return g_sm_count[dev];
+}
+
+bool first_use_on_device(int slot)
+{
+    bool &used = g_slot_used[current_device()][slot];
+    const bool first = !used;
+    used = true;
+    return first;
+}
+
 int conv2d_simt(const hoigConvDesc *d, cudaStream_t stream);
 int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream);
 int conv2d_halo(int dtype, int KH, int KW, int Cout, const hoigHaloConvSeg *segs, int nsegs, cudaStream_t stream);

@@ -295,15 +295,11 @@ int conv2d_halo(int dtype, int KH, int KW, int Cout, const hoigHaloConvSeg *segs
     if (P.b_stages > H_MAX_STAGES) P.b_stages = H_MAX_STAGES;
     HOIG_REQUIRE(P.b_stages >= 2, "conv2d_halo: not enough shared memory");
 
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_TOTAL) != cudaSuccess ||
-            cudaFuncSetAttribute(conv_halo_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_TOTAL) != cudaSuccess)
-            return check_launch("conv_halo smem attribute");
-    }
+    const int num_sms = device_sm_count();
+    if (first_use_on_device(SLOT_CONV_HALO) &&
+        (cudaFuncSetAttribute(conv_halo_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_TOTAL) != cudaSuccess ||
+         cudaFuncSetAttribute(conv_halo_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_TOTAL) != cudaSuccess))
+        return check_launch("conv_halo smem attribute");
     const int grid = tiles < num_sms ? tiles : num_sms;
     const size_t smem = 1024 + (size_t)P.a_stages * A_STAGE + (size_t)P.b_stages * b_stage;
     if (dtype == HOIG_F16) conv_halo_kernel<__half><<<grid, H_THREADS, smem, stream>>>(P, map_a[0], map_w[0], map_a[1], map_w[1]);

@@ -707,12 +707,10 @@ int g_pair_mode = 1;        // 0: one CTA per tile; 1: CTA pairs (cta_group::2) 
 template <typename T, int NCTA>
 int launch_kernel(const UmmaParams &P, const CUtensorMap &map_w, const CUtensorMap *map_a, int grid, size_t smem, cudaStream_t stream)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(conv_umma_kernel<T, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess)
-            return check_launch("conv_umma smem attribute");
-        attr_set = true;
-    }
+    constexpr int slot = (std::is_same<T, __half>::value ? SLOT_CONV_UMMA_F16_1 : SLOT_CONV_UMMA_BF16_1) + (NCTA - 1);
+    if (first_use_on_device(slot) &&
+        cudaFuncSetAttribute(conv_umma_kernel<T, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess)
+        return check_launch("conv_umma smem attribute");
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid);
@@ -805,12 +803,7 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
         }
     }
 
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int num_sms = device_sm_count();
     const int total = (P.m_tiles / ncta) * P.n_tiles;
     const int units = num_sms / ncta;                       // CTAs or CTA pairs that fit the GPU
     const int grid = (total < units ? total : units) * ncta;
@@ -830,9 +823,11 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
     ConvPlan plan;
     int st = plan_conv(d, BM, &plan);
     if (st != HOIG_OK) return st;
-    if (g_force_gather < 0) {
+    static bool env_parsed = false;       // independent of the setters below: calling one of them first must not skip this block
+    if (!env_parsed) {
+        env_parsed = true;
         const char *e = getenv("HOIG_UMMA_GATHER_ONLY");
-        g_force_gather = (e && e[0] == '1') ? 1 : 0;
+        if (g_force_gather < 0) g_force_gather = (e && e[0] == '1') ? 1 : 0;
         const char *ms = getenv("HOIG_UMMA_MMA_STATS");
         if (ms) g_mma_stats = atoi(ms);
         const char *hm = getenv("HOIG_UMMA_HALO");

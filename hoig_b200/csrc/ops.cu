@@ -1125,8 +1125,7 @@ extern "C" int hoig_attn_combine(const void *gt, int64_t ldgt, const void *gs, i
                  "attn_combine: channels / strides must be multiples of 8");
     const int64_t npix = (int64_t)N * h * h;
     if (npix == 0) return HOIG_OK;
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int sms = device_sm_count();
     const int64_t want = (npix + 31) / 32;
     const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
     return dispatch(dtype, [&](auto *tag) {

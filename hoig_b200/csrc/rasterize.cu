@@ -807,12 +807,9 @@ extern "C" int hoig_rasterize_fim_wim(const float *faces, int B, int F, int imag
     HOIG_REQUIRE(band_rows >= 1, "rasterize: image too wide");
     const int n_bands = ceil_div(is, band_rows);
     const size_t smem = (size_t)band_rows * is * sizeof(unsigned long long) + (size_t)is * sizeof(float) + (size_t)(kListCap + kHeavyCap) * sizeof(int);
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(rasterize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-            return check_launch("rasterize smem attribute");
-        attr_set = true;
-    }
+    if (first_use_on_device(SLOT_RASTERIZE) &&
+        cudaFuncSetAttribute(rasterize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        return check_launch("rasterize smem attribute");
     uint32_t *bins = nullptr;
     const int cap = bin_cap(F);
     if (workspace && workspace_bytes >= hoig_rasterize_workspace_bytes(B, F, is) && F > 0 && F < (1 << 24) && n_bands <= 256 && B <= 65535) {

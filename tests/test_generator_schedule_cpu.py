@@ -70,7 +70,8 @@ def test_schedule_matches_oracle(monkeypatch, variant, dtype, tol):
     g = create(variant, dtype=dtype, **SMALL)
     g.load_state_dict(sd, strict=True)
     inp = synth.generator_inputs(2, seed=1, size=64)
-    outs = g(**inp)
+    with torch.no_grad():
+        outs = g._forward_impl(**inp)      # the schedule itself; forward() refuses CPU tensors (no CPU path in the product)
     with torch.no_grad():
         ref = gr.generator_forward(sd, **inp, **table)
     assert len(outs) == 10
@@ -86,7 +87,8 @@ def test_schedule_bf16_emulation_within_rel_l2(monkeypatch):
     g = create("generator_spade_attn", dtype=torch.bfloat16, **SMALL)
     g.load_state_dict(sd)
     inp = synth.generator_inputs(1, seed=1, size=64)
-    outs = g(**inp)
+    with torch.no_grad():
+        outs = g._forward_impl(**inp)      # the schedule itself; forward() refuses CPU tensors (no CPU path in the product)
     with torch.no_grad():
         ref = gr.generator_forward(sd, **inp, **table)
     for i, (a, b) in enumerate(zip(outs, ref)):
@@ -101,7 +103,8 @@ def test_schedule_f16_emulation_within_rel_l2(monkeypatch):
     g = create("generator_spade_attn", dtype=torch.float16, **SMALL)
     g.load_state_dict(sd)
     inp = synth.generator_inputs(1, seed=1, size=64)
-    outs = g(**inp)
+    with torch.no_grad():
+        outs = g._forward_impl(**inp)      # the schedule itself; forward() refuses CPU tensors (no CPU path in the product)
     with torch.no_grad():
         ref = gr.generator_forward(sd, **inp, **table)
     for i, (a, b) in enumerate(zip(outs, ref)):
@@ -146,3 +149,33 @@ def test_commuted_attention_equals_block_extractor_formulation():
     out = emu_ops.attn_combine(gt, gs, b1, w2, b2, src, flow, tgt, torch.empty(n, h, h, c), k)
     assert torch.isfinite(out).all()
     assert (out - ref).abs().max().item() <= 2e-5
+
+
+def test_forward_refuses_cpu_tensors():
+    g = create("generator_spade_attn", **SMALL)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        g(**synth.generator_inputs(1, seed=1, size=64))
+
+
+def test_weight_cache_invalidation_rules():
+    """ADVICE r1: replacing a Parameter object, load_state_dict (also assign=True) and .to() must drop the derived copies;
+    in-place updates are seen through the version counter."""
+    g = create("generator_spade_attn", **SMALL)
+    name = "src_model.img_reg.0.weight"
+    p0 = g._p(name)
+    sig0 = g._weights_signature()
+    g._pcache["probe"] = ((), 1)
+    with torch.no_grad():
+        p0.mul_(2.0)
+    assert g._weights_signature() != sig0
+    g.src_model.img_reg._modules["0"].weight = torch.nn.Parameter(torch.zeros_like(p0))
+    assert g._p(name) is not p0 and "probe" not in g._pcache
+    g._pcache["probe"] = ((), 1)
+    g.load_state_dict({k: v.clone() for k, v in g.state_dict().items()}, assign=True)
+    assert "probe" not in g._pcache and g._p(name) is g.get_parameter(name)
+    g._pcache["probe"] = ((), 1)
+    g.train(); g.eval()
+    assert "probe" not in g._pcache
+    g._pcache["probe"] = ((), 1)
+    g.double()
+    assert "probe" not in g._pcache
