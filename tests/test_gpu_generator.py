@@ -29,6 +29,7 @@ REL_L2_GATE = 1e-2          # north_star's gate for the 16-bit path; applies to 
 # reproduced by the judge on the oracle port.  bf16 is therefore NOT the default; its test records the measured budget and
 # still holds the outputs that do meet 1e-2 (the four masks) to 1e-2.
 BF16_MEASURED_BUDGET = 2.5e-2
+SLOT_REL_L2 = 4e-3          # same sample, different batch size: fp16 rounding-noise floor (see the batch-4 test)
 NAMES = ["src_img_bg", "tsf_img_bg", "src_obj", "src_hand", "src_mask_bg", "src_mask_hand", "tsf_obj", "tsf_hand",
          "tsf_mask_bg", "tsf_mask_hand"]
 
@@ -126,8 +127,10 @@ def _slot(inp, i):
 def test_f16_full_config_batch4_vs_fp32_and_slots():
     """Parity at the benchmarked layer shapes (conv_dim 64, 256x256) with batch > 1: every conv then runs on the TMA /
     CTA-pair / dual-pipeline / contiguous-tile-range paths with tile ranges that cross images, and the per-image statistics
-    flush is exercised.  Checks (a) relative L2 <= 1e-2 per output against the fp32 SIMT path on the same batch and (b) that
-    each sample equals its own batch-1 run (statistics are per sample; only the summation grouping differs)."""
+    flush is exercised.  Checks (a) relative L2 <= 1e-2 per output AND per sample against the fp32 SIMT path on the same
+    batch and (b) that each sample agrees with its own batch-1 run to within the fp16 rounding-noise floor (statistics are per
+    sample; the summation grouping differs between batch sizes, which flips individual fp16 roundings: measured 1.9e-3,
+    against 3e-3 between fp16 and fp32) -- a tile attributed to the wrong image would show up as percent-level errors."""
     variant = "generator_spade_attn"
     sd = gr.init_state_dict(seed=0, jitter=0.05, **FULL, **TABLE[variant])
     inp = {k: v.cuda() for k, v in synth.generator_inputs(4, seed=3, size=256).items()}
@@ -140,7 +143,7 @@ def test_f16_full_config_batch4_vs_fp32_and_slots():
         o1 = g16(**_slot(inp, i))
         for n, a, b in zip(NAMES, o16, o1):
             rel = ((a[i:i + 1] - b).norm() / b.norm()).item()
-            assert rel <= 1e-3, (n, i, rel)
+            assert rel <= SLOT_REL_L2, (n, i, rel)
     g32 = create(variant, dtype=torch.float32, **FULL)
     g32.load_state_dict(sd)
     g32 = g32.cuda().eval()
@@ -148,6 +151,9 @@ def test_f16_full_config_batch4_vs_fp32_and_slots():
     torch.cuda.synchronize()
     _, rel = _stats([o.cpu() for o in o16], [o.cpu() for o in o32])
     assert rel <= REL_L2_GATE
+    for i in range(4):
+        for n, a, b in zip(NAMES, o16, o32):
+            assert ((a[i] - b[i]).norm() / b[i].norm()).item() <= REL_L2_GATE, (n, i)
 
 
 def test_f16_bench_shape_batch64_slots():
@@ -166,7 +172,7 @@ def test_f16_bench_shape_batch64_slots():
         o1 = g(**_slot(inp, i))
         for n, a, b in zip(NAMES, o64, o1):
             rel = ((a[i:i + 1] - b).norm() / b.norm()).item()
-            assert rel <= 1e-3, (n, i, rel)
+            assert rel <= SLOT_REL_L2, (n, i, rel)
             assert torch.isfinite(a).all()
 
 
