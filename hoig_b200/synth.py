@@ -155,6 +155,41 @@ def make_scene(B: int, seed: int = 0, obj_faces: int = 12238) -> Scene:
     return Scene(torch.from_numpy(faces_idx), out[0], out[1], default_cam(B), nv, map_fn, sem)
 
 
+def uv_atlas(scene: Scene, rasterize, n_hand_faces: int = N_HAND_F):
+    """Synthetic UV atlas in the reference's layout (utils/nmr.py:359-401: hand atlas | 128-px gap | object atlas, 256 x 640).
+
+    Per-vertex UVs come from a planar (hand) / spherical (object) projection of the rest pose; ``rasterize(tri)`` maps
+    ``tri`` (1,Fp,3,3) f32 (UV triangles at z = 1) to ``(fim (1,256,256) int32, wim (1,256,256,3) f32)`` WITHOUT the vertical
+    flip -- the caller supplies the rasterizer (the CUDA op in bench / product code, the C oracle in CPU tests).
+    Returns ``(faces_uv_coord (F,3,2), fim_uv (256,640) int32, wim_uv (256,640,3))``: the tables the reference registers as
+    ``faces_uv_coord_<obj>[0]``, ``fim_uv_<obj>[0]``, ``wim_uv_<obj>[0]``; atlas coordinates are in grid_sample's
+    align_corners=True convention like the reference's ``(uv - mean) * scale`` (nmr.py:393-395)."""
+    faces_idx = scene.faces_idx.long()
+    v = scene.verts_src[0, : scene.n_verts].double()
+    nh = N_HAND_V
+    uv = torch.zeros(v.shape[0], 2, dtype=torch.float64)
+    h = v[:nh, :2] - v[:nh, :2].mean(0)
+    uv[:nh] = 0.9 * h / h.abs().max()
+    o = v[nh:] - v[nh:].mean(0)
+    o = o / o.norm(dim=1, keepdim=True).clamp_min(1e-9)
+    uv[nh:, 0] = 0.9 * torch.atan2(o[:, 1], o[:, 0]) / math.pi
+    uv[nh:, 1] = 0.9 * (2 * torch.acos(o[:, 2].clamp(-1, 1)) / math.pi - 1)
+    fuv = uv[faces_idx].float()                                   # (F,3,2) local [-1,1]^2 coordinates of each part
+    fim_uv = torch.full((256, 640), -1, dtype=torch.int32)
+    wim_uv = torch.zeros(256, 640, 3)
+    for lo, hi, x0 in ((0, n_hand_faces, 0), (n_hand_faces, fuv.shape[0], 384)):
+        tri = torch.cat([fuv[lo:hi], torch.ones(hi - lo, 3, 1)], 2)[None].contiguous()             # z = 1: inside the frustum
+        fim, wim = rasterize(tri)
+        fim, wim = fim.cpu(), wim.cpu()
+        fim_uv[:, x0:x0 + 256] = torch.where(fim[0] >= 0, fim[0] + lo, fim[0])
+        wim_uv[:, x0:x0 + 256] = wim[0]
+    px = (fuv[..., 0] + 1) / 2 * 255
+    px[n_hand_faces:] += 384
+    py = (fuv[..., 1] + 1) / 2 * 255
+    coord = torch.stack([px / 639 * 2 - 1, py / 255 * 2 - 1], -1).contiguous()
+    return coord, fim_uv.contiguous(), wim_uv.contiguous()
+
+
 def generator_inputs(B: int, seed: int = 0, size: int = 256, img_cond_dim: int = 3,
                      obj_cond_dim: int = 12, device="cpu", with_holes: bool = True):
     """Random tensors with the shapes/ranges ``Generator.forward`` receives

@@ -16,33 +16,8 @@ from hoig_b200 import ops, renderer, synth  # noqa: E402
 
 
 def uv_atlas(scene, dev):
-    """Synthetic atlas in the reference's layout (hand atlas | 128-px gap | object atlas, 256 x 640): per-vertex UVs from a
-    planar (hand) / spherical (object) projection of the rest pose, per-face atlas coordinates, and the atlas face-index /
-    weight maps obtained by rasterizing the UV triangles."""
-    faces_idx = scene.faces_idx.long()
-    v = scene.verts_src[0, : scene.n_verts].double()
-    nh = synth.N_HAND_V
-    uv = torch.zeros(v.shape[0], 2, dtype=torch.float64)
-    h = v[:nh, :2] - v[:nh, :2].mean(0)
-    uv[:nh] = 0.9 * h / h.abs().max()
-    o = v[nh:] - v[nh:].mean(0)
-    o = o / o.norm(dim=1, keepdim=True).clamp_min(1e-9)
-    uv[nh:, 0] = 0.9 * torch.atan2(o[:, 1], o[:, 0]) / np.pi
-    uv[nh:, 1] = 0.9 * (2 * torch.acos(o[:, 2].clamp(-1, 1)) / np.pi - 1)
-    fuv = uv[faces_idx].float()                                   # (F,3,2) local [-1,1]^2 coordinates of each part
-    n_hand_f = renderer.N_HAND_FACES
-    fim_uv = torch.full((256, 640), -1, dtype=torch.int32, device=dev)
-    wim_uv = torch.zeros(256, 640, 3, device=dev)
-    for lo, hi, x0 in ((0, n_hand_f, 0), (n_hand_f, fuv.shape[0], 384)):
-        tri = torch.cat([fuv[lo:hi], torch.ones(hi - lo, 3, 1)], 2)[None].contiguous().to(dev)     # z = 1: inside the frustum
-        fim, wim = ops.rasterize(tri, 256, flip_y=False)
-        fim_uv[:, x0:x0 + 256] = torch.where(fim[0] >= 0, fim[0] + lo, fim[0])
-        wim_uv[:, x0:x0 + 256] = wim[0]
-    px = (fuv[..., 0] + 1) / 2 * 255
-    px[n_hand_f:] += 384
-    py = (fuv[..., 1] + 1) / 2 * 255
-    coord = torch.stack([px / 639 * 2 - 1, py / 255 * 2 - 1], -1).contiguous().to(dev)             # align_corners=True atlas coordinates
-    return coord, fim_uv.contiguous(), wim_uv.contiguous()
+    coord, fim_uv, wim_uv = synth.uv_atlas(scene, lambda tri: ops.rasterize(tri.to(dev), 256, flip_y=False))
+    return coord.to(dev), fim_uv.to(dev), wim_uv.to(dev)
 
 
 def main():
