@@ -12,10 +12,11 @@ Torch-CPU fp32 restatement of stages R0 and R4-R7 of SURVEY.md section 8a
 * R7  ``utils/nmr.py:874-968`` cal_bc_transform (T only; O is discarded by the
       caller, trainer.py:80) and ``trainer.py:81`` T_hand
 
-Pinned by the reference's look_at KAT (tests/test_look_at.py:10-19) in
-tests/test_oracle_geometry.py; the remaining functions have no reference
-tests ("parity unpinned" by the reference) and are restated
-op-for-op from the cited lines.
+Pinned to the reference itself: tests/golden/geometry_stage_r.npz is produced by running the UNMODIFIED
+``HandRecoveryFlow.forward`` / ``MANORenderer`` methods / ``util.morph`` from /root/reference
+(tests/golden/make_golden_geometry.py), and tests/test_geometry_fixture_cpu.py holds every function below
+to it (bit-equal for T, masks, encoded maps; <= 1e-6 for projected faces and textures); plus the reference's
+look_at KAT (tests/test_look_at.py:10-19) in tests/test_oracle_geometry.py.
 """
 from __future__ import annotations
 
