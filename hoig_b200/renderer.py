@@ -103,3 +103,56 @@ def sample_from_texture_dense(fim, wim, faces_uv_coord):
 def render_from_texture(texture, fim, wim, faces_uv_coord):
     """models/trainer.py:84-87: re-render the texture atlas at a pose given its face-index / weight maps."""
     return ops.grid_sample_nchw(texture, sample_from_texture_dense(fim, wim, faces_uv_coord), align_corners=True)
+
+
+# ------------------------------------------------------------------ row N1: the batched HandRecoveryFlow
+class HandRecoveryFlowB200(torch.nn.Module):
+    """Batched replacement for ``HandRecoveryFlow.forward`` (models/trainer.py:46-145) downstream of the MANO layer.
+
+    The reference runs, per sample and in Python, two rasterizations, ~100 small kernels of table gathers / masks / boolean
+    scatter and the UV-texture warp; here the whole batch is ~10 launches.  MANO/smplx (``HandModelRecovery.get_details``) is out
+    of scope, so ``forward`` takes what ``get_details`` returns -- vertices and the 15-value camera row -- instead of MANO
+    parameters.  The per-object tables are the reference's own buffers (utils/nmr.py:286-401), passed in unchanged:
+
+      faces_idx (F,3) int32 ``faces_<obj>``; map_fn (F+1,3) ``map_fn_<obj>``; sem_full (F+1,1) ``sem_full_<obj>``;
+      fim_uv (Hu,Wu) int32 / wim_uv (Hu,Wu,3) ``fim_uv_<obj>[0]`` / ``wim_uv_<obj>[0]``; faces_uv_coord (F,3,2)
+      ``faces_uv_coord_<obj>[0]``; obj_tex (Hu, Wu-384, 3) ``obj_tex_img_<obj>`` (or None for ``pre_load=False``).
+
+    One object per batch (the reference looks the object up per sample; group samples by object upstream)."""
+
+    def __init__(self, faces_idx, map_fn, sem_full, fim_uv, wim_uv, faces_uv_coord, obj_tex=None, image_size: int = 256,
+                 n_hand_faces: int = N_HAND_FACES, tex_x0: int = 384):
+        super().__init__()
+        self.image_size, self.n_hand_faces, self.tex_x0 = image_size, n_hand_faces, tex_x0
+        self.n_verts = int(faces_idx.max().item()) + 1                          # trainer.py:65 ``length``
+        self.register_buffer("faces_idx", faces_idx.contiguous().int())
+        self.register_buffer("map_fn", map_fn.contiguous().float())
+        self.register_buffer("sem_full", sem_full.contiguous().float())
+        self.register_buffer("fim_uv", fim_uv.contiguous().int())
+        self.register_buffer("wim_uv", wim_uv.contiguous().float())
+        self.register_buffer("faces_uv_coord", faces_uv_coord.contiguous().float())
+        self.register_buffer("obj_tex", None if obj_tex is None else obj_tex.contiguous().float())
+
+    @torch.no_grad()
+    def forward(self, src_img, src_verts, ref_verts, src_cam, ref_cam=None, src_armask=None, tsf_armask=None):
+        """src_img (B,3,H,W); *_verts (B,V,3) (rows beyond the object's vertex count are ignored, data/hov3_dataset.py:246-248);
+        *_cam (B,15).  Returns ``(generator_kwargs, masks)``: the keyword arguments of ``Generator.forward`` as built at
+        trainer.py:377-393 and the four crop masks of trainer.py:144-145."""
+        ref_cam = src_cam if ref_cam is None else ref_cam
+        with torch.cuda.device(src_img.device):
+            nv = self.n_verts
+            vs = src_verts if src_verts.shape[1] == nv else src_verts[:, :nv].contiguous()
+            vr = ref_verts if ref_verts.shape[1] == nv else ref_verts[:, :nv].contiguous()
+            fs, fim_s, wim_s = render_fim_wim_batched(src_cam, vs, self.faces_idx, self.image_size)
+            _, fim_r, wim_r = render_fim_wim_batched(ref_cam, vr, self.faces_idx, self.image_size)
+            src_img = src_img.contiguous().float()
+            tex = texture_backward_warp(src_img, fs, fim_s, self.fim_uv, self.wim_uv, self.obj_tex, self.tex_x0)   # trainer.py:83
+            r_ref = render_from_texture(tex, fim_r, wim_r, self.faces_uv_coord)                                    # trainer.py:84-85
+            r_src = render_from_texture(tex, fim_s, wim_s, self.faces_uv_coord)                                    # trainer.py:86-87
+            kwargs, masks = condition_inputs_fused(src_img, fs, fim_s, fim_r, wim_r, self.map_fn, self.sem_full, r_src, r_ref,
+                                                   self.n_hand_faces)
+            if src_armask is not None:
+                kwargs["src_armask"] = src_armask
+            if tsf_armask is not None:
+                kwargs["tsf_armask"] = tsf_armask
+            return kwargs, masks

@@ -155,6 +155,28 @@ def make_scene(B: int, seed: int = 0, obj_faces: int = 12238) -> Scene:
     return Scene(torch.from_numpy(faces_idx), out[0], out[1], default_cam(B), nv, map_fn, sem)
 
 
+def pose_batch(scene: Scene, n: int, seed: int = 0, device="cpu", z_range=(-0.6, -0.45), xy_range: float = 0.06):
+    """``n`` DISTINCT seeded rigid poses of the scene's hand+object assembly, generated with torch on ``device`` (so that
+    thousands of meshes need no Python loop): returns verts (n, n_verts, 3) f32 in OpenGL coordinates.  ``z_range`` sets the
+    camera distance, i.e. the fraction of the frame the meshes cover (HO3D-like default ~7 %, (-0.3, -0.25) ~25 %)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    base = scene.verts_src[0, : scene.n_verts].double()
+    # undo the first pose's translation roughly: centre the assembly, then apply fresh rotations / translations
+    base = base - base.mean(0, keepdim=True)
+    axis = torch.randn(n, 3, generator=g, dtype=torch.float64)
+    axis = axis / axis.norm(dim=1, keepdim=True)
+    ang = (torch.rand(n, generator=g, dtype=torch.float64) * 2 - 1) * math.pi
+    K = torch.zeros(n, 3, 3, dtype=torch.float64)
+    K[:, 0, 1], K[:, 0, 2], K[:, 1, 0] = -axis[:, 2], axis[:, 1], axis[:, 2]
+    K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -axis[:, 0], -axis[:, 1], axis[:, 0]
+    R = torch.eye(3, dtype=torch.float64)[None] + torch.sin(ang)[:, None, None] * K + (1 - torch.cos(ang))[:, None, None] * (K @ K)
+    t = torch.stack([(torch.rand(n, generator=g, dtype=torch.float64) * 2 - 1) * xy_range,
+                     (torch.rand(n, generator=g, dtype=torch.float64) * 2 - 1) * xy_range,
+                     z_range[0] + torch.rand(n, generator=g, dtype=torch.float64) * (z_range[1] - z_range[0])], 1)
+    R, t, base = R.to(device), t.to(device), base.to(device)
+    return (torch.einsum("vk,nik->nvi", base, R) + t[:, None, :]).float().contiguous()
+
+
 def uv_atlas(scene: Scene, rasterize, n_hand_faces: int = N_HAND_F):
     """Synthetic UV atlas in the reference's layout (utils/nmr.py:359-401: hand atlas | 128-px gap | object atlas, 256 x 640).
 

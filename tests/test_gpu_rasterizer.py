@@ -3,7 +3,6 @@
 Bit-exact face-index maps against (a) the C oracle and (b), when oracle/_ref was
 built, the reference's own kernel compiled with the same nvcc, on the same GPU.
 """
-import importlib.util
 import os
 
 import numpy as np
@@ -15,33 +14,7 @@ from hoig_b200 import ops, synth
 from oracle import geometry_ref as geo
 
 pytestmark = pytest.mark.gpu
-REF_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
-
-
-def _load_ref(name):
-    path = os.path.join(REF_DIR, name + ".so")
-    if not os.path.exists(path):
-        return None
-    # the reference's rasterizer hard-codes its pybind module name (rasterize_cuda.cpp:194)
-    init = "rasterize" if name == "ref_rasterize_cuda" else name
-    spec = importlib.util.spec_from_file_location(init, path)
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    return mod
-
-
-def _ref_rasterize(mod, faces, is_, near=0.1, far=100.0):
-    """rasterize.py:50-52 allocation + rasterize_cuda.cpp:70 call + rasterize.py:335-338 flip."""
-    B, F = faces.shape[:2]
-    dev = faces.device
-    fim = torch.full((B, is_, is_), -1, dtype=torch.int32, device=dev)
-    wim = torch.zeros(B, is_, is_, 3, device=dev)
-    depth = torch.full((B, is_, is_), far, device=dev)
-    finv_map = torch.zeros(1, device=dev)
-    finv = torch.zeros(B, F, 3, 3, device=dev)
-    mod.forward_face_index_map(faces.clone(), fim, wim, depth, finv_map, finv, is_, near, far, 0, 0, 0)
-    torch.cuda.synchronize()
-    return torch.flip(fim, dims=(1,)), torch.flip(wim, dims=(1,)), torch.flip(depth, dims=(1,)), finv
+from oracle.ref_kernels import load_ref as _load_ref, ref_rasterize as _ref_rasterize  # noqa: E402
 
 
 def _scene_faces(B, seed, obj_faces):
