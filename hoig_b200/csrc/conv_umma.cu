@@ -36,6 +36,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int A_HALO_BYTES = 17 * 1024;   // (128 + up to 7 halo pixels) x 128 B, rounded up to the 1024 B swizzle period
+constexpr int VH_COLS = 8, VH_ROWS = 16;  // vhalo tile: 8 columns (1024 B of 64 channels = one swizzle period) x 16 rows = 128 pixels
 constexpr int EPI_WARPS = 8, PROD_WARPS = 4;    // epilogue warp w: TMEM lane quadrant w % 4, 16-column chunks of parity w / 4
 constexpr int EPI_END = 16;                     // warps 12-15: a further epilogue group
 constexpr int TMA_WARP = 16, MMA_WARP = 17, WB_WARP = 18, MMA2_WARP = 19;   // WB: weight-tile producer (TMA-A mode), MMA2: second issue stream (dual mode)
@@ -60,7 +61,11 @@ struct UmmaParams {
     int halo;            // 1: regular kh x kw stride-1 conv whose tiles are 128 consecutive pixels of ONE image row: a stage holds one
                          //    activation box of 128 + kw - 1 pixels per (kernel row, 64 channels) and the kw taps read it through
                          //    descriptors shifted by one pixel row (128 B) each -- L2->SM activation traffic / kw (see conv_halo.cu)
-    int k_steps;         // halo: kh * Cin / 64 pipeline steps of kw taps each
+    int k_steps;         // halo: kh * Cin / 64 pipeline steps of kw taps each; vhalo: Cin / 64 steps of kh taps each
+    int vhalo;           // 1: kh x 1 conv (the re-associated 7x7 stems / heads) on 8-column x 16-row tiles with RESIDENT weights: a stage
+                         //    holds ONE activation box of 8 x (16 + kh - 1) pixels per 64 channels; tap r reads it r pixel-rows of the
+                         //    box (8 pixels = 1024 B, a whole swizzle period) further on -- L2->SM activation traffic / (kh * 16 / 22)
+    int tiles_x;         // vhalo: tiles per image row (GW / 8)
     int mma_stats;       // 1: per-plane statistics reduced with warp-level MMAs (colsum16), 0: shuffle transpose-reduce
     int bres;            // 1: the whole packed weight matrix (k_blocks tiles of BN x 64) stays RESIDENT in shared memory, loaded
                          //    once per CTA; the ring then carries activations only.  For the narrow high-resolution convs the
@@ -92,11 +97,11 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
     const ConvParams &p = P.c;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int BN = P.BN;
-    const int TPS = P.halo ? p.kw : 1;                                  // taps per pipeline step
-    const int a_bytes = P.halo ? A_HALO_BYTES : A_STAGE_BYTES;          // activation region of a stage
+    const int TPS = P.halo ? p.kw : (P.vhalo ? p.kh : 1);               // taps per pipeline step
+    const int a_bytes = P.halo ? A_HALO_BYTES : (P.vhalo ? (VH_ROWS + p.kh - 1) * VH_COLS * 128 : A_STAGE_BYTES);   // activation region of a stage
     const int b_tile = (BN / NCTA) * BK * 2;                            // one tap's weight tile (this CTA's share)
     const int stage_bytes = P.bres ? a_bytes : a_bytes + TPS * b_tile;
-    const int n_steps = P.halo ? P.k_steps : P.k_blocks;
+    const int n_steps = (P.halo || P.vhalo) ? P.k_steps : P.k_blocks;
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     const uint32_t stg_base = smem_u32(smem);                  // epilogue staging first (1024-aligned)
     const uint32_t smem_base = stg_base + STG_BYTES;           // then the operand ring
@@ -304,11 +309,32 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                     if (P.n_tiles > 1) { mt = tile / P.n_tiles; nt[w] = tile - mt * P.n_tiles; }
                     mt = mt * NCTA + (int)rank;
                     n_img[w] = mt / p.tiles_per_image;
-                    const int pix0 = (mt % p.tiles_per_image) * BM;
-                    gy0[w] = pix0 / p.GW; gx0[w] = pix0 % p.GW;
+                    if (P.vhalo) {
+                        const int t_in = mt % p.tiles_per_image;
+                        gy0[w] = (t_in / P.tiles_x) * VH_ROWS; gx0[w] = (t_in % P.tiles_x) * VH_COLS;
+                    } else {
+                        const int pix0 = (mt % p.tiles_per_image) * BM;
+                        gy0[w] = pix0 / p.GW; gx0[w] = pix0 % p.GW;
+                    }
                 }
                 int tap = 0, c = 0;
-                if (!P.halo) {
+                if (P.vhalo) {
+                    // vertical-halo mode (weights resident, so only the activation warp is here): step = 64-channel slice, ONE box of
+                    // 8 columns x (16 + kh - 1) rows starting pad_h rows above the tile
+                    for (int kb = 0; kb < P.k_steps; ++kb) {
+                        for (int w = 0; w < NP; ++w) {
+                            if (!live[w]) continue;
+                            const uint32_t st = q[w] * (uint32_t)NP + (uint32_t)w;
+                            mbar_wait(empty0 + 8u * st, ph[w] ^ 1u);
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx(full0 + 8u * st, (uint32_t)a_bytes);
+                                tma_load_4d(smem_base + st * (uint32_t)stage_bytes, &map_a0, full0 + 8u * st, kb * BK, gx0[w], gy0[w] - p.pad_h, n_img[w]);
+                            }
+                            __syncwarp();
+                            if (++q[w] == sp) { q[w] = 0; ph[w] ^= 1u; }
+                        }
+                    }
+                } else if (!P.halo) {
                     for (int kb = 0; kb < P.k_blocks; ++kb) {
                         const int tt = tap < p.ntaps ? tap : p.ntaps - 1;   // K padding blocks: any finite data (weights are zero)
                         for (int w = 0; w < NP; ++w) {
@@ -415,7 +441,27 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                 mbar_wait(smem_u32(&tempty_bar[acc]), (use & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)BN;
-                if (!P.halo) {
+                if (P.vhalo) {
+                    for (int kb = 0; kb < P.k_steps; ++kb) {
+                        const uint32_t st = q * (uint32_t)NP + (uint32_t)w;
+                        mbar_wait(full0 + 8u * st, ph);
+                        tc_fence_after();
+                        const uint64_t da = desc0 + (uint64_t)(st * stage16);
+                        // tap r reads the shared box r pixel-rows (8 pixels = 1024 B) further on; its weight k-block is r * (Cin / 64) + kb
+                        for (int r = 0; r < TPS; ++r) {             // warp-uniform loop, one elected lane issues
+                            const uint64_t das = da + (uint64_t)(r * (VH_COLS * 128 / 16));
+                            const uint64_t dbs = bres_desc + (uint64_t)((uint32_t)(r * P.k_steps + kb) * (uint32_t)(BN * 8));
+                            if (elect_one()) {
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k)
+                                    umma_bf16(d_tmem, das + (uint64_t)(2 * k), dbs + (uint64_t)(2 * k), idesc, (kb | r | k) ? 1u : 0u);
+                                if (r == TPS - 1) umma_commit(empty0 + 8u * st);
+                            }
+                            __syncwarp();
+                        }
+                        if (++q == sp) { q = 0; ph ^= 1u; }
+                    }
+                } else if (!P.halo) {
                     for (int kb = 0; kb < P.k_blocks; ++kb) {
                         const uint32_t st = q * (uint32_t)NP + (uint32_t)w;
                         mbar_wait(full0 + 8u * st, ph);
@@ -510,7 +556,11 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
             if (P.n_tiles > 1) { mt = tile / P.n_tiles; nt = tile - mt * P.n_tiles; }
             mt = mt * NCTA + (int)rank;
             const int n_img = P.tpi_shift >= 0 ? mt >> P.tpi_shift : mt / p.tiles_per_image;
-            const int pix = (mt - n_img * p.tiles_per_image) * BM + quad * 32 + lane;
+            int pix = (mt - n_img * p.tiles_per_image) * BM + quad * 32 + lane;
+            if (P.vhalo) {   // 8-column x 16-row tiles, row-major over the image
+                const int t_in = mt - n_img * p.tiles_per_image, ty = t_in / P.tiles_x, r = quad * 32 + lane;
+                pix = (ty * VH_ROWS + (r >> 3)) * p.GW + (t_in - ty * P.tiles_x) * VH_COLS + (r & 7);
+            }
             const bool valid = pix < npix;
             const int64_t m = valid ? out_pixel(p, n_img, pix) : 0;
             const int pc = p.phase_cout;     // > 0: transposed conv, column n = phase * pc + channel
@@ -700,6 +750,7 @@ int g_umma_debug = 0;
 int g_contig_mode = 1;      // HOIG_UMMA_CONTIG
 int g_mma_stats = 1;        // HOIG_UMMA_MMA_STATS
 int g_halo_mode = 1;        // HOIG_UMMA_HALO: row-halo activation reuse for full-row tiles
+int g_vhalo_mode = 1;       // HOIG_UMMA_VHALO: vertical-halo activation reuse for kh x 1 convs
 int g_bres_mode = 1;        // HOIG_UMMA_BRES: resident weights for small weight matrices
 int g_dual_mode = 1;        // 1: narrow-N TMA convs run two MMA issue pipelines per CTA (HOIG_UMMA_DUAL=0 disables)
 int g_pair_mode = 1;        // 0: one CTA per tile; 1: CTA pairs (cta_group::2) where they pay off; 2: pairs wherever legal (tests)
@@ -755,15 +806,22 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     // the halved weight traffic saves below ~12 k-blocks (7x1 stems, 64->128 stride-2, 128->64 transposed).
     const bool pair_ok = P.tma_a && P.m_tiles % 2 == 0 && P.BN % 32 == 0 && p.Npad % P.BN == 0;
     int ncta = (pair_ok && (g_pair_mode == 2 || (g_pair_mode == 1 && P.k_blocks >= 12))) ? 2 : 1;
+    // Vertical-halo mode for the kh x 1 convs (7x7 stems / heads after re-association): single CTAs, resident weights
+    const int vh_a_bytes = (VH_ROWS + p.kh - 1) * VH_COLS * 128;
+    P.vhalo = (g_vhalo_mode && g_pair_mode != 2 && P.tma_a && p.nviews == 1 && p.kw == 1 && p.kh >= 2 && p.kh <= 8 && p.GW % VH_COLS == 0 &&
+               p.GH % VH_ROWS == 0 && p.Cin % BK == 0 && P.n_tiles == 1 && p.Kpad == p.kh * p.Cin &&
+               (size_t)P.k_blocks * P.BN * BK * 2 + 4 * (size_t)vh_a_bytes <= (size_t)RING_BUDGET) ? 1 : 0;
+    P.tiles_x = P.vhalo ? p.GW / VH_COLS : 0;
+    if (P.vhalo) ncta = 1;
     // Resident weights (single-CTA tiles, one n-tile): worth it when the whole matrix fits beside >= 4 activation stages
     // Row-halo mode: regular stride-1 kh x kw conv, tiles = 128 consecutive pixels of one image row
     P.halo = (g_halo_mode && P.tma_a && p.nviews == 1 && p.kw >= 2 && p.kw <= 7 && p.GW % BM == 0 && p.Cin % BK == 0) ? 1 : 0;
     if (P.halo && RING_BUDGET / (A_HALO_BYTES + p.kw * (P.BN / ncta) * BK * 2) < 3) P.halo = 0;   // needs >= 3 stages of kw weight tiles
-    P.k_steps = P.halo ? p.kh * (p.Cin / BK) : 0;
+    P.k_steps = P.halo ? p.kh * (p.Cin / BK) : (P.vhalo ? p.Cin / BK : 0);
     const size_t w_bytes = (size_t)P.k_blocks * P.BN * BK * 2;
     // (not when the conv would run on CTA pairs: measured slower for 128->64 @256^2, whose 147 KB of weights leave 4 stages)
-    P.bres = (g_bres_mode && !P.halo && P.tma_a && P.n_tiles == 1 && ncta == 1 && w_bytes + 4 * (size_t)A_STAGE_BYTES <= (size_t)RING_BUDGET) ? 1 : 0;
-    const int stage_bytes = P.bres ? A_STAGE_BYTES
+    P.bres = (P.vhalo || (g_bres_mode && !P.halo && P.tma_a && P.n_tiles == 1 && ncta == 1 && w_bytes + 4 * (size_t)A_STAGE_BYTES <= (size_t)RING_BUDGET)) ? 1 : 0;
+    const int stage_bytes = P.vhalo ? vh_a_bytes : P.bres ? A_STAGE_BYTES
                                    : (P.halo ? A_HALO_BYTES + p.kw * (P.BN / ncta) * BK * 2 : A_STAGE_BYTES + (P.BN / ncta) * BK * 2);
     P.stages = (int)((RING_BUDGET - (P.bres ? w_bytes : 0)) / stage_bytes);
     if (P.stages > MAX_STAGES) P.stages = MAX_STAGES;
@@ -791,8 +849,8 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     }
     for (int v = 0; v < 4; ++v) map_a[v] = map_w;
     if (P.tma_a) {
-        const int bw = P.halo ? BM + p.kw - 1 : (p.GW < BM ? p.GW : BM);
-        const int bh = P.halo ? 1 : BM / bw;
+        const int bw = P.vhalo ? VH_COLS : P.halo ? BM + p.kw - 1 : (p.GW < BM ? p.GW : BM);
+        const int bh = P.vhalo ? VH_ROWS + p.kh - 1 : P.halo ? 1 : BM / bw;
         const cuuint32_t box[4] = {BK, (cuuint32_t)bw, (cuuint32_t)bh, 1};
         for (int v = 0; v < p.nviews; ++v) {
             const InputView &vw = p.view[v];
@@ -832,6 +890,8 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
         if (ms) g_mma_stats = atoi(ms);
         const char *hm = getenv("HOIG_UMMA_HALO");
         if (hm) g_halo_mode = atoi(hm);
+        const char *vm = getenv("HOIG_UMMA_VHALO");
+        if (vm) g_vhalo_mode = atoi(vm);
         const char *bm = getenv("HOIG_UMMA_BRES");
         if (bm) g_bres_mode = atoi(bm);
         const char *cm = getenv("HOIG_UMMA_CONTIG");
@@ -859,6 +919,8 @@ extern "C" void hoig_set_umma_gather_only(int on) { hoig::g_force_gather = on ? 
 extern "C" void hoig_set_umma_pair_mode(int on) { hoig::g_pair_mode = on; }
 // Diagnostic switch: 1 = full-row tiles of regular stride-1 convs share one activation box per kernel row (default), 0 = one box per tap.
 extern "C" void hoig_set_umma_halo_mode(int on) { hoig::g_halo_mode = on ? 1 : 0; }
+// Diagnostic switch: 1 = kh x 1 convs share one activation box per 64 channels across their vertical taps (default), 0 = one box per tap.
+extern "C" void hoig_set_umma_vhalo_mode(int on) { hoig::g_vhalo_mode = on ? 1 : 0; }
 // Diagnostic switch: 1 = small weight matrices stay resident in shared memory (default), 0 = always streamed.
 extern "C" void hoig_set_umma_bres_mode(int on) { hoig::g_bres_mode = on ? 1 : 0; }
 // Diagnostic switch: 1 = two MMA issue pipelines per CTA for narrow-N tiles (default), 0 = one.

@@ -201,6 +201,9 @@ void hoig_set_umma_dual_mode(int on);
 void hoig_set_umma_bres_mode(int on);
 /* Test hook: 1 (default) = full-row tiles of regular stride-1 convs load one activation box per kernel row, 0 = one per tap. */
 void hoig_set_umma_halo_mode(int on);
+/* Test hook: 1 (default) = kh x 1 convs (the re-associated 7x7 stems / heads) run on 8 x 16 pixel tiles that load one activation box
+ * per 64 channels for all kh vertical taps (weights resident), 0 = one box per tap. */
+void hoig_set_umma_vhalo_mode(int on);
 /* Tuning hook: pixels per rasterizer band (256..16384; the band's 64-bit key buffer lives in shared memory). */
 void hoig_set_rasterizer_band_pixels(int n);
 

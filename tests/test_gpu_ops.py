@@ -278,6 +278,8 @@ CONV_CASES = [
     ("1x1_k3200_attn_gemm", 1, 16, 3200, 128, 1, 1, "conv", dict(bias=True, act=2)),
     ("7x1_stem_c64", 2, 32, 64, 64, 7, 1, "conv", dict(stats=True, kw=1)),
     ("7x1_heads_c128_n56", 1, 32, 128, 56, 7, 1, "conv", dict(kw=1)),
+    ("7x1_stem_c64_w256", 3, 256, 64, 64, 7, 1, "conv", dict(stats=True, kw=1)),
+    ("7x1_bg_head_c64_n21", 2, 64, 64, 21, 7, 1, "conv", dict(kw=1)),
     ("3x3_tiny_8x8", 2, 8, 32, 32, 3, 1, "conv", dict(stats=True)),
     ("convT_3x3_s2", 2, 16, 128, 64, 3, 2, "convT", dict(stats=True)),
     ("convT_3x3_s2_small", 1, 8, 32, 16, 3, 2, "convT", dict(stats=True)),

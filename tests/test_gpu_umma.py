@@ -232,3 +232,31 @@ def test_row_halo_equals_box_per_tap(case):
     assert ((a - b).abs() <= 2.0 ** -7 * b.abs() + 1e-3).all()
     if outs[0][1] is not None:   # statistics of stored values that may differ by one ulp here and there
         assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-3, atol=0.5)
+
+
+VHALO_CASES = [c for c in CONV_CASES if c[0].startswith("7x1_")]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+@pytest.mark.parametrize("case", VHALO_CASES, ids=[c[0] for c in VHALO_CASES])
+def test_vertical_halo_mode_matches_per_tap_boxes(case, dtype):
+    """kh x 1 convs on 8 x 16 pixel tiles with one activation box per 64 channels (vhalo, resident weights) against the
+    one-box-per-tap path: same products, k order (slice, tap) instead of (tap, slice), so equal to fp32 summation order."""
+    import hoig_b200._lib as L
+    outs = []
+    try:
+        for mode in (0, 1):
+            L.lib().hoig_set_umma_vhalo_mode(mode)
+            out, ref, st, st_ref = _run_conv(case, dtype)
+            outs.append((out.float().cpu(), None if st is None else st.cpu()))
+            Cout = case[4]
+            ok, rel = _report(f"vhalo={mode} " + case[0], out[..., :Cout], ref[..., :Cout], 2e-2, 2e-2)
+            assert ok
+    finally:
+        L.lib().hoig_set_umma_vhalo_mode(1)
+    a, b = outs[0][0], outs[1][0]
+    ulp = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+    assert ((a - b).abs() <= 2 * ulp * b.abs() + 1e-3).all()
+    assert (a != b).float().mean().item() < 0.05          # almost every element rounds identically
+    if outs[0][1] is not None:
+        assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-4, atol=0.3)
