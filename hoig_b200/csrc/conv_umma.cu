@@ -72,7 +72,7 @@ struct UmmaParams {
                          //    L2->SM path (~42 B/clk/SM), not the tensor pipe, is the bound, and weights are 1/3 of that traffic.
     int dual;            // 1: two independent pipelines per CTA (narrow N): tiles alternate between two MMA-issuing warps,
                          //    each with its own half of the smem ring and two of the four TMEM accumulator stages
-    int debug;           // timing knock-outs (HOIG_UMMA_DEBUG, results are garbage): 1 = epilogue only drains TMEM, 2 = A tile loaded once per tile
+    int debug;           // timing knock-outs (HOIG_UMMA_DEBUG, results are garbage): 1 = epilogue only drains TMEM, 2 = A tile loaded once per tile, 4 = no statistics, 8 = no output stores
 };
 
 // ------------------------------------------------------------------------ kernel
@@ -659,7 +659,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                     uint32_t pk[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) pk[j] = pack2<T>(v[2 * j], v[2 * j + 1]);
-                    if (valid) {
+                    if (valid && !(P.debug & 8)) {
                         if (full && vec_ok) {
                             *reinterpret_cast<uint4 *>(drow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                             *reinterpret_cast<uint4 *>(drow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -668,7 +668,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                                 if (n0 + j < p.Cout) DT<T>::st(drow + c0 + j, v[j]);
                         }
                     }
-                    if (p.stats) {
+                    if (p.stats && !(P.debug & 4)) {
                         if (P.mma_stats) {
                             // Column sums of the stored 16-bit values and of their squares (rounded to bf16) on the warp-level
                             // tensor-core path (umma_common.cuh colsum16): ~60 instructions instead of ~140 per chunk.

@@ -193,6 +193,22 @@ class GeneratorB200(nn.Module):
         for name, shape, kind in self._layout:
             top, rest = name.split(".", 1)
             self._modules[top].add(rest, shape)
+        # SPADE layers of one sub-network at one resolution share their segmentation input: their mlp_shared convs run as ONE GEMM
+        self._spade_group: Dict[str, List[str]] = {}
+        for net in ("obj_model", "src_model", "tsf_model"):
+            by_level: Dict[int, List[str]] = {}
+            if self.spade_layers[0]:
+                for i in range(1, self.n_down + 1):
+                    by_level.setdefault(i, []).append(f"{net}.encoders.{i}.norm.")
+            for i in range(repeat_num):
+                if self._is_spade_res(i):
+                    by_level.setdefault(self.n_down, []).extend([f"{net}.resnets.{i}.norm_0.", f"{net}.resnets.{i}.norm_1."])
+            if self.spade_layers[3]:
+                for i in range(self.n_down):
+                    by_level.setdefault(self.n_down - 1 - i, []).append(f"{net}.decoders.{i}.norm.")
+            for lst in by_level.values():
+                for q in lst:
+                    self._spade_group[q] = lst
         self._pcache: Dict[str, tuple] = {}
         self._ptable: Dict[str, torch.Tensor] = {}     # name -> Parameter, see _p()
         self._seen_epoch = -1
@@ -353,11 +369,20 @@ class GeneratorB200(nn.Module):
             if key not in seg_cache:
                 b, cs = seg_nchw.shape[:2]
                 seg_cache[key] = ops.seg_unfold3(seg_nchw.float().contiguous(), self._new(b, h, h, ceil_to(9 * cs, 64)))
-            prm = self._p(prefix + "mlp_shared.0.weight")
-            wsh = self._cached(prefix + "mlp_shared.0#u3", [prm], lambda: pack_unfolded3_weight(prm, self.compute_dtype))
-            actv = self._new(n, h, w, NHIDDEN)
-            ops.conv2d(seg_cache[key], wsh, actv, kh=1, kw=1, stride=1, pad=0, bias=self._f32(prefix + "mlp_shared.0.bias"),
-                       act=ops.ACT_RELU)
+            # ... and the mlp_shared convs of ALL SPADE layers of this sub-network at this resolution (they read the same map) run
+            # as one GEMM with N = 128 * layers on first use; each layer then takes its 128-channel slice
+            group = self._spade_group[prefix]
+            gkey = ("actv", h, group[0])
+            if gkey not in seg_cache:
+                prms = [self._p(q + "mlp_shared.0.weight") for q in group] + [self._p(q + "mlp_shared.0.bias") for q in group]
+                ng = len(group)
+                wsh, bsh = self._cached(group[0] + "mlp_shared#merged", prms, lambda: (
+                    torch.cat([pack_unfolded3_weight(t, self.compute_dtype) for t in prms[:ng]], 0).contiguous(),
+                    torch.cat([t.detach().float() for t in prms[ng:]], 0).contiguous()))
+                seg_cache[gkey] = ops.conv2d(seg_cache[key], wsh, self._new(n, h, w, NHIDDEN * ng), kh=1, kw=1, stride=1, pad=0,
+                                             bias=bsh, act=ops.ACT_RELU)
+            gi = group.index(prefix)
+            actv = seg_cache[gkey][..., gi * NHIDDEN:(gi + 1) * NHIDDEN]
         else:
             s = self._seg(seg_nchw, h, seg_cache)
             actv, _ = self._conv(s, prefix + "mlp_shared.0.weight", NHIDDEN, 3, bias=prefix + "mlp_shared.0.bias", act=ops.ACT_RELU)
@@ -673,8 +698,14 @@ class GeneratorB200(nn.Module):
             src_bg.append(src_armask)
         if tsf_armask is not None:
             tsf_bg.append(tsf_armask)
-        src_img_bg = self._bg(src_bg)
-        tsf_img_bg = self._bg(tsf_bg)
+        if len(src_bg) == len(tsf_bg):
+            # the two bg_model passes share their weights: one pass over a batch of 2B (InstanceNorm statistics are per sample)
+            both = self._bg([torch.cat([a, b], 0) for a, b in zip(src_bg, tsf_bg)])
+            nb = bg_inputs.shape[0]
+            src_img_bg, tsf_img_bg = both[:nb], both[nb:]
+        else:
+            src_img_bg = self._bg(src_bg)
+            tsf_img_bg = self._bg(tsf_bg)
         outs = self._infer_front(src_obj_inputs, tsf_obj_inputs, src_hand_inputs, tsf_hand_inputs, T.float().contiguous(),
                                  src_obj_conds, src_hand_conds, tsf_obj_conds, tsf_hand_conds)
         self._arena = None
@@ -715,10 +746,15 @@ class GeneratorB200(nn.Module):
             tx = self._warp(i + nd + 1, sx, tx, T, flows)    # (:427, :446)
         # decoders (:449-461): hand and object decoder outputs share one 2c-wide buffer per side so
         # attetion_reg_bg's cat[x, y] input is a plain view
-        s_xy, t_xy = self._new(n, H, W, 2 * c0), self._new(n, H, W, 2 * c0)
-        seg_so, seg_to = {}, {}
-        self._unet_features("obj_model", src_obj_inputs, src_obj_conds, seg_so, s_xy[..., c0:])
-        self._unet_features("obj_model", tsf_obj_inputs, tsf_obj_conds, seg_to, t_xy[..., c0:])
+        xy = self._new(2 * n, H, W, 2 * c0)
+        s_xy, t_xy = xy[:n], xy[n:]
+        # obj_model runs on the source and the target object with the same weights: one pass over a batch of 2B
+        obj_conds = None if src_obj_conds is None or tsf_obj_conds is None else torch.cat([src_obj_conds, tsf_obj_conds], 0)
+        if (src_obj_conds is None) == (tsf_obj_conds is None):
+            self._unet_features("obj_model", torch.cat([src_obj_inputs, tsf_obj_inputs], 0), obj_conds, {}, xy[..., c0:])
+        else:
+            self._unet_features("obj_model", src_obj_inputs, src_obj_conds, {}, s_xy[..., c0:])
+            self._unet_features("obj_model", tsf_obj_inputs, tsf_obj_conds, {}, t_xy[..., c0:])
         self._decode("src_model", sx, s_cats, src_hand_conds, seg_s, s_xy[..., :c0])
         self._decode("tsf_model", tx, t_cats, tsf_hand_conds, seg_t, t_xy[..., :c0])
         res = {}
