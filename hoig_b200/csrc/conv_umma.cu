@@ -81,7 +81,7 @@ struct UmmaParams {
 // pixels of A and HALF of the weight tile (BN/2 rows), the leader (cluster rank 0) issues 256 x BN x 16 MMAs that read both
 // CTAs' shared memory, and each CTA drains its own 128 TMEM lanes.  Weight traffic (L2->SM and smem writes) per CTA halves,
 // which is what bounds the wide-N convs: TMA writes and UMMA operand reads share the 128 B/clk shared-memory port.
-template <typename T, int NCTA>
+template <typename T, int NCTA, bool PERSIST>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
@@ -537,6 +537,34 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
         uint32_t e_sel[4], e_sel_bf[4];      // 0/1 selection fragments of colsum16 in the operand type / in bf16 (squares)
         colsum_select<std::is_same<T, __half>::value>(lane, e_sel);
         colsum_select<false>(lane, e_sel_bf);
+        // persistent statistics accumulators (see finalize): valid when this warp sees at most two chunks per tile and one n-tile
+        // (PERSIST kernels are launched only for statistics-producing convs with one n-tile and n_chunks <= 2 * ngrp, see launch_one)
+        constexpr bool persist = PERSIST;
+        constexpr int NSLOT = PERSIST ? 2 : 1;
+        float st_sum[NSLOT][4], st_sq[NSLOT][4];
+#pragma unroll
+        for (int sl = 0; sl < NSLOT; ++sl)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { st_sum[sl][j] = 0.f; st_sq[sl][j] = 0.f; }
+        auto dump_stats = [&]() {      // registers -> this warp's private s_stats columns, then clear
+#pragma unroll
+            for (int sl = 0; sl < NSLOT; ++sl) {
+                const int ch = half + sl * ngrp;
+                float s_lo = st_sum[sl][0] + st_sum[sl][1], s_hi = st_sum[sl][2] + st_sum[sl][3];
+                float q_lo = st_sq[sl][0] + st_sq[sl][1], q_hi = st_sq[sl][2] + st_sq[sl][3];
+                s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1); s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1);
+                q_lo += __shfl_xor_sync(0xffffffffu, q_lo, 1); q_hi += __shfl_xor_sync(0xffffffffu, q_hi, 1);
+                s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 2); s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 2);
+                q_lo += __shfl_xor_sync(0xffffffffu, q_lo, 2); q_hi += __shfl_xor_sync(0xffffffffu, q_hi, 2);
+                if (ch < n_chunks && (lane & 3) == 0) {
+                    const int col = ch * 16 + (lane >> 2);
+                    s_stats[quad][0][col] += s_lo; s_stats[quad][0][col + 8] += s_hi;
+                    s_stats[quad][1][col] += q_lo; s_stats[quad][1][col + 8] += q_hi;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { st_sum[sl][j] = 0.f; st_sq[sl][j] = 0.f; }
+            }
+        };
         const bool spade = p.spade_x != nullptr;
         float *s_mod = &s_stats[0][0][0];   // SPADE epilogue: mean[1024] | rstd[1024] (the statistics buffer is idle in that mode)
         // per-plane sum / sum of squares of the tiles since the last flush: one atomicAdd(double) per column
@@ -568,6 +596,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
             const uint32_t acc = tcount % nacc, use = tcount / nacc;
             if (n_img != cur_img || nt != cur_nt) {
                 // new (image, n-tile): hand the finished plane's statistics over and reload the bias slice
+                if (persist && cur_img >= 0) dump_stats();
                 epi_bar(epi_threads);                   // every warp is done with the previous tiles' s_stats / s_bias
                 if (p.stats && cur_img >= 0) flush_stats(cur_img, cur_nt);
                 if (spade && n_img != cur_img) {        // instance-norm constants of the modulated tensor's planes of this image
@@ -594,7 +623,8 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)BN;
             uint32_t ra[16], rb[16];
-            auto finalize = [&](const uint32_t (&r)[16], int ch) {
+            auto finalize = [&](const uint32_t (&r)[16], int ch, auto slot_tag) {
+                constexpr int slot = decltype(slot_tag)::value;      // which of this warp's (up to two) persistent statistics slots
                 const int c0 = ch * 16;
                     const int n0 = nt * BN + c0;
                     if (n0 >= p.Cout) return;     // warp-uniform: padded output channels
@@ -659,7 +689,25 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                     uint32_t pk[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) pk[j] = pack2<T>(v[2 * j], v[2 * j + 1]);
-                    if (valid && !(P.debug & 8)) {
+                    if (full && vec_ok && all_valid && !(P.debug & 8)) {
+                        // Lane pairs swap one 16-byte piece so that the two lanes of a pair write the 32 contiguous bytes of ONE row per
+                        // instruction (first the even lane's row, then the odd lane's): a store instruction then touches 16 lines
+                        // with a full 32-byte sector each instead of 32 lines with half a sector -- half the LSU wavefronts.
+                        const bool odd = lane & 1;
+                        uint32_t keep[4], got[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t send = odd ? pk[j] : pk[4 + j];
+                            keep[j] = odd ? pk[4 + j] : pk[j];
+                            got[j] = __shfl_xor_sync(0xffffffffu, send, 1);
+                        }
+                        T *own = drow + c0 + (odd ? 8 : 0);
+                        const uint64_t oth_bits = __shfl_xor_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(drow), 1);
+                        T *oth = reinterpret_cast<T *>((uintptr_t)oth_bits) + c0 + (odd ? 8 : 0);
+                        // even lane: row r <- own piece 0, row r+1 <- partner's piece 0;  odd lane: row r-1 <- partner's piece 1, row r <- own piece 1
+                        *reinterpret_cast<uint4 *>(odd ? oth : own) = odd ? make_uint4(got[0], got[1], got[2], got[3]) : make_uint4(keep[0], keep[1], keep[2], keep[3]);
+                        *reinterpret_cast<uint4 *>(odd ? own : oth) = odd ? make_uint4(keep[0], keep[1], keep[2], keep[3]) : make_uint4(got[0], got[1], got[2], got[3]);
+                    } else if (valid && !(P.debug & 8)) {
                         if (full && vec_ok) {
                             *reinterpret_cast<uint4 *>(drow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                             *reinterpret_cast<uint4 *>(drow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -675,12 +723,16 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                             constexpr bool kF16 = std::is_same<T, __half>::value;
                             uint32_t sq[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                if (!all_valid && !valid) pk[j] = 0u;
-                                float lo, hi;
-                                unpack2<T>(pk[j], lo, hi);
-                                sq[j] = pack2<__nv_bfloat16>(lo * lo, hi * hi);
+                            for (int j = 0; j < 8; ++j) {     // squares of the fp32 values, rounded to bf16 (range of fp32)
+                                if (!all_valid && !valid) { pk[j] = 0u; v[2 * j] = 0.f; v[2 * j + 1] = 0.f; }
+                                sq[j] = pack2<__nv_bfloat16>(v[2 * j] * v[2 * j], v[2 * j + 1] * v[2 * j + 1]);
                             }
+                            if (persist) {
+                                // narrow tiles: this warp owns the same (at most two) 16-column chunks on every tile, so the warp-level
+                                // MMAs keep accumulating in registers; shuffles + shared-memory adds happen once per image (dump_stats)
+                                colsum16_acc<kF16>(pk, e_sel, st_sum[slot < NSLOT ? slot : 0]);
+                                colsum16_acc<false>(sq, e_sel_bf, st_sq[slot < NSLOT ? slot : 0]);
+                            } else {
                             float s_lo, s_hi, q_lo, q_hi;
                             colsum16<kF16>(pk, e_sel, s_lo, s_hi);
                             colsum16<false>(sq, e_sel_bf, q_lo, q_hi);
@@ -688,6 +740,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                                 const int col = c0 + (lane >> 2);
                                 s_stats[quad][0][col] += s_lo; s_stats[quad][0][col + 8] += s_hi;
                                 s_stats[quad][1][col] += q_lo; s_stats[quad][1][col + 8] += q_hi;
+                            }
                             }
                         } else {
                         // Statistics of the fp32 values (before the 16-bit store rounding); rows past the end of the plane
@@ -716,11 +769,11 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
             for (int ch = half; ch < n_chunks; ch += 2 * ngrp) {
                 tmem_ld_wait(ra);
                 if (ch + ngrp < n_chunks) tmem_ld16(t_row + (uint32_t)((ch + ngrp) * 16), rb);
-                finalize(ra, ch);
+                finalize(ra, ch, std::integral_constant<int, 0>());
                 if (ch + ngrp < n_chunks) {
                     tmem_ld_wait(rb);
                     if (ch + 2 * ngrp < n_chunks) tmem_ld16(t_row + (uint32_t)((ch + 2 * ngrp) * 16), ra);
-                    finalize(rb, ch + ngrp);
+                    finalize(rb, ch + ngrp, std::integral_constant<int, 1>());
                 }
             }
             }
@@ -730,6 +783,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
             else mbar_arrive(tempty0 + 8u * acc);
         }
         if (p.stats && cur_img >= 0) {   // the last plane this CTA touched
+            if (persist) dump_stats();
             epi_bar(epi_threads);
             flush_stats(cur_img, cur_nt);
         }
@@ -755,12 +809,12 @@ int g_bres_mode = 1;        // HOIG_UMMA_BRES: resident weights for small weight
 int g_dual_mode = 1;        // 1: narrow-N TMA convs run two MMA issue pipelines per CTA (HOIG_UMMA_DUAL=0 disables)
 int g_pair_mode = 1;        // 0: one CTA per tile; 1: CTA pairs (cta_group::2) where they pay off; 2: pairs wherever legal (tests)
 
-template <typename T, int NCTA>
+template <typename T, int NCTA, bool PERSIST>
 int launch_kernel(const UmmaParams &P, const CUtensorMap &map_w, const CUtensorMap *map_a, int grid, size_t smem, cudaStream_t stream)
 {
-    constexpr int slot = (std::is_same<T, __half>::value ? SLOT_CONV_UMMA_F16_1 : SLOT_CONV_UMMA_BF16_1) + (NCTA - 1);
+    constexpr int slot = (std::is_same<T, __half>::value ? SLOT_CONV_UMMA_F16_1 : SLOT_CONV_UMMA_BF16_1) + 2 * (NCTA - 1) + (PERSIST ? 1 : 0);
     if (first_use_on_device(slot) &&
-        cudaFuncSetAttribute(conv_umma_kernel<T, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess)
+        cudaFuncSetAttribute(conv_umma_kernel<T, NCTA, PERSIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess)
         return check_launch("conv_umma smem attribute");
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -773,7 +827,7 @@ int launch_kernel(const UmmaParams &P, const CUtensorMap &map_w, const CUtensorM
     attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = NCTA > 1 ? 1 : 0;
-    if (cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, NCTA>, P, map_w, map_a[0], map_a[1], map_a[2], map_a[3]) != cudaSuccess)
+    if (cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, NCTA, PERSIST>, P, map_w, map_a[0], map_a[1], map_a[2], map_a[3]) != cudaSuccess)
         return check_launch("conv_umma_kernel launch");
     return check_launch("conv_umma_kernel");
 }
@@ -866,10 +920,20 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     const int units = num_sms / ncta;                       // CTAs or CTA pairs that fit the GPU
     const int grid = (total < units ? total : units) * ncta;
     const size_t smem = (size_t)STG_BYTES + (size_t)P.stages * stage_bytes + (P.bres ? w_bytes : 0) + 1024;
-    if (dtype == HOIG_F16)
-        return ncta == 2 ? launch_kernel<__half, 2>(P, map_w, map_a, grid, smem, stream) : launch_kernel<__half, 1>(P, map_w, map_a, grid, smem, stream);
-    return ncta == 2 ? launch_kernel<__nv_bfloat16, 2>(P, map_w, map_a, grid, smem, stream)
-                     : launch_kernel<__nv_bfloat16, 1>(P, map_w, map_a, grid, smem, stream);
+    // persistent register statistics: at most two 16-column chunks per epilogue warp, one n-tile, MMA column sums enabled
+    const int ngrp = P.tma_a ? 4 : 3;
+    const bool persist = p.stats && P.mma_stats && P.n_tiles == 1 && P.BN / 16 <= 2 * ngrp && !p.spade_x;
+    auto go = [&](auto tag, auto nc, auto ps) {
+        using T = std::remove_pointer_t<decltype(tag)>;
+        return launch_kernel<T, decltype(nc)::value, decltype(ps)::value>(P, map_w, map_a, grid, smem, stream);
+    };
+    auto pick_ps = [&](auto tag, auto nc) {
+        return persist ? go(tag, nc, std::true_type()) : go(tag, nc, std::false_type());
+    };
+    auto pick_nc = [&](auto tag) {
+        return ncta == 2 ? pick_ps(tag, std::integral_constant<int, 2>()) : pick_ps(tag, std::integral_constant<int, 1>());
+    };
+    return dtype == HOIG_F16 ? pick_nc((__half *)nullptr) : pick_nc((__nv_bfloat16 *)nullptr);
 }
 
 }  // namespace

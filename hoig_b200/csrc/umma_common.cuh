@@ -262,6 +262,15 @@ __device__ __forceinline__ void colsum_select(int lane, uint32_t (&e)[4])
 #pragma unroll
     for (int i = 0; i < 4; ++i) e[i] = (g == 2 * i ? one : 0u) | (g == 2 * i + 1 ? one << 16 : 0u);
 }
+// the four MMAs of colsum16 accumulating into a caller-held fragment (reduce later: lo = d0 + d1, hi = d2 + d3, then the two shuffles)
+template <bool F16>
+__device__ __forceinline__ void colsum16_acc(const uint32_t (&pk)[8], const uint32_t (&e)[4], float (&d)[4])
+{
+    hmma_16816<F16>(d, e[0], 0u, e[1], 0u, pk[0], pk[1]);
+    hmma_16816<F16>(d, e[2], 0u, e[3], 0u, pk[2], pk[3]);
+    hmma_16816<F16>(d, 0u, e[0], 0u, e[1], pk[4], pk[5]);
+    hmma_16816<F16>(d, 0u, e[2], 0u, e[3], pk[6], pk[7]);
+}
 template <bool F16>
 __device__ __forceinline__ void colsum16(const uint32_t (&pk)[8], const uint32_t (&e)[4], float &lo, float &hi)
 {
