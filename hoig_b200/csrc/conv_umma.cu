@@ -72,6 +72,8 @@ struct UmmaParams {
                          //    L2->SM path (~42 B/clk/SM), not the tensor pipe, is the bound, and weights are 1/3 of that traffic.
     int dual;            // 1: two independent pipelines per CTA (narrow N): tiles alternate between two MMA-issuing warps,
                          //    each with its own half of the smem ring and two of the four TMEM accumulator stages
+    int early_release;   // epilogue: hand the accumulator stage back right after the last tcgen05.ld (HOIG_UMMA_EARLY_RELEASE)
+    int relaxed_release; // epilogue: relaxed (signal-only) arrival on the accumulator barrier (HOIG_UMMA_RELAXED_RELEASE)
     int debug;           // timing knock-outs (HOIG_UMMA_DEBUG, results are garbage): 1 = epilogue only drains TMEM, 2 = A tile loaded once per tile, 4 = no statistics, 8 = no output stores
 };
 
@@ -765,19 +767,39 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                 for (int ch = half; ch < n_chunks; ch += ngrp) { tmem_ld16(t_row + (uint32_t)(ch * 16), ra); tmem_ld_wait(ra); }
                 if (ra[0] == 0x7fc12345u && valid) dst[m * p.ldd] = T(0);
             } else {
+            // HOIG_UMMA_EARLY_RELEASE (P.early_release): 1 = the accumulator stage goes back to the MMA warp as soon as this warp's LAST
+            // tcgen05.ld has landed in registers (before the arithmetic and stores of that chunk), 0 = after the whole tile.  Either
+            // way the arrival is relaxed: it only signals, so nothing waits for the outstanding global stores.
+            auto release = [&]() {
+                tc_fence_before();
+                if (NCTA == 2) mbar_arrive_cluster_relaxed(tempty0 + 8u * acc);
+                else mbar_arrive_relaxed(tempty0 + 8u * acc);
+            };
+            const bool early = P.early_release != 0;
             if (half < n_chunks) tmem_ld16(t_row + (uint32_t)(half * 16), ra);
+            else if (early) release();
             for (int ch = half; ch < n_chunks; ch += 2 * ngrp) {
                 tmem_ld_wait(ra);
-                if (ch + ngrp < n_chunks) tmem_ld16(t_row + (uint32_t)((ch + ngrp) * 16), rb);
+                const bool more1 = ch + ngrp < n_chunks;
+                if (more1) tmem_ld16(t_row + (uint32_t)((ch + ngrp) * 16), rb);
+                else if (early) release();
                 finalize(ra, ch, std::integral_constant<int, 0>());
-                if (ch + ngrp < n_chunks) {
+                if (more1) {
                     tmem_ld_wait(rb);
-                    if (ch + 2 * ngrp < n_chunks) tmem_ld16(t_row + (uint32_t)((ch + 2 * ngrp) * 16), ra);
+                    const bool more2 = ch + 2 * ngrp < n_chunks;
+                    if (more2) tmem_ld16(t_row + (uint32_t)((ch + 2 * ngrp) * 16), ra);
+                    else if (early) release();
                     finalize(rb, ch + ngrp, std::integral_constant<int, 1>());
                 }
             }
+            if (!early) {
+                tc_fence_before();
+                if (P.early_release == 0 && P.relaxed_release) { if (NCTA == 2) mbar_arrive_cluster_relaxed(tempty0 + 8u * acc); else mbar_arrive_relaxed(tempty0 + 8u * acc); }
+                else { if (NCTA == 2) mbar_arrive_cluster(tempty0 + 8u * acc); else mbar_arrive(tempty0 + 8u * acc); }
             }
-            // accumulator drained: hand the TMEM stage back to the MMA warp
+            continue;
+            }
+            // (debug drain path) accumulator drained: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             if (NCTA == 2) mbar_arrive_cluster(tempty0 + 8u * acc);
             else mbar_arrive(tempty0 + 8u * acc);
@@ -804,6 +826,8 @@ int g_umma_debug = 0;
 int g_contig_mode = 1;      // HOIG_UMMA_CONTIG
 int g_mma_stats = 1;        // HOIG_UMMA_MMA_STATS
 int g_halo_mode = 1;        // HOIG_UMMA_HALO: row-halo activation reuse for full-row tiles
+int g_early_release = 0;    // HOIG_UMMA_EARLY_RELEASE
+int g_relaxed_release = 1;  // HOIG_UMMA_RELAXED_RELEASE
 int g_vhalo_mode = 1;       // HOIG_UMMA_VHALO: vertical-halo activation reuse for kh x 1 convs
 int g_bres_mode = 1;        // HOIG_UMMA_BRES: resident weights for small weight matrices
 int g_dual_mode = 1;        // 1: narrow-N TMA convs run two MMA issue pipelines per CTA (HOIG_UMMA_DUAL=0 disables)
@@ -889,6 +913,8 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     HOIG_REQUIRE(P.stages >= (P.tma_a ? 2 : LOOKAHEAD + 1), "conv2d: not enough shared memory stages");
 
     P.debug = g_umma_debug;
+    P.early_release = g_early_release;
+    P.relaxed_release = g_relaxed_release;
     P.tpi_shift = -1;
     if ((p.tiles_per_image & (p.tiles_per_image - 1)) == 0) { P.tpi_shift = 0; while ((1 << P.tpi_shift) < p.tiles_per_image) ++P.tpi_shift; }
 
@@ -954,6 +980,10 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
         if (ms) g_mma_stats = atoi(ms);
         const char *hm = getenv("HOIG_UMMA_HALO");
         if (hm) g_halo_mode = atoi(hm);
+        const char *er = getenv("HOIG_UMMA_EARLY_RELEASE");
+        if (er) g_early_release = atoi(er);
+        const char *rr = getenv("HOIG_UMMA_RELAXED_RELEASE");
+        if (rr) g_relaxed_release = atoi(rr);
         const char *vm = getenv("HOIG_UMMA_VHALO");
         if (vm) g_vhalo_mode = atoi(vm);
         const char *bm = getenv("HOIG_UMMA_BRES");

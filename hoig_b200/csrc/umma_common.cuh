@@ -115,6 +115,16 @@ __device__ __forceinline__ void cluster_sync()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Relaxed arrivals: they only SIGNAL (no memory ordering), so the arriving warp does not wait for its outstanding global stores.
+// Used to hand a TMEM accumulator stage back once tcgen05.wait::ld has put its contents into registers.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
 {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
