@@ -98,7 +98,7 @@ conv_simt_kernel(const ConvParams p)
             if (p.phase_cout) {                   // transposed conv: column = phase * Cout + channel
                 const int ph = ng / p.phase_cout;
                 n = ng - ph * p.phase_cout;
-                m = m0 + (int64_t)(ph >> 1) * p.OWf + (ph & 1);
+                m = m0 + (int64_t)(ph >> 1) * p.OWf + ((ph & 1) ^ (ph >> 1));   // block order (0,0),(0,1),(1,1),(1,0)
             }
             float val = acc[i][j];
             if (p.bias) val += p.bias[n];

@@ -72,6 +72,9 @@ struct UmmaParams {
                          //    L2->SM path (~42 B/clk/SM), not the tensor pipe, is the bound, and weights are 1/3 of that traffic.
     int dual;            // 1: two independent pipelines per CTA (narrow N): tiles alternate between two MMA-issuing warps,
                          //    each with its own half of the smem ring and two of the four TMEM accumulator stages
+    uint8_t tap_live[16]; // transposed conv: per n-tile, bit t set = tap t of the 2x2 input neighbourhood feeds some parity block of the tile;
+                         //    dead (n-tile, tap) k-blocks are skipped by the producers and the MMA issuer (their weight blocks are zero)
+    int tap_skip;        // 1: tap_live is in use (TMA-fed transposed conv)
     int early_release;   // epilogue: hand the accumulator stage back right after the last tcgen05.ld (HOIG_UMMA_EARLY_RELEASE)
     int relaxed_release; // epilogue: relaxed (signal-only) arrival on the accumulator barrier (HOIG_UMMA_RELAXED_RELEASE)
     int debug;           // timing knock-outs (HOIG_UMMA_DEBUG, results are garbage): 1 = epilogue only drains TMEM, 2 = A tile loaded once per tile, 4 = no statistics, 8 = no output stores
@@ -336,6 +339,47 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                             if (++q[w] == sp) { q[w] = 0; ph[w] ^= 1u; }
                         }
                     }
+                } else if (P.tap_skip) {
+                    // transposed conv: same loop, minus the (n-tile, tap) k-blocks whose weight blocks are structurally zero
+                    const int lmask[2] = {P.tap_live[nt[0]], P.tap_live[NP > 1 ? nt[1] : nt[0]]};
+                    for (int kb = 0; kb < P.k_blocks; ++kb) {
+                        const int tt = tap < p.ntaps ? tap : p.ntaps - 1;   // K padding blocks: any finite data (weights are zero)
+                        for (int w = 0; w < NP; ++w) {
+                            if (!live[w] || !((lmask[w] >> tt) & 1)) continue;
+                            // ring position / phase kept incrementally: a runtime division per k-block on this single
+                            // thread costs more than the MMAs of a short k-block
+                            const uint32_t st = q[w] * (uint32_t)NP + (uint32_t)w;
+                            mbar_wait(empty0 + 8u * st, ph[w] ^ 1u);
+                            const uint32_t bar = full0 + 8u * st;
+                            const uint32_t a_dst = smem_base + st * (uint32_t)stage_bytes;
+                            if (do_a) {
+                                const bool skip_a = NCTA == 1 && (P.debug & 2) && kb > 0;
+                                if (elect_one()) {
+                                    if (skip_a) {
+                                        mbar_arrive(bar);
+                                    } else if (NCTA == 2) {
+                                        if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[0]) + 8u * st, 2u * (uint32_t)A_STAGE_BYTES);
+                                        tma_load_4d_2sm(a_dst, maps[p.tap_map[tt]], bar, c, gx0[w] + p.tap_dx[tt], gy0[w] + p.tap_dy[tt], n_img[w]);
+                                    } else {
+                                        mbar_arrive_expect_tx(bar, (uint32_t)A_STAGE_BYTES);
+                                        tma_load_4d(a_dst, maps[p.tap_map[tt]], bar, c, gx0[w] + p.tap_dx[tt], gy0[w] + p.tap_dy[tt], n_img[w]);
+                                    }
+                                }
+                            } else if (elect_one()) {
+                                if (NCTA == 2) {
+                                    if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[0]) + 8u * st, b_bytes);
+                                    tma_load_2d_2sm(a_dst + A_STAGE_BYTES, &map_w, bar, kb * BK, nt[w] * BN + (int)(rank * b_rows));
+                                } else {
+                                    mbar_arrive_expect_tx(bar, b_bytes);
+                                    tma_load_2d(a_dst + A_STAGE_BYTES, &map_w, bar, kb * BK, nt[w] * BN);
+                                }
+                            }
+                            __syncwarp();
+                            if (++q[w] == sp) { q[w] = 0; ph[w] ^= 1u; }
+                        }
+                        c += BK;
+                        if (c >= p.Cin) { c = 0; ++tap; }
+                    }
                 } else if (!P.halo) {
                     for (int kb = 0; kb < P.k_blocks; ++kb) {
                         const int tt = tap < p.ntaps ? tap : p.ntaps - 1;   // K padding blocks: any finite data (weights are zero)
@@ -461,6 +505,34 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                             }
                             __syncwarp();
                         }
+                        if (++q == sp) { q = 0; ph ^= 1u; }
+                    }
+                } else if (P.tap_skip) {
+                    // transposed conv: skip the (n-tile, tap) k-blocks the producers skipped (tap 0 is always live, so kb = 0 initialises)
+                    const int tile = tile0 + (int)i * tile_step;
+                    const int live_mask = P.tap_live[P.n_tiles > 1 ? tile % P.n_tiles : 0];
+                    const int cin_blocks = p.Cin / BK;
+                    int tap = 0, cb = 0;
+                    for (int kb = 0; kb < P.k_blocks; ++kb) {
+                        const int t = tap;
+                        if (++cb == cin_blocks) { cb = 0; ++tap; }
+                        if (!((live_mask >> t) & 1)) continue;
+                        const uint32_t st = q * (uint32_t)NP + (uint32_t)w;
+                        mbar_wait(full0 + 8u * st, ph);
+                        tc_fence_after();
+                        const uint64_t da = desc0 + (uint64_t)(st * stage16);
+                        const uint64_t db = P.bres ? bres_desc + (uint64_t)((uint32_t)kb * (uint32_t)(BN * 8)) : da + (uint64_t)(A_STAGE_BYTES >> 4);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) {
+                                if (NCTA == 2) umma_bf16_2sm(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                                else umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                            }
+                            // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+                            if (NCTA == 2) umma_commit_2sm(empty0 + 8u * st);
+                            else umma_commit(empty0 + 8u * st);
+                        }
+                        __syncwarp();
                         if (++q == sp) { q = 0; ph ^= 1u; }
                     }
                 } else if (!P.halo) {
@@ -635,7 +707,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                     if (pc) {   // output parity (a,b) = phase: pixel (2gy+a, 2gx+b), channel n0 - phase*pc
                         const int ph = n0 / pc;
                         ncol = n0 - ph * pc;
-                        mm = m + (int64_t)(ph >> 1) * p.OWf + (ph & 1);
+                        mm = m + (int64_t)(ph >> 1) * p.OWf + ((ph & 1) ^ (ph >> 1));   // parity blocks are ordered (0,0),(0,1),(1,1),(1,0)
                     }
                     T *drow = dst + mm * p.ldd + ncol - c0;
                     const T *rrow = res ? res + mm * p.ldr + ncol - c0 : nullptr;
@@ -826,6 +898,7 @@ int g_umma_debug = 0;
 int g_contig_mode = 1;      // HOIG_UMMA_CONTIG
 int g_mma_stats = 1;        // HOIG_UMMA_MMA_STATS
 int g_halo_mode = 1;        // HOIG_UMMA_HALO: row-halo activation reuse for full-row tiles
+int g_tap_skip_mode = 1;    // HOIG_UMMA_TAP_SKIP: transposed convs skip (n-tile, tap) k-blocks whose weight blocks are structurally zero
 int g_early_release = 0;    // HOIG_UMMA_EARLY_RELEASE
 int g_relaxed_release = 1;  // HOIG_UMMA_RELAXED_RELEASE
 int g_vhalo_mode = 1;       // HOIG_UMMA_VHALO: vertical-halo activation reuse for kh x 1 convs
@@ -912,6 +985,25 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     if (P.dual) P.stages &= ~1;
     HOIG_REQUIRE(P.stages >= (P.tma_a ? 2 : LOOKAHEAD + 1), "conv2d: not enough shared memory stages");
 
+    // transposed conv: which taps feed which n-tile (packing.parity_block order (0,0),(0,1),(1,1),(1,0); tap (dy,dx) feeds (a,b) iff
+    // dy <= a and dx <= b)
+    P.tap_skip = 0;
+    memset(P.tap_live, 0xff, sizeof(P.tap_live));
+    if (g_tap_skip_mode && p.phase_cout > 0 && P.tma_a && p.ntaps == 4 && P.n_tiles <= 16 && p.Cin % BK == 0) {
+        P.tap_skip = 1;
+        for (int nt = 0; nt < P.n_tiles; ++nt) {
+            const int j0 = (nt * P.BN) / p.phase_cout;
+            int j1 = ((nt + 1) * P.BN - 1) / p.phase_cout;
+            if (j1 > 3) j1 = 3;
+            uint8_t mask = 0;
+            for (int j = j0; j <= j1; ++j) {
+                const int a = j >> 1, b = (j & 1) ^ (j >> 1);
+                for (int t = 0; t < 4; ++t)
+                    if ((t >> 1) <= a && (t & 1) <= b) mask |= (uint8_t)(1u << t);
+            }
+            P.tap_live[nt] = mask;
+        }
+    }
     P.debug = g_umma_debug;
     P.early_release = g_early_release;
     P.relaxed_release = g_relaxed_release;
@@ -980,6 +1072,8 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
         if (ms) g_mma_stats = atoi(ms);
         const char *hm = getenv("HOIG_UMMA_HALO");
         if (hm) g_halo_mode = atoi(hm);
+        const char *ts = getenv("HOIG_UMMA_TAP_SKIP");
+        if (ts) g_tap_skip_mode = atoi(ts);
         const char *er = getenv("HOIG_UMMA_EARLY_RELEASE");
         if (er) g_early_release = atoi(er);
         const char *rr = getenv("HOIG_UMMA_RELAXED_RELEASE");

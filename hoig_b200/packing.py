@@ -5,8 +5,9 @@ consume a K-major matrix ``Wp[Cout_pad16][cols]``:
 
 * ``nn.Conv2d`` (and the local-attention k5s5 conv): ``k = (r*KW + s)*Cin_pad + c``, padded to 64 columns
   (``Cin_pad`` = Cin rounded up to 8, matching the zero-padded NHWC activations);
-* ``nn.ConvTranspose2d`` (k3 s2 p1 op1): ``[4*Cout][4*Cin_pad]`` -- row block (a,b) = output parity, column
-  block (dy,dx) = input tap of the 2x2 neighbourhood; blocks a parity does not use are zero (``csrc/conv_plan.cu``).
+* ``nn.ConvTranspose2d`` (k3 s2 p1 op1): ``[4*Cout][4*Cin_pad]`` -- row block = output parity (a,b) in the order
+  (0,0), (0,1), (1,1), (1,0) (``parity_block``), column block (dy,dx) = input tap of the 2x2 neighbourhood; blocks a parity does
+  not use are zero (``csrc/conv_plan.cu``) and are skipped by the tensor-core kernel.
 
 Packed copies are derived caches.
 """
@@ -17,6 +18,13 @@ import torch
 
 def ceil_to(x: int, m: int) -> int:
     return (x + m - 1) // m * m
+
+
+def parity_block(a: int, b: int) -> int:
+    """Row block of output parity (a, b) in the packed transposed-conv matrix: order (0,0), (0,1), (1,1), (1,0).  Tap (dy, dx) of
+    the 2x2 input neighbourhood feeds parity (a, b) only if dy <= a and dx <= b, so in this order the blocks every tap feeds are
+    CONTIGUOUS ([0,4), [1,3), [2,4), [2,3)) and the kernel can skip the dead (n-tile, tap) combinations (csrc/conv_umma.cu)."""
+    return a * 2 + (b ^ a)
 
 
 def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, transposed: bool = False, pad: int = 1) -> torch.Tensor:
@@ -41,7 +49,7 @@ def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, transposed: bool = Fal
                 for dx in (0, 1):
                     r, s_ = a + pad - 2 * dy, b + pad - 2 * dx
                     if 0 <= r < kh and 0 <= s_ < kw:
-                        ph, t = a * 2 + b, dy * 2 + dx
+                        ph, t = parity_block(a, b), dy * 2 + dx
                         out[ph * cout:(ph + 1) * cout, t * cin_p:t * cin_p + cin] = w[:, :, r, s_].t()
     return out.to(dtype).contiguous()
 

@@ -35,7 +35,7 @@ def unpack_transposed(wp, cout, kh, kw, cin_p, pad):
                 for dx in (0, 1):
                     r, s_ = a + pad - 2 * dy, b + pad - 2 * dx
                     if 0 <= r < kh and 0 <= s_ < kw:
-                        ph, t = a * 2 + b, dy * 2 + dx
+                        ph, t = a * 2 + (b ^ a), dy * 2 + dx        # packing.parity_block
                         w[:, :, r, s_] = wp.float()[ph * cout:(ph + 1) * cout, t * cin_p:(t + 1) * cin_p]
     return w
 
