@@ -93,6 +93,9 @@ _SIGNATURES = {
                                  c_int, c_int, c_void_p]),
     "hoig_block_extract_backward_f32": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
     "hoig_local_attn_reshape_backward_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "hoig_conv2d_wgrad_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p] + [c_int] * 12 + [c_void_p]),
+    "hoig_instnorm_backward_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                           c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "hoig_condition_inputs": (c_int, [POINTER(CondInputsDesc), c_void_p]),
     "hoig_uv_backward_warp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "hoig_sample_texture_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libhoig_b200.so")
-SOURCES = ["api.cu", "rasterize.cu", "ops.cu", "conv_plan.cu", "conv_simt.cu", "conv_umma.cu", "conv_halo.cu"]
+SOURCES = ["api.cu", "rasterize.cu", "ops.cu", "conv_plan.cu", "conv_simt.cu", "conv_umma.cu", "conv_halo.cu", "train.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

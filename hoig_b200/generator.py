@@ -650,7 +650,8 @@ class GeneratorB200(nn.Module):
         """generator.py:347-376.  Inputs NCHW fp32 CUDA tensors, ``T`` (B,H,W,2); returns the
         reference's 10-tuple of NCHW fp32 tensors.
 
-        Inference (no gradient required): the schedule of sm_100a kernels below.  Repeated calls with the same input shapes
+        ``train()`` mode with autograd enabled runs the differentiable fp32 path (``hoig_b200.training.generator_forward_train``).
+        Inference (``eval()`` mode or ``torch.no_grad()``): the schedule of sm_100a kernels below.  Repeated calls with the same input shapes
         and unchanged weights are served by ONE captured CUDA graph from the third call on (``auto_graph``; ~360 launches
         become one replay, which is what makes batch 1 -- the eval.py case -- run at kernel speed instead of host speed);
         the results are copied out of the graph's static buffers, so they behave like the eager ones."""
@@ -660,6 +661,12 @@ class GeneratorB200(nn.Module):
                       src_armask=src_armask, tsf_armask=tsf_armask)
         if not bg_inputs.is_cuda:
             raise RuntimeError("GeneratorB200: inputs must be CUDA tensors (hoig_b200 has no CPU path)")
+        if self.training and torch.is_grad_enabled():
+            # train() mode with autograd on: the differentiable fp32 schedule (hoig_b200.training, row N3) -- train.py's use.
+            # eval() mode or torch.no_grad(): the fused 16-bit inference schedule below -- eval.py's use.
+            from .training import generator_forward_train
+            with torch.cuda.device(bg_inputs.device):
+                return generator_forward_train(self, **inputs)
         with torch.cuda.device(bg_inputs.device), torch.no_grad():
             if self.auto_graph and not ops._lib.recorder.timing and not torch.cuda.is_current_stream_capturing():
                 return self._forward_auto_graph(inputs)

@@ -305,6 +305,25 @@ int hoig_hfold_nchw(const void *z, int64_t ldz, int dtype, int B, int H, int W, 
 int hoig_composite(const float *img_bg, const float *obj, const float *hand, const float *mask_bg,
                    const float *mask_hand, float *out, int B, int HW, hoigStream_t stream);
 
+
+/* ----------------------------------------------------------------- training (row N3, fp32)
+ * The reference trains through torch.autograd of nn.Conv2d / nn.ConvTranspose2d / nn.InstanceNorm2d (models/networks/generator.py,
+ * discriminator.py; step: models/trainer.py:417-434).  Here the data gradient of a convolution is itself a convolution and runs on
+ * hoig_conv2d (hoig_b200/autograd.py); the two entry points below are the pieces that have no forward equivalent.
+ *
+ * hoig_conv2d_wgrad_f32: dW[co][r][s][ci] += sum_{n,oy,ox} g[n,oy,ox,co] * x[n, oy*stride + r - pad_h, ox*stride + s - pad_w, ci]
+ *   x (N,H,W,Cin) / g (N,OH,OW,Cout) NHWC f32 with pixel strides ldx / ldg (multiples of 4); dW dense [Cout][KH][KW][Cin] f32 that
+ *   the caller zero-fills (the kernel accumulates with atomics, like the reference's float-atomic backward kernels).
+ *   nn.ConvTranspose2d: call it with the roles swapped (x := grad_out, g := input, the transposed conv's stride / padding).
+ * hoig_instnorm_backward_f32: backward of y = gamma * (x - mean) * rstd + beta per (n, c) plane (biased variance, eps as forward):
+ *   stats = the forward's double [N][C][2] (sum, sum of squares) of x; scratch = double [N][C][2] zero-filled by the caller;
+ *   dx (N,HW,C); dgamma / dbeta (C) f32 accumulated (both NULL for affine=False, gamma NULL = 1). */
+int hoig_conv2d_wgrad_f32(const float *x, int64_t ldx, const float *g, int64_t ldg, float *dw, int N, int H, int W, int Cin,
+                          int OH, int OW, int Cout, int KH, int KW, int stride, int pad_h, int pad_w, hoigStream_t stream);
+int hoig_instnorm_backward_f32(const float *x, int64_t ldx, const float *gy, int64_t ldg, const double *stats, const float *gamma,
+                               float *dx, int64_t lddx, double *scratch, float *dgamma, float *dbeta, int N, int HW, int C,
+                               float eps, hoigStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

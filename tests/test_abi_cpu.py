@@ -106,6 +106,9 @@ def test_packing_layout():
     assert pt.shape == (16, 64)                            # 4 parities x Cout=2 rows (pad 16), 4 taps x Cin_pad=8 cols (pad 64)
     assert pt[0 * 2 + 1, 0 * 8 + 2] == wt[2, 1, 1, 1]      # parity (0,0) uses only tap (0,0) with the centre weight
     assert pt[0 * 2 + 1, 8:].abs().sum() == 0
-    assert pt[3 * 2 + 1, (1 * 2 + 0) * 8 + 2] == wt[2, 1, 0, 2]   # parity (1,1), tap (dy,dx)=(1,0): kernel index (0,2)
+    from hoig_b200.packing import parity_block
+    assert [parity_block(a, b) for a in (0, 1) for b in (0, 1)] == [0, 1, 3, 2]     # row blocks ordered (0,0),(0,1),(1,1),(1,0)
+    assert pt[2 * 2 + 1, (1 * 2 + 0) * 8 + 2] == wt[2, 1, 0, 2]   # parity (1,1) = block 2, tap (dy,dx)=(1,0): kernel index (0,2)
+    assert pt[3 * 2 + 1, (0 * 2 + 1) * 8:(0 * 2 + 2) * 8].abs().sum() == 0        # parity (1,0) = block 3 never uses a dx = 1 tap
     from tests.emu_ops import unpack_transposed
     assert torch.equal(unpack_transposed(pt, 2, 3, 3, 8, 1)[:, :3], wt.permute(1, 0, 2, 3))

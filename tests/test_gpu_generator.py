@@ -249,7 +249,7 @@ def test_batch_slot_isolation_f16():
     sd = gr.init_state_dict(seed=0, jitter=0.05, **SMALL, **TABLE["generator_spade_attn"])
     g = create("generator_spade_attn", dtype=torch.float16, **SMALL)
     g.load_state_dict(sd)
-    g = g.cuda()
+    g = g.cuda().eval()
     inp4 = {k: v.cuda() for k, v in synth.generator_inputs(4, seed=2, size=64).items()}
     inp1 = {k: v[2:3].contiguous() for k, v in inp4.items()}
     o4, o1 = g(**inp4), g(**inp1)

@@ -1,0 +1,169 @@
+"""Training path (rows N3 / N4): autograd Functions over the C ABI against torch.autograd of the same ops, the differentiable
+generator forward against the oracle port under autograd, the PatchGAN discriminator against the reference module's math, and one
+generator + discriminator step."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from hoig_b200 import autograd as ag
+from hoig_b200 import synth
+from hoig_b200.generator import create
+from hoig_b200.training import PatchDiscriminatorB200, TrainStep, generator_forward_train
+from oracle import generator_ref as gr
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(bg_dim=8, img_dim=3, obj_dim=3, img_cond_dim=3, obj_cond_dim=12, conv_dim=16, repeat_num=6)
+TABLE = dict(spade_layers=(1, 1, 0, 0), attn_layers=tuple(range(1, 10)))
+
+
+def _rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+CONVS = [  # Cin, Cout, k, stride, pad, H, bias
+    (16, 32, 3, 1, 1, 24, True), (3, 16, 7, 1, 3, 32, False), (16, 32, 3, 2, 1, 32, False), (19, 64, 4, 2, 1, 32, True),
+    (64, 64, 4, 1, 1, 15, True), (32, 128, 5, 5, 0, 40, True), (128, 25, 1, 1, 0, 8, True), (12, 128, 3, 1, 1, 16, True),
+    (128, 3, 7, 1, 3, 32, False),
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,pad,h,bias", CONVS)
+def test_conv2d_function_forward_and_gradients(cin, cout, k, stride, pad, h, bias):
+    g = torch.Generator().manual_seed(cin * 7 + k)
+    x = torch.randn(2, cin, h, h, generator=g).cuda().requires_grad_()
+    w = (torch.randn(cout, cin, k, k, generator=g) * 0.1).cuda().requires_grad_()
+    b = torch.randn(cout, generator=g).cuda().requires_grad_() if bias else None
+    y = ag.conv2d(x, w, b, stride, pad)
+    ref = F.conv2d(x, w, b, stride=stride, padding=pad)
+    assert y.shape == ref.shape and _rel(y, ref) <= 1e-5
+    go = torch.randn(ref.shape, generator=g).cuda()
+    gx, gw, *gb = torch.autograd.grad(y, [x, w] + ([b] if bias else []), go)
+    rx, rw, *rb = torch.autograd.grad(ref, [x, w] + ([b] if bias else []), go)
+    assert _rel(gx, rx) <= 2e-5 and _rel(gw, rw) <= 2e-5
+    if bias:
+        assert _rel(gb[0], rb[0]) <= 2e-5
+
+
+@pytest.mark.parametrize("cin,cout,h", [(32, 16, 12), (64, 32, 16)])
+def test_conv_transpose2d_function(cin, cout, h):
+    g = torch.Generator().manual_seed(cin)
+    x = torch.randn(2, cin, h, h, generator=g).cuda().requires_grad_()
+    w = (torch.randn(cin, cout, 3, 3, generator=g) * 0.1).cuda().requires_grad_()
+    y = ag.conv_transpose2d(x, w)
+    ref = F.conv_transpose2d(x, w, None, stride=2, padding=1, output_padding=1)
+    assert _rel(y, ref) <= 1e-5
+    go = torch.randn(ref.shape, generator=g).cuda()
+    gx, gw = torch.autograd.grad(y, [x, w], go)
+    rx, rw = torch.autograd.grad(ref, [x, w], go)
+    assert _rel(gx, rx) <= 2e-5 and _rel(gw, rw) <= 2e-5
+
+
+@pytest.mark.parametrize("affine", [True, False])
+def test_instance_norm_function(affine):
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(3, 32, 20, 24, generator=g) * 2 + 0.7).cuda().requires_grad_()
+    gam = torch.randn(32, generator=g).cuda().requires_grad_() if affine else None
+    bet = torch.randn(32, generator=g).cuda().requires_grad_() if affine else None
+    y = ag.instance_norm(x, gam, bet)
+    ref = F.instance_norm(x, weight=gam, bias=bet, eps=1e-5)
+    assert _rel(y, ref) <= 1e-5
+    go = torch.randn(ref.shape, generator=g).cuda()
+    ins = [x] + ([gam, bet] if affine else [])
+    got, want = torch.autograd.grad(y, ins, go), torch.autograd.grad(ref, ins, go)
+    for a, b in zip(got, want):
+        assert _rel(a, b) <= 5e-5
+
+
+def test_block_extract_and_reshape_functions_match_torch_restatement():
+    g = torch.Generator().manual_seed(5)
+    src = torch.randn(2, 8, 12, 12, generator=g).cuda().requires_grad_()
+    flow = (torch.rand(2, 2, 12, 12, generator=g) * 3 - 1.5).cuda()
+    be = ag.block_extract(src, flow, 5)
+    ref = gr.block_extract(src.detach().cpu(), flow.cpu(), 5)
+    assert (be.detach().cpu() - ref).abs().max().item() <= 1e-5
+    a = torch.randn(2, 25, 12, 12, generator=g).cuda().requires_grad_()
+    out = F.avg_pool2d(ag.local_attn_reshape(F.softmax(a, 1), 5) * be, 5, 5)
+    out.square().sum().backward()
+    assert torch.isfinite(src.grad).all() and torch.isfinite(a.grad).all() and src.grad.abs().sum() > 0
+    ref_ps = F.pixel_shuffle(F.softmax(a.detach(), 1), 5)
+    assert torch.equal(ag.local_attn_reshape(F.softmax(a.detach(), 1), 5), ref_ps)
+
+
+def test_generator_train_forward_and_gradients_vs_oracle_autograd():
+    """Differentiable forward == the oracle port; parameter gradients of a scalar loss == torch.autograd through the oracle port
+    (the reference's op graph) -- a sample of parameters from every sub-network and op type."""
+    sd = gr.init_state_dict(seed=0, jitter=0.05, **SMALL, **TABLE)
+    g = create("generator_spade_attn", **SMALL)
+    g.load_state_dict(sd)
+    g = g.cuda().train()
+    inp = synth.generator_inputs(1, seed=1, size=64)
+    outs = g(**{k: v.cuda() for k, v in inp.items()})
+    sdg = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    ref = gr.generator_forward(sdg, **inp, **TABLE)
+    for a, b in zip(outs, ref):
+        assert (a.detach().cpu() - b.detach()).abs().max().item() <= 1e-3
+    wts = [torch.randn(o.shape, generator=torch.Generator().manual_seed(i)) for i, o in enumerate(ref)]
+    loss = sum((o * w.cuda()).sum() for o, w in zip(outs, wts))
+    loss_ref = sum((o * w).sum() for o, w in zip(ref, wts))
+    loss.backward()
+    loss_ref.backward()
+    names = ["bg_model.model.0.weight", "bg_model.model.1.weight", "bg_model.model.12.main.3.weight", "bg_model.model.18.weight",
+             "src_model.encoders.0.0.weight", "src_model.encoders.1.conv.weight", "src_model.encoders.2.norm.mlp_gamma.weight",
+             "src_model.resnets.0.conv_0.bias", "src_model.resnets.1.norm_1.mlp_shared.0.weight", "src_model.resnets.4.main.1.bias",
+             "tsf_model.decoders.0.0.weight", "tsf_model.skippers.2.0.weight", "tsf_model.attetion_reg_bg.0.weight",
+             "obj_model.img_reg.0.weight", "obj_model.resnets.5.main.0.weight", "attn_1.fully_connect_layer.0.weight",
+             "attn_5.fully_connect_layer.2.bias", "attn_9.fully_connect_layer.0.bias"]
+    worst = 0.0
+    for n in names:
+        a, b = g.get_parameter(n).grad.cpu(), sdg[n].grad
+        worst = max(worst, _rel(a, b))
+        assert _rel(a, b) <= 2e-3, (n, _rel(a, b))
+    print("worst relative gradient error", worst)
+    assert all(p.grad is not None for p in g.parameters())
+
+
+def test_patch_discriminator_matches_reference_math_and_keys():
+    D = PatchDiscriminatorB200(input_nc=19, ndf=16, n_layers=4).cuda()
+    assert list(D.state_dict().keys()) == [f"model.{i}.{n}" for i in (0, 2, 5, 8, 11, 14) for n in ("weight", "bias")]
+    x = torch.randn(2, 19, 64, 64, generator=torch.Generator().manual_seed(0)).cuda().requires_grad_()
+    y = D(x)
+    h = x
+    for i, (idx, stride, has_norm, has_act) in enumerate(D.layers):
+        m = getattr(D.model, str(idx))
+        h = F.conv2d(h, m.weight, m.bias, stride=stride, padding=1)
+        if has_norm:
+            h = F.instance_norm(h)
+        if has_act:
+            h = F.leaky_relu(h, 0.2)
+    assert y.shape == h.shape == (2, 1, 2, 2) and _rel(y, h) <= 1e-4
+    gy = torch.autograd.grad(y.square().mean(), [x, D.model._modules["5"].weight], retain_graph=True)
+    gh = torch.autograd.grad(h.square().mean(), [x, D.model._modules["5"].weight])
+    assert _rel(gy[0], gh[0]) <= 1e-3 and _rel(gy[1], gh[1]) <= 1e-3
+
+
+def test_train_step_updates_both_networks_and_inference_sees_new_weights():
+    sd = gr.init_state_dict(seed=0, jitter=0.05, **SMALL, **TABLE)
+    G = create("generator_spade_attn", **SMALL)
+    G.load_state_dict(sd)
+    G = G.cuda().train()
+    D = PatchDiscriminatorB200(input_nc=3 + 12 + 3 + 1, ndf=16, n_layers=4).cuda()
+    step = TrainStep(G, D, lr_G=1e-3, lr_D=1e-3)
+    kw = {k: v.cuda() for k, v in synth.generator_inputs(2, seed=4, size=64).items()}
+    gen = torch.Generator().manual_seed(9)
+    real_src, real_tsf = (torch.rand(2, 3, 64, 64, generator=gen) * 2 - 1).cuda(), (torch.rand(2, 3, 64, 64, generator=gen) * 2 - 1).cuda()
+    bg_mask, hand_mask = (torch.rand(4, 1, 64, 64, generator=gen) > 0.5).float().cuda(), (torch.rand(4, 1, 64, 64, generator=gen) > 0.5).float().cuda()
+    w0 = G.get_parameter("src_model.img_reg.0.weight").detach().clone()
+    d0 = D.model._modules["0"].weight.detach().clone()
+    l1 = step(kw, real_src, real_tsf, bg_mask, hand_mask)
+    l2 = step(kw, real_src, real_tsf, bg_mask, hand_mask)
+    assert all(torch.isfinite(torch.tensor(v)) for v in l1.values())
+    assert not torch.equal(w0, G.get_parameter("src_model.img_reg.0.weight")) and not torch.equal(d0, D.model._modules["0"].weight)
+    assert l2["g_rec"] < l1["g_rec"]                     # two Adam steps on the same batch reduce the reconstruction term
+    G.eval()
+    with torch.no_grad():
+        a = G(**kw)                                     # fused fp16 inference path with the UPDATED weights
+    G.train()
+    b = G(**kw)
+    for x, y in zip(a, b):
+        assert _rel(x, y.detach()) <= 1e-2
