@@ -321,7 +321,7 @@ class TrainStep:
         loss_G.backward()
         self.allreduce_bytes = allreduce_gradients(list(self.G.parameters()))
         self.opt_G.step()
-        losses = dict(g_adv=l_adv.item(), g_rec=l_rec.item(), g_tsf=l_tsf.item(), g_mask=l_mask.item(), g_mask_smooth=float(l_smooth))
+        losses = dict(g_adv=l_adv.item(), g_rec=l_rec.item(), g_tsf=l_tsf.item(), g_mask=l_mask.item(), g_mask_smooth=float(l_smooth.detach()))
         # ---- discriminator (trainer.py:463-481)
         if train_D:
             self.opt_D.zero_grad(set_to_none=True)

