@@ -537,13 +537,69 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """BASELINE configs[4]: generator + discriminator training step (models/trainer.py:417-481) with the DDP gradient all-reduce,
+    one process per GPU.  fp32 training path (hoig_b200.training).  Prints one JSON line (not the driver's default line)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from hoig_b200 import dist_utils
+    from hoig_b200.generator import create
+    from hoig_b200.training import PatchDiscriminatorB200, TrainStep
+    B = args.batch
+    torch.manual_seed(1234)                      # same initial weights on every rank, like DDP's broadcast
+    G = create("generator_spade_attn", **CFG).to(dev).train()
+    G.init_weights()
+    D = PatchDiscriminatorB200(input_nc=19, ndf=64, n_layers=4).to(dev)
+    sc, flow, host = _gpu_workload(B, dist_utils.shard_seed(100, rank), dev)
+    kw, masks = flow(**{k: v.to(dev) for k, v in host.items()})
+    g = torch.Generator().manual_seed(7 + rank)
+    real_src = host["src_img"].to(dev)
+    real_tsf = (torch.rand(B, 3, 256, 256, generator=g) * 2 - 1).to(dev)
+    bg_mask = torch.cat([masks["src_mask_bg"], masks["ref_mask_bg"]], 0)
+    hand_mask = torch.cat([masks["src_mask_hand"], masks["ref_mask_hand"]], 0)
+    step = TrainStep(G, D)
+    for _ in range(args.warmup):
+        losses = step(kw, real_src, real_tsf, bg_mask, hand_mask)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ar_ms = 0.0
+    e0.record()
+    for _ in range(args.steps):
+        losses = step(kw, real_src, real_tsf, bg_mask, hand_mask)
+        ar_ms += step.allreduce_ms
+    e1.record()
+    torch.cuda.synchronize()
+    (ms, ar_ms) = dist_utils.reduce_max([e0.elapsed_time(e1), ar_ms], "cuda")
+    if rank == 0:
+        print(json.dumps({"mode": "train", "metric": "training images/sec at 256x256 (G + D step, fp32 training path)",
+                          "value": B * world * args.steps / (ms / 1e3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": ms / args.steps, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "HOGAN generator + PatchGAN discriminator training step, Adam, DDP-style gradient all-reduce",
+                                     "batch_per_gpu": B, "parallelism": f"dp{world}"},
+                          "allreduce": {"bytes_per_step": step.allreduce_bytes, "ms_per_step": ar_ms / args.steps,
+                                        "note": "bucketed NCCL all-reduce of G (734 MB) and D gradients, fp32"},
+                          "losses": {k: round(v, 5) for k, v in losses.items()}}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step (BASELINE config: 64)")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="train: BASELINE configs[4] (G + D step, own JSON line)")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (BASELINE config: 64; --mode train: 4)")
     ap.add_argument("--dtype", default="f16", choices=["bf16", "f16", "f32"],
                     help="operand / storage type of the tensor-core path (f16 meets the 1e-2 gate; bf16 measures 2.4e-2)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
@@ -552,6 +608,10 @@ def main():
     ap.add_argument("--no-cpu-extras", dest="cpu_extras", action="store_false", help="--impl reference: skip the B=4 / rasterizer rows")
     ap.add_argument("--raster-meshes", type=int, default=8192)
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 4 if args.mode == "train" else 64
+    if args.mode == "train":
+        return run_train(args)
     if args.impl == "reference":
         run_reference(args)
     else:

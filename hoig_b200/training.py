@@ -294,11 +294,23 @@ class TrainStep:
         self.lam = dict(rec=lambda_rec, tsf=lambda_tsf, d=lambda_D_prob, mask=lambda_mask, smooth=lambda_mask_smooth)
         self.tsf_loss = tsf_loss or (lambda fake, real: (fake - real).abs().mean())
         self.allreduce_bytes = 0
+        self.allreduce_ms = 0.0          # device time of the gradient all-reduces of the last step (CUDA events)
+
+    def _allreduce(self, params):
+        if not torch.cuda.is_available():
+            return allreduce_gradients(params)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = allreduce_gradients(params)
+        e1.record()
+        self._events.append((e0, e1))
+        return n
 
     def __call__(self, gen_kwargs, real_src, real_tsf, bg_mask, hand_mask, train_D: bool = True):
         """gen_kwargs: the Generator.forward keyword arguments (HandRecoveryFlowB200 output); real_* (B,3,H,W); bg_mask / hand_mask
         (2B,1,H,W) = cat of the source and target crop masks (trainer.py:359-360).  Returns the dict of loss values."""
         lam = self.lam
+        self._events = []
         outs = self.G(**gen_kwargs)
         (src_bg, tsf_bg, src_obj, src_hand, src_mbg, src_mh, tsf_obj, tsf_hand, tsf_mbg, tsf_mh) = outs
         fake_src = composite(src_bg, src_obj, src_hand, src_mbg, src_mh)
@@ -319,7 +331,7 @@ class TrainStep:
         self.opt_G.zero_grad(set_to_none=True)
         self.opt_D.zero_grad(set_to_none=True)
         loss_G.backward()
-        self.allreduce_bytes = allreduce_gradients(list(self.G.parameters()))
+        self.allreduce_bytes = self._allreduce(list(self.G.parameters()))
         self.opt_G.step()
         losses = dict(g_adv=l_adv.item(), g_rec=l_rec.item(), g_tsf=l_tsf.item(), g_mask=l_mask.item(), g_mask_smooth=float(l_smooth.detach()))
         # ---- discriminator (trainer.py:463-481)
@@ -329,9 +341,12 @@ class TrainStep:
             d_fake = self.D(torch.cat([fake_tsf.detach(), tsf_cond], 1))
             loss_D = (((d_real - 1) ** 2).mean() + ((d_fake + 1) ** 2).mean()) * lam["d"]
             loss_D.backward()
-            self.allreduce_bytes += allreduce_gradients(list(self.D.parameters()))
+            self.allreduce_bytes += self._allreduce(list(self.D.parameters()))
             self.opt_D.step()
             losses.update(d_real=d_real.mean().item(), d_fake=d_fake.mean().item(), loss_D=loss_D.item())
+        if self._events:
+            torch.cuda.synchronize()
+            self.allreduce_ms = sum(a.elapsed_time(b) for a, b in self._events)
         if hasattr(self.G, "refresh_weights"):
             self.G.refresh_weights()           # the packed inference copies are stale after the optimiser step
         return losses
