@@ -110,6 +110,7 @@ _SIGNATURES = {
     "hoig_set_umma_bres_mode": (None, [c_int]),
     "hoig_set_umma_halo_mode": (None, [c_int]),
     "hoig_set_umma_vhalo_mode": (None, [c_int]),
+    "hoig_set_attn_tc_mode": (None, [c_int]),
     "hoig_attn_combine": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "hoig_grid_sample": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int,
@@ -183,7 +184,7 @@ recorder = LaunchRecorder()
 _NO_LAUNCH = {"hoig_version", "hoig_last_error", "hoig_check_device", "hoig_conv_packed_dims",
               "hoig_rasterize_workspace_bytes", "hoig_set_umma_gather_only", "hoig_set_rasterizer_band_pixels",
               "hoig_set_halo_variant", "hoig_set_umma_pair_mode", "hoig_set_umma_dual_mode", "hoig_set_umma_bres_mode",
-              "hoig_set_umma_halo_mode", "hoig_set_umma_vhalo_mode"}
+              "hoig_set_umma_halo_mode", "hoig_set_umma_vhalo_mode", "hoig_set_attn_tc_mode"}
 
 
 class _Proxy:

@@ -2,6 +2,10 @@
 // reference op boundaries (BlockExtractor / LocalAttnReshape forward).
 // All kernels move 8-channel (16/32-byte) chunks of NHWC rows so that warps
 // issue fully coalesced 128-bit accesses.
+#include <stdlib.h>
+
+#include <type_traits>
+
 #include "conv_common.cuh"
 
 namespace hoig {
@@ -741,6 +745,262 @@ attn_combine_kernel(const T *__restrict__ gt, int64_t ldgt, const T *__restrict_
     }
 }
 
+// ---- attn_combine on the tensor cores, source tiles staged in shared memory -------------------------------------------------------
+// The weighted patch sum  out[p][c] = sum_u coef[p][u] * src[patch_p(u)][c]  (36 taps per pixel, all channels) is 85 % of attn_combine's
+// work and was instruction-issue bound as per-pixel gathers.  For a TILE of 8 x 8 pixels whose (unclamped) patches fall into a window of
+// WW x WH <= 336 source positions -- always the case for HOGAN's flows, which are normalised coordinates used as pixel offsets (quirk Q1,
+// |flow| <= 3) -- it is a small dense GEMM:   OUT[64 px][C] = A[64 px][WW*WH] * S[WW*WH][C]
+//   A: the pixels' 36 coefficients scattered to their window positions (zeros elsewhere), built once per tile in shared memory (fp16/bf16);
+//   S: the window's source pixels (border positions replicate the clamped pixel, so unclamped patch coordinates index it directly), staged
+//      in shared memory 64 channels at a time with 16-byte cp.async copies (XOR-swizzled rows, conflict-free ldmatrix);
+//   warp-level mma.sync.m16n8k16 (fp32 accumulate): 8 warps = 4 row tiles x 2 halves of the 64-channel slab.
+// The L2->SM traffic per pixel drops from 36 source pixels to WW*WH/64 (~3-5), and the instruction count ~7x.  Tiles whose window is larger
+// (arbitrary flows) take the per-pixel gather path inside the same kernel, so the result is defined for every input.
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+template <typename T>
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    if (sizeof(T) == 2 && std::is_same<T, __half>::value)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+constexpr int ATC_TILE = 8, ATC_PX = 64, ATC_KMAX = 336, ATC_AP = 344;       // tile side, pixels per tile, window capacity, A row pitch (halves)
+constexpr int ATC_CONST_BYTES = 16384, ATC_A_BYTES = ATC_PX * ATC_AP * 2, ATC_S_BYTES = ATC_KMAX * 128;
+constexpr int ATC_SMEM = ATC_CONST_BYTES + ATC_A_BYTES + ATC_S_BYTES;           // 103424 B: two CTAs per SM
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+attn_combine_tc_kernel(const T *__restrict__ gt, int64_t ldgt, const T *__restrict__ gs, int64_t ldgs, const float *__restrict__ b1,
+                       const float *__restrict__ w2, const float *__restrict__ b2, const T *__restrict__ src, int64_t lds,
+                       const float *__restrict__ flow, const T *__restrict__ tgt, int64_t ldt, T *__restrict__ dst, int64_t ldd,
+                       int N, int h, int C)
+{
+    constexpr int K = 5, KK = 25, HID = 128, PK = K + 1, R = K / 2;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    float *s_w2 = reinterpret_cast<float *>(smem_raw);              // [KK][HID]
+    float *s_b1 = s_w2 + KK * HID;                                  // [HID]
+    float *s_b2 = s_b1 + HID;                                       // [KK] (32 reserved)
+    int *s_box = reinterpret_cast<int *>(s_b2 + 32);                // bx0, by0, WW, fits
+    int *s_xy = s_box + 4;                                          // [64][2]: x0, y0 of every pixel of the tile
+    T *sA = reinterpret_cast<T *>(smem_raw + ATC_CONST_BYTES);
+    uint8_t *sS = smem_raw + ATC_CONST_BYTES + ATC_A_BYTES;
+    float *s_coef = reinterpret_cast<float *>(sS);                  // fallback path only: [8 warps][4][PK*PK+4] (S is idle then)
+    const uint32_t sA_u = (uint32_t)__cvta_generic_to_shared(sA), sS_u = (uint32_t)__cvta_generic_to_shared(sS);
+    for (int i = threadIdx.x; i < KK * HID; i += blockDim.x) s_w2[i] = w2[i];
+    for (int i = threadIdx.x; i < HID; i += blockDim.x) s_b1[i] = b1[i];
+    for (int i = threadIdx.x; i < KK; i += blockDim.x) s_b2[i] = b2[i];
+    const int lane = threadIdx.x % 32, warp = threadIdx.x / 32, sub = lane & 7, grp = lane >> 3;
+    const int tiles_x = h / ATC_TILE, tiles_per_img = tiles_x * tiles_x;
+    const int hpt = h + 2 * R, hps = h + 4 * R;
+    for (int tile = blockIdx.x; tile < N * tiles_per_img; tile += gridDim.x) {
+        const int n = tile / tiles_per_img, t_in = tile - n * tiles_per_img;
+        const int ty = t_in / tiles_x, tx = t_in - ty * tiles_x;
+        __syncthreads();                       // constants loaded / previous tile fully done with A, S and s_xy
+        if (threadIdx.x < ATC_PX) {
+            const int x = tx * ATC_TILE + (threadIdx.x & 7), y = ty * ATC_TILE + (threadIdx.x >> 3);
+            const int64_t pix = ((int64_t)n * h + y) * h + x;
+            const float dx = __fadd_rn(__fadd_rn(flow[pix * 2], 0.f), (float)x), dy = __fadd_rn(__fadd_rn(flow[pix * 2 + 1], 0.f), (float)y);
+            s_xy[2 * threadIdx.x] = (int)fminf(fmaxf(floorf(dx), -(float)(K + 2)), (float)(h + K + 2));
+            s_xy[2 * threadIdx.x + 1] = (int)fminf(fmaxf(floorf(dy), -(float)(K + 2)), (float)(h + K + 2));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int mnx = s_xy[0], mxx = s_xy[0], mny = s_xy[1], mxy = s_xy[1];
+            for (int i = 1; i < ATC_PX; ++i) {
+                mnx = min(mnx, s_xy[2 * i]); mxx = max(mxx, s_xy[2 * i]);
+                mny = min(mny, s_xy[2 * i + 1]); mxy = max(mxy, s_xy[2 * i + 1]);
+            }
+            const int WW = mxx - mnx + PK, WH = mxy - mny + PK;
+            s_box[0] = mnx - R; s_box[1] = mny - R; s_box[2] = WW;
+            s_box[3] = (WW * WH <= ATC_KMAX) ? WW * WH : 0;
+        }
+        __syncthreads();
+        const int bx0 = s_box[0], by0 = s_box[1], WW = s_box[2], wpos = s_box[3];
+        const bool fits = wpos > 0;
+        const int ksteps = (wpos + 15) / 16, kcols = ksteps * 16;
+        if (fits) {           // zero the used columns of A (16-byte stores; AP * 2 and kcols * 2 are multiples of 16)
+            const int per_row = kcols / 8;
+            for (int i = threadIdx.x; i < ATC_PX * per_row; i += blockDim.x)
+                *reinterpret_cast<uint4 *>(sA + (i / per_row) * ATC_AP + (i % per_row) * 8) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+        // ---- phase 1: per pixel (8 lanes each): hidden, logits, softmax, the 36 patch coefficients
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            const int pi = pass * 32 + warp * 4 + grp;          // pixel of the tile
+            const int x = tx * ATC_TILE + (pi & 7), y = ty * ATC_TILE + (pi >> 3);
+            const int64_t pix = ((int64_t)n * h + y) * h + x;
+            const float dx = __fadd_rn(__fadd_rn(flow[pix * 2], 0.f), (float)x), dy = __fadd_rn(__fadd_rn(flow[pix * 2 + 1], 0.f), (float)y);
+            const float fdx = floorf(dx), fdy = floorf(dy);
+            const float wx1 = __fsub_rn(dx, fdx), wx0 = __fsub_rn(1.f, wx1), wy1 = __fsub_rn(dy, fdy), wy0 = __fsub_rn(1.f, wy1);
+            const int x0 = s_xy[2 * pi], y0 = s_xy[2 * pi + 1];
+            float hv[16];
+            {
+                const T *g = gt + (((int64_t)n * hpt + y + R) * hpt + x + R) * ldgt + 4 * sub;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    load4(g + 32 * i, hv + 4 * i);
+                    const float4 bv = *reinterpret_cast<const float4 *>(&s_b1[32 * i + 4 * sub]);
+                    hv[4 * i] += bv.x; hv[4 * i + 1] += bv.y; hv[4 * i + 2] += bv.z; hv[4 * i + 3] += bv.w;
+                }
+#pragma unroll
+                for (int qy = 0; qy < 2; ++qy)
+#pragma unroll
+                    for (int qx = 0; qx < 2; ++qx) {
+                        const int cy = max(min(y0 + qy, h - 1 + R), -R) + 2 * R, cx = max(min(x0 + qx, h - 1 + R), -R) + 2 * R;
+                        const float w = __fmul_rn(qx ? wx1 : wx0, qy ? wy1 : wy0);
+                        const T *gq = gs + (((int64_t)n * hps + cy) * hps + cx) * ldgs + 4 * sub;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float u[4];
+                            load4(gq + 32 * i, u);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) hv[4 * i + j] = fmaf(w, u[j], hv[4 * i + j]);
+                        }
+                    }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) hv[j] = hv[j] > 0.f ? hv[j] : 0.01f * hv[j];
+            }
+            float a[KK];
+#pragma unroll
+            for (int t = 0; t < KK; ++t) {
+                float acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 wv = *reinterpret_cast<const float4 *>(&s_w2[t * HID + 32 * i + 4 * sub]);
+                    acc = fmaf(hv[4 * i], wv.x, acc); acc = fmaf(hv[4 * i + 1], wv.y, acc);
+                    acc = fmaf(hv[4 * i + 2], wv.z, acc); acc = fmaf(hv[4 * i + 3], wv.w, acc);
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                a[t] = acc + s_b2[t];
+            }
+            float mx = a[0];
+#pragma unroll
+            for (int t = 1; t < KK; ++t) mx = fmaxf(mx, a[t]);
+            float den = 0.f;
+#pragma unroll
+            for (int t = 0; t < KK; ++t) { a[t] = expf(a[t] - mx); den += a[t]; }
+            const float inv = 1.0f / (den * (float)KK);
+            float *cf = s_coef + ((warp * 4 + grp) * (PK * PK + 4));
+            T *arow = sA + pi * ATC_AP + (y0 - R - by0) * WW + (x0 - R - bx0);
+#pragma unroll
+            for (int uy = 0; uy < PK; ++uy)
+#pragma unroll
+                for (int ux = 0; ux < PK; ++ux) {
+                    float c = 0.f;
+                    if (uy < K && ux < K) c = fmaf(a[uy * K + ux], wy0 * wx0, c);
+                    if (uy < K && ux > 0) c = fmaf(a[uy * K + ux - 1], wy0 * wx1, c);
+                    if (uy > 0 && ux < K) c = fmaf(a[(uy - 1) * K + ux], wy1 * wx0, c);
+                    if (uy > 0 && ux > 0) c = fmaf(a[(uy - 1) * K + ux - 1], wy1 * wx1, c);
+                    if (((uy * PK + ux) & 7) == sub) {
+                        if (fits) DT<T>::st(arow + uy * WW + ux, c * inv);
+                        else cf[uy * PK + ux] = c * inv;
+                    }
+                }
+            if (!fits) {      // per-pixel gathers (window too large for the staged GEMM): same arithmetic as attn_combine_kernel
+                __syncwarp();
+                const T *splane = src + (int64_t)n * h * h * lds;
+                const int xb = x0 - R, yb = y0 - R;
+                for (int cc = sub; cc < C / 8; cc += 8) {
+                    float acc[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll 2
+                    for (int uy = 0; uy < PK; ++uy) {
+                        const T *srow = splane + (int64_t)max(min(yb + uy, h - 1), 0) * h * lds + cc * 8;
+#pragma unroll
+                        for (int ux = 0; ux < PK; ++ux) {
+                            float u[8];
+                            load8(srow + (int64_t)max(min(xb + ux, h - 1), 0) * lds, u);
+                            const float c = cf[uy * PK + ux];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) acc[j] = fmaf(c, u[j], acc[j]);
+                        }
+                    }
+                    float tv[8];
+                    load8(tgt + pix * ldt + cc * 8, tv);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) tv[j] += acc[j];
+                    store8(dst + pix * ldd + cc * 8, tv);
+                }
+                __syncwarp();
+            }
+        }
+        if (!fits) continue;
+        // ---- phase 2: OUT[64][C] = A[64][kcols] * S[kcols][C], 64 channels per slab
+        const int mt = warp & 3, nh = warp >> 2, g = lane >> 2, tq = lane & 3;
+        const uint32_t a_addr = sA_u + (uint32_t)(((mt * 16 + (lane & 15)) * ATC_AP + (lane >> 4) * 8) * 2);
+        const int b_krow = (lane & 7) + ((lane >> 3) & 1) * 8, b_csel = lane >> 4;     // ldmatrix.trans source row / chunk select of this lane
+        const T *splane = src + (int64_t)n * h * h * lds;
+#pragma unroll 1
+        for (int slab = 0; slab < C / 64; ++slab) {
+            __syncthreads();                   // A complete (first slab) / every warp is done reading S of the previous slab
+            for (int i = threadIdx.x; i < kcols * 8; i += blockDim.x) {
+                const int pos = i >> 3, c = i & 7;
+                const uint32_t d = sS_u + (uint32_t)(pos * 128 + ((c ^ (pos & 7)) << 4));
+                if (pos < wpos) {
+                    const int wy = pos / WW, wx = pos - wy * WW;
+                    const int sy = max(min(by0 + wy, h - 1), 0), sx = max(min(bx0 + wx, h - 1), 0);
+                    cp_async16(d, splane + ((int64_t)sy * h + sx) * lds + slab * 64 + c * 8);
+                } else {
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(d), "r"(0u) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            float acc[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+#pragma unroll 3
+            for (int ks = 0; ks < ksteps; ++ks) {
+                uint32_t af[4], bf0[4], bf1[4];
+                ldmatrix_x4(af, a_addr + (uint32_t)(ks * 32));
+                const int krow = ks * 16 + b_krow;
+                const uint32_t rb = sS_u + (uint32_t)(krow * 128);
+                ldmatrix_x4_trans(bf0, rb + (uint32_t)((((nh * 4 + 0 + b_csel) ^ (krow & 7))) << 4));
+                ldmatrix_x4_trans(bf1, rb + (uint32_t)((((nh * 4 + 2 + b_csel) ^ (krow & 7))) << 4));
+                mma_16816<T>(acc[0], af, bf0[0], bf0[1]);
+                mma_16816<T>(acc[1], af, bf0[2], bf0[3]);
+                mma_16816<T>(acc[2], af, bf1[0], bf1[1]);
+                mma_16816<T>(acc[3], af, bf1[2], bf1[3]);
+            }
+            // epilogue: dst = tgt + OUT; lane holds rows g, g + 8 of its row tile and channels 2*tq, 2*tq + 1 of each 8-channel group
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int r = mt * 16 + g + hrow * 8;
+                const int64_t pix = ((int64_t)n * h + ty * ATC_TILE + (r >> 3)) * h + tx * ATC_TILE + (r & 7);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ch = slab * 64 + (nh * 4 + j) * 8 + 2 * tq;
+                    const uint32_t tv = *reinterpret_cast<const uint32_t *>(tgt + pix * ldt + ch);
+                    float lo, hi;
+                    unpack2<T>(tv, lo, hi);
+                    *reinterpret_cast<uint32_t *>(dst + pix * ldd + ch) = pack2<T>(lo + acc[j][hrow * 2], hi + acc[j][hrow * 2 + 1]);
+                }
+            }
+        }
+    }
+}
+
 // x7[b,y,x, s*C + c] = x[b,c,y,x+s-k/2]  (zero outside the row / beyond k*C), from the NCHW f32 input
 template <typename T>
 __global__ void hunfold_kernel(const float *__restrict__ src, int B, int C, int H, int W, int k, T *__restrict__ dst, int64_t ldd, int Cpad)
@@ -1114,6 +1374,9 @@ extern "C" int hoig_replicate_pad(const void *src, int64_t lds, void *dst, int64
     });
 }
 
+static int g_attn_tc = 1;      // HOIG_ATTN_TC / hoig_set_attn_tc_mode: 1 = tensor-core attn_combine with staged source windows, 0 = per-pixel gathers
+extern "C" void hoig_set_attn_tc_mode(int on) { g_attn_tc = on ? 1 : 0; }
+
 extern "C" int hoig_attn_combine(const void *gt, int64_t ldgt, const void *gs, int64_t ldgs, int Chid, const float *b1, const float *w2,
                                  const float *b2, const void *src, int64_t lds, const float *flow, const void *tgt, int64_t ldt,
                                  void *dst, int64_t ldd, int dtype, int N, int h, int C, int k, hoigStream_t stream)
@@ -1128,6 +1391,32 @@ extern "C" int hoig_attn_combine(const void *gt, int64_t ldgt, const void *gs, i
     const int sms = device_sm_count();
     const int64_t want = (npix + 31) / 32;
     const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+    static bool env_parsed = false;
+    if (!env_parsed) {
+        env_parsed = true;
+        const char *e = getenv("HOIG_ATTN_TC");
+        if (e) g_attn_tc = atoi(e) ? 1 : 0;
+    }
+    if (g_attn_tc && (dtype == HOIG_BF16 || dtype == HOIG_F16) && k == 5 && h % ATC_TILE == 0 && C % 64 == 0) {
+        // tensor-core formulation with shared-memory staging of the source window (attn_combine_tc_kernel)
+        const int64_t tiles = (int64_t)N * (h / ATC_TILE) * (h / ATC_TILE);
+        const int tgrid = (int)(tiles < (int64_t)sms * 2 ? tiles : (int64_t)sms * 2);
+        if (dtype == HOIG_F16) {
+            if (first_use_on_device(SLOT_ATTN_TC_F16) &&
+                cudaFuncSetAttribute(attn_combine_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM) != cudaSuccess)
+                return check_launch("attn_combine_tc smem attribute");
+            attn_combine_tc_kernel<__half><<<tgrid, 256, ATC_SMEM, as_stream(stream)>>>(
+                (const __half *)gt, ldgt, (const __half *)gs, ldgs, b1, w2, b2, (const __half *)src, lds, flow, (const __half *)tgt, ldt, (__half *)dst, ldd, N, h, C);
+        } else {
+            if (first_use_on_device(SLOT_ATTN_TC_BF16) &&
+                cudaFuncSetAttribute(attn_combine_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM) != cudaSuccess)
+                return check_launch("attn_combine_tc smem attribute");
+            attn_combine_tc_kernel<__nv_bfloat16><<<tgrid, 256, ATC_SMEM, as_stream(stream)>>>(
+                (const __nv_bfloat16 *)gt, ldgt, (const __nv_bfloat16 *)gs, ldgs, b1, w2, b2, (const __nv_bfloat16 *)src, lds, flow, (const __nv_bfloat16 *)tgt, ldt,
+                (__nv_bfloat16 *)dst, ldd, N, h, C);
+        }
+        return check_launch("attn_combine_tc_kernel");
+    }
     return dispatch(dtype, [&](auto *tag) {
         using T = std::remove_pointer_t<decltype(tag)>;
         if (k == 5)

@@ -204,6 +204,9 @@ void hoig_set_umma_halo_mode(int on);
 /* Test hook: 1 (default) = kh x 1 convs (the re-associated 7x7 stems / heads) run on 8 x 16 pixel tiles that load one activation box
  * per 64 channels for all kh vertical taps (weights resident), 0 = one box per tap. */
 void hoig_set_umma_vhalo_mode(int on);
+/* Test hook: 1 (default) = hoig_attn_combine runs its weighted source-patch sum on the tensor cores with the source window of an 8x8
+ * pixel tile staged in shared memory (16-bit dtypes, k = 5, h % 8 == 0, C % 64 == 0), 0 = per-pixel gathers for every pixel. */
+void hoig_set_attn_tc_mode(int on);
 /* Tuning hook: pixels per rasterizer band (256..16384; the band's 64-bit key buffer lives in shared memory). */
 void hoig_set_rasterizer_band_pixels(int n);
 

@@ -141,3 +141,59 @@ def test_commuted_attention_block_vs_reference_formulation(dtype):
     rel = (d.norm() / ref.norm()).item()
     print(f"commuted attention block {dtype}: maxabs {d.abs().max().item():.3e} relL2 {rel:.3e}")
     assert rel <= (5e-3 if dtype == torch.bfloat16 else 8e-4)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("flows", ["hogan_like", "large_random", "mixed"])
+def test_attn_combine_tensor_core_path_vs_gather_path_and_contract(dtype, flows):
+    """attn_combine_tc_kernel (8x8-pixel tiles, source window staged in shared memory, patch sum as an mma.sync GEMM) against the
+    per-pixel gather kernel and the op contract.  'hogan_like': normalised coordinates used as pixel offsets (|flow| <= 3, quirk Q1) --
+    every tile takes the staged path; 'large_random': windows exceed the capacity -- every tile takes the in-kernel gather path;
+    'mixed': both within one launch."""
+    import hoig_b200._lib as L
+    n, h, c, k, hid = 2, 32, 128, 5, 128
+    src, tgt, flow, w0, b1, w2, b2 = _attn_inputs(n, h, c, k, 11)
+    g = torch.Generator().manual_seed(13)
+    small = torch.rand(n, h, h, 2, generator=g) * 5.0 - 3.0          # [-3, 2)
+    if flows == "hogan_like":
+        flow = small
+    elif flows == "mixed":
+        flow = torch.where((torch.arange(h)[None, :, None, None] < h // 2), small, flow)
+    gt = torch.randn(n, h + 4, h + 4, hid, generator=g).to(dtype)
+    gs = torch.randn(n, h + 8, h + 8, hid, generator=g).to(dtype)
+    src, tgt = src.to(dtype), tgt.to(dtype)
+    outs = []
+    try:
+        for mode in (0, 1):
+            L.lib().hoig_set_attn_tc_mode(mode)
+            out = ops.attn_combine(gt.cuda(), gs.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), src.cuda(), flow.cuda(), tgt.cuda(),
+                                   torch.empty(n, h, h, c, dtype=dtype, device="cuda"), k)
+            torch.cuda.synchronize()
+            outs.append(out.cpu().float())
+    finally:
+        L.lib().hoig_set_attn_tc_mode(1)
+    ref = emu_ops.attn_combine(gt, gs, b1, w2, b2, src, flow, tgt, torch.empty(n, h, h, c), k)
+    tol = TOL[dtype] * 2.5
+    d_ref = (outs[1] - ref).abs().max().item()
+    d_modes = (outs[1] - outs[0]).abs().max().item()
+    print(f"attn_combine tc {dtype} {flows}: vs contract {d_ref:.3e}, vs gather path {d_modes:.3e}")
+    assert d_ref <= tol and d_modes <= tol
+    if flows == "large_random":
+        assert torch.equal(outs[0], outs[1])          # same arithmetic on the gather path
+
+
+def test_attn_combine_tc_in_place_and_channel_slices():
+    """The generator calls it in place (out = tgt = tsf) on full tensors; also exercise ld > C views."""
+    n, h, c, k, hid, dtype = 1, 16, 64, 5, 128, torch.float16
+    src, tgt, flow, w0, b1, w2, b2 = _attn_inputs(n, h, c, k, 21)
+    flow = torch.rand(n, h, h, 2, generator=torch.Generator().manual_seed(2)) * 5.0 - 3.0
+    g = torch.Generator().manual_seed(5)
+    gt = torch.randn(n, h + 4, h + 4, hid, generator=g).to(dtype)
+    gs = torch.randn(n, h + 8, h + 8, hid, generator=g).to(dtype)
+    sbuf = torch.randn(n, h, h, c + 64, generator=g).to(dtype).cuda()
+    tbuf = torch.randn(n, h, h, c + 64, generator=g).to(dtype).cuda()
+    s_v, t_v = sbuf[..., :c], tbuf[..., 64:]
+    ref = emu_ops.attn_combine(gt, gs, b1, w2, b2, s_v.cpu(), flow, t_v.cpu(), torch.empty(n, h, h, c), k)
+    ops.attn_combine(gt.cuda(), gs.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), s_v, flow.cuda(), t_v, t_v, k)
+    torch.cuda.synchronize()
+    assert (t_v.cpu().float() - ref).abs().max().item() <= TOL[dtype] * 2.5
