@@ -748,8 +748,8 @@ attn_combine_kernel(const T *__restrict__ gt, int64_t ldgt, const T *__restrict_
 // ---- attn_combine on the tensor cores, source tiles staged in shared memory -------------------------------------------------------
 // The weighted patch sum  out[p][c] = sum_u coef[p][u] * src[patch_p(u)][c]  (36 taps per pixel, all channels) is 85 % of attn_combine's
 // work and was instruction-issue bound as per-pixel gathers.  For a TILE of 8 x 8 pixels whose (unclamped) patches fall into a window of
-// WW x WH <= 336 source positions -- always the case for HOGAN's flows, which are normalised coordinates used as pixel offsets (quirk Q1,
-// |flow| <= 3) -- it is a small dense GEMM:   OUT[64 px][C] = A[64 px][WW*WH] * S[WW*WH][C]
+// WW x WH <= 256 source positions -- the case for HOGAN's flows, which are normalised coordinates used as pixel offsets (quirk Q1,
+// |flow| <= 3) and vary smoothly -- it is a small dense GEMM:   OUT[64 px][C] = A[64 px][WW*WH] * S[WW*WH][C]
 //   A: the pixels' 36 coefficients scattered to their window positions (zeros elsewhere), built once per tile in shared memory (fp16/bf16);
 //   S: the window's source pixels (border positions replicate the clamped pixel, so unclamped patch coordinates index it directly), staged
 //      in shared memory 64 channels at a time with 16-byte cp.async copies (XOR-swizzled rows, conflict-free ldmatrix);
@@ -779,16 +779,16 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
-constexpr int ATC_TILE = 8, ATC_PX = 64, ATC_KMAX = 336, ATC_AP = 344;       // tile side, pixels per tile, window capacity, A row pitch (halves)
-constexpr int ATC_CONST_BYTES = 16384, ATC_A_BYTES = ATC_PX * ATC_AP * 2, ATC_S_BYTES = ATC_KMAX * 128;
-constexpr int ATC_SMEM = ATC_CONST_BYTES + ATC_A_BYTES + ATC_S_BYTES;           // 103424 B: two CTAs per SM
+constexpr int ATC_TILE = 8, ATC_PX = 64, ATC_KMAX = 256, ATC_AP = 264;       // tile side, pixels per tile, window capacity (16 x 16), A row pitch (halves)
+constexpr int ATC_CONST_BYTES = 15360, ATC_A_BYTES = ATC_PX * ATC_AP * 2, ATC_S_BYTES = 2 * ATC_KMAX * 128;   // S: two buffers (slab s + 1 staged during slab s)
+constexpr int ATC_SMEM = ATC_CONST_BYTES + ATC_A_BYTES + ATC_S_BYTES;           // 114688 B: two CTAs per SM
 
 template <typename T>
 __global__ void __launch_bounds__(256, 2)
 attn_combine_tc_kernel(const T *__restrict__ gt, int64_t ldgt, const T *__restrict__ gs, int64_t ldgs, const float *__restrict__ b1,
                        const float *__restrict__ w2, const float *__restrict__ b2, const T *__restrict__ src, int64_t lds,
                        const float *__restrict__ flow, const T *__restrict__ tgt, int64_t ldt, T *__restrict__ dst, int64_t ldd,
-                       int N, int h, int C)
+                       int N, int h, int C, int debug)
 {
     constexpr int K = 5, KK = 25, HID = 128, PK = K + 1, R = K / 2;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -797,6 +797,7 @@ attn_combine_tc_kernel(const T *__restrict__ gt, int64_t ldgt, const T *__restri
     float *s_b2 = s_b1 + HID;                                       // [KK] (32 reserved)
     int *s_box = reinterpret_cast<int *>(s_b2 + 32);                // bx0, by0, WW, fits
     int *s_xy = s_box + 4;                                          // [64][2]: x0, y0 of every pixel of the tile
+    int *s_off = s_xy + 2 * ATC_PX;                                 // [ATC_KMAX]: element offset of the (clamped) source pixel of every window position
     T *sA = reinterpret_cast<T *>(smem_raw + ATC_CONST_BYTES);
     uint8_t *sS = smem_raw + ATC_CONST_BYTES + ATC_A_BYTES;
     float *s_coef = reinterpret_cast<float *>(sS);                  // fallback path only: [8 warps][4][PK*PK+4] (S is idle then)
@@ -834,6 +835,10 @@ attn_combine_tc_kernel(const T *__restrict__ gt, int64_t ldgt, const T *__restri
         const bool fits = wpos > 0;
         const int ksteps = (wpos + 15) / 16, kcols = ksteps * 16;
         if (fits) {           // zero the used columns of A (16-byte stores; AP * 2 and kcols * 2 are multiples of 16)
+            for (int pos = threadIdx.x; pos < wpos; pos += blockDim.x) {
+                const int wy = pos / WW, wx = pos - wy * WW;
+                s_off[pos] = (max(min(by0 + wy, h - 1), 0) * h + max(min(bx0 + wx, h - 1), 0)) * (int)lds;
+            }
             const int per_row = kcols / 8;
             for (int i = threadIdx.x; i < ATC_PX * per_row; i += blockDim.x)
                 *reinterpret_cast<uint4 *>(sA + (i / per_row) * ATC_AP + (i % per_row) * 8) = make_uint4(0u, 0u, 0u, 0u);
@@ -841,7 +846,7 @@ attn_combine_tc_kernel(const T *__restrict__ gt, int64_t ldgt, const T *__restri
         __syncthreads();
         // ---- phase 1: per pixel (8 lanes each): hidden, logits, softmax, the 36 patch coefficients
 #pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
+        for (int pass = 0; pass < ((debug & 2) ? 0 : 2); ++pass) {
             const int pi = pass * 32 + warp * 4 + grp;          // pixel of the tile
             const int x = tx * ATC_TILE + (pi & 7), y = ty * ATC_TILE + (pi >> 3);
             const int64_t pix = ((int64_t)n * h + y) * h + x;
@@ -943,28 +948,48 @@ attn_combine_tc_kernel(const T *__restrict__ gt, int64_t ldgt, const T *__restri
                 __syncwarp();
             }
         }
-        if (!fits) continue;
-        // ---- phase 2: OUT[64][C] = A[64][kcols] * S[kcols][C], 64 channels per slab
+        if (!fits || (debug & 1)) continue;
+        // ---- phase 2: OUT[64][C] = A[64][kcols] * S[kcols][C], 64 channels per slab; slab s + 1 is staged (cp.async) while slab s is
+        //      multiplied when the window fits twice into the S region
         const int mt = warp & 3, nh = warp >> 2, g = lane >> 2, tq = lane & 3;
         const uint32_t a_addr = sA_u + (uint32_t)(((mt * 16 + (lane & 15)) * ATC_AP + (lane >> 4) * 8) * 2);
         const int b_krow = (lane & 7) + ((lane >> 3) & 1) * 8, b_csel = lane >> 4;     // ldmatrix.trans source row / chunk select of this lane
         const T *splane = src + (int64_t)n * h * h * lds;
-#pragma unroll 1
-        for (int slab = 0; slab < C / 64; ++slab) {
-            __syncthreads();                   // A complete (first slab) / every warp is done reading S of the previous slab
+        const int nslab = C / 64;
+        auto stage = [&](int slab, uint32_t base) {
             for (int i = threadIdx.x; i < kcols * 8; i += blockDim.x) {
                 const int pos = i >> 3, c = i & 7;
-                const uint32_t d = sS_u + (uint32_t)(pos * 128 + ((c ^ (pos & 7)) << 4));
-                if (pos < wpos) {
-                    const int wy = pos / WW, wx = pos - wy * WW;
-                    const int sy = max(min(by0 + wy, h - 1), 0), sx = max(min(bx0 + wx, h - 1), 0);
-                    cp_async16(d, splane + ((int64_t)sy * h + sx) * lds + slab * 64 + c * 8);
-                } else {
-                    asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(d), "r"(0u) : "memory");
-                }
+                const uint32_t d = base + (uint32_t)(pos * 128 + ((c ^ (pos & 7)) << 4));
+                if (pos < wpos) cp_async16(d, splane + s_off[pos] + slab * 64 + c * 8);
+                else asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(d), "r"(0u) : "memory");
             }
-            asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-            __syncthreads();
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        int64_t pix_r[2];
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+            const int r = mt * 16 + g + hrow * 8;
+            pix_r[hrow] = ((int64_t)n * h + ty * ATC_TILE + (r >> 3)) * h + tx * ATC_TILE + (r & 7);
+        }
+        __syncthreads();                       // A and s_off complete
+        stage(0, sS_u);
+#pragma unroll 1
+        for (int slab = 0; slab < nslab; ++slab) {
+            const uint32_t sbuf = sS_u + (uint32_t)((slab & 1) * ATC_KMAX * 128);
+            if (slab + 1 < nslab) {
+                stage(slab + 1, sS_u + (uint32_t)(((slab + 1) & 1) * ATC_KMAX * 128));
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            // the target values this lane will add to (loaded now, consumed after the MMAs)
+            uint32_t tv[2][4];
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    tv[hrow][j] = *reinterpret_cast<const uint32_t *>(tgt + pix_r[hrow] * ldt + slab * 64 + (nh * 4 + j) * 8 + 2 * tq);
+            __syncthreads();                   // this slab's S is visible to every warp
             float acc[4][4];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -975,7 +1000,7 @@ attn_combine_tc_kernel(const T *__restrict__ gt, int64_t ldgt, const T *__restri
                 uint32_t af[4], bf0[4], bf1[4];
                 ldmatrix_x4(af, a_addr + (uint32_t)(ks * 32));
                 const int krow = ks * 16 + b_krow;
-                const uint32_t rb = sS_u + (uint32_t)(krow * 128);
+                const uint32_t rb = sbuf + (uint32_t)(krow * 128);
                 ldmatrix_x4_trans(bf0, rb + (uint32_t)((((nh * 4 + 0 + b_csel) ^ (krow & 7))) << 4));
                 ldmatrix_x4_trans(bf1, rb + (uint32_t)((((nh * 4 + 2 + b_csel) ^ (krow & 7))) << 4));
                 mma_16816<T>(acc[0], af, bf0[0], bf0[1]);
@@ -985,18 +1010,15 @@ attn_combine_tc_kernel(const T *__restrict__ gt, int64_t ldgt, const T *__restri
             }
             // epilogue: dst = tgt + OUT; lane holds rows g, g + 8 of its row tile and channels 2*tq, 2*tq + 1 of each 8-channel group
 #pragma unroll
-            for (int hrow = 0; hrow < 2; ++hrow) {
-                const int r = mt * 16 + g + hrow * 8;
-                const int64_t pix = ((int64_t)n * h + ty * ATC_TILE + (r >> 3)) * h + tx * ATC_TILE + (r & 7);
+            for (int hrow = 0; hrow < 2; ++hrow)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int ch = slab * 64 + (nh * 4 + j) * 8 + 2 * tq;
-                    const uint32_t tv = *reinterpret_cast<const uint32_t *>(tgt + pix * ldt + ch);
                     float lo, hi;
-                    unpack2<T>(tv, lo, hi);
-                    *reinterpret_cast<uint32_t *>(dst + pix * ldd + ch) = pack2<T>(lo + acc[j][hrow * 2], hi + acc[j][hrow * 2 + 1]);
+                    unpack2<T>(tv[hrow][j], lo, hi);
+                    *reinterpret_cast<uint32_t *>(dst + pix_r[hrow] * ldd + slab * 64 + (nh * 4 + j) * 8 + 2 * tq) =
+                        pack2<T>(lo + acc[j][hrow * 2], hi + acc[j][hrow * 2 + 1]);
                 }
-            }
+            __syncthreads();                   // every warp is done with this slab's S before it is overwritten
         }
     }
 }
@@ -1374,6 +1396,7 @@ extern "C" int hoig_replicate_pad(const void *src, int64_t lds, void *dst, int64
     });
 }
 
+static int g_attn_debug = 0;
 static int g_attn_tc = 1;      // HOIG_ATTN_TC / hoig_set_attn_tc_mode: 1 = tensor-core attn_combine with staged source windows, 0 = per-pixel gathers
 extern "C" void hoig_set_attn_tc_mode(int on) { g_attn_tc = on ? 1 : 0; }
 
@@ -1396,6 +1419,8 @@ extern "C" int hoig_attn_combine(const void *gt, int64_t ldgt, const void *gs, i
         env_parsed = true;
         const char *e = getenv("HOIG_ATTN_TC");
         if (e) g_attn_tc = atoi(e) ? 1 : 0;
+        const char *dbg = getenv("HOIG_ATTN_DEBUG");       // timing knock-outs (garbage results): 1 = no patch-sum GEMM, 2 = no per-pixel phase
+        if (dbg) g_attn_debug = atoi(dbg);
     }
     if (g_attn_tc && (dtype == HOIG_BF16 || dtype == HOIG_F16) && k == 5 && h % ATC_TILE == 0 && C % 64 == 0) {
         // tensor-core formulation with shared-memory staging of the source window (attn_combine_tc_kernel)
@@ -1406,14 +1431,14 @@ extern "C" int hoig_attn_combine(const void *gt, int64_t ldgt, const void *gs, i
                 cudaFuncSetAttribute(attn_combine_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM) != cudaSuccess)
                 return check_launch("attn_combine_tc smem attribute");
             attn_combine_tc_kernel<__half><<<tgrid, 256, ATC_SMEM, as_stream(stream)>>>(
-                (const __half *)gt, ldgt, (const __half *)gs, ldgs, b1, w2, b2, (const __half *)src, lds, flow, (const __half *)tgt, ldt, (__half *)dst, ldd, N, h, C);
+                (const __half *)gt, ldgt, (const __half *)gs, ldgs, b1, w2, b2, (const __half *)src, lds, flow, (const __half *)tgt, ldt, (__half *)dst, ldd, N, h, C, g_attn_debug);
         } else {
             if (first_use_on_device(SLOT_ATTN_TC_BF16) &&
                 cudaFuncSetAttribute(attn_combine_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM) != cudaSuccess)
                 return check_launch("attn_combine_tc smem attribute");
             attn_combine_tc_kernel<__nv_bfloat16><<<tgrid, 256, ATC_SMEM, as_stream(stream)>>>(
                 (const __nv_bfloat16 *)gt, ldgt, (const __nv_bfloat16 *)gs, ldgs, b1, w2, b2, (const __nv_bfloat16 *)src, lds, flow, (const __nv_bfloat16 *)tgt, ldt,
-                (__nv_bfloat16 *)dst, ldd, N, h, C);
+                (__nv_bfloat16 *)dst, ldd, N, h, C, g_attn_debug);
         }
         return check_launch("attn_combine_tc_kernel");
     }

@@ -148,13 +148,17 @@ def test_commuted_attention_block_vs_reference_formulation(dtype):
 def test_attn_combine_tensor_core_path_vs_gather_path_and_contract(dtype, flows):
     """attn_combine_tc_kernel (8x8-pixel tiles, source window staged in shared memory, patch sum as an mma.sync GEMM) against the
     per-pixel gather kernel and the op contract.  'hogan_like': normalised coordinates used as pixel offsets (|flow| <= 3, quirk Q1) --
-    every tile takes the staged path; 'large_random': windows exceed the capacity -- every tile takes the in-kernel gather path;
+    (almost) every tile takes the staged path; 'large_random': windows exceed the capacity -- every tile takes the in-kernel gather path;
     'mixed': both within one launch."""
     import hoig_b200._lib as L
     n, h, c, k, hid = 2, 32, 128, 5, 128
     src, tgt, flow, w0, b1, w2, b2 = _attn_inputs(n, h, c, k, 11)
     g = torch.Generator().manual_seed(13)
-    small = torch.rand(n, h, h, 2, generator=g) * 5.0 - 3.0          # [-3, 2)
+    # the generator's flows: T - identity grid with T in [-1, 1] or the -2 sentinel, smooth except at mask borders (quirk Q1)
+    ramp = torch.arange(-1.0, 1.0, 2.0 / h)
+    small = torch.stack([-2.0 - ramp[None, :].expand(h, h), 0.6 * torch.sin(torch.arange(h) / 5.0)[:, None].expand(h, h) - ramp[:, None]], -1)
+    small = small[None].repeat(n, 1, 1, 1).clone()
+    small[:, 10:20, 12:24] += torch.rand(n, 10, 12, 2, generator=g) * 1.5          # a 'valid correspondence' patch with per-pixel jitter
     if flows == "hogan_like":
         flow = small
     elif flows == "mixed":
