@@ -1054,36 +1054,42 @@ struct FoldSegs8 {          // per output channel g: its NCHW plane base (image 
 // chunks from consecutive lanes (the per-pixel kernel above scatters 16-byte pieces 128+ bytes apart).
 template <typename T>
 __global__ void __launch_bounds__(256) hunfold_row_kernel(const float *__restrict__ src, int C, int H, int W, int k, T *__restrict__ dst,
-                                                          int64_t ldd, int Cpad)
+                                                          int64_t ldd, int Cpad, int rows)
 {
-    constexpr int PX = 128, MAXC = 16, MAXK = 7;
-    __shared__ float tile[MAXC][PX + MAXK - 1];
-    __shared__ int8_t s_of[256], c_of[256];   // channel kc -> (tap s, input channel c), s = -1: zero padding
-    const int segs = W / PX;
-    const int x0 = (blockIdx.x % segs) * PX, y = (blockIdx.x / segs) % H, b = blockIdx.x / (segs * H);
+    // A CTA takes `rows` consecutive image rows of one 128-pixel column segment.  Every thread owns ONE 8-channel chunk position
+    // (its (tap, input channel) sources stay in registers) and walks the pixels, so a warp writes four pixels' 128 contiguous bytes
+    // per store instruction and the per-row work is: C x 134 coalesced loads, a barrier, 8 shared loads + one 16-byte store per chunk.
+    constexpr int PX = 128, MAXC = 16, MAXK = 7, TW = PX + MAXK - 1;
+    __shared__ float tile[2][MAXC][TW];
+    const int segs = W / PX, rgroups = H / rows;
+    const int x0 = (blockIdx.x % segs) * PX, y0 = ((blockIdx.x / segs) % rgroups) * rows, b = blockIdx.x / (segs * rgroups);
     const int halo = k / 2, tw = PX + k - 1;
-    for (int i = threadIdx.x; i < Cpad; i += blockDim.x) {
-        const int sft = i / C;
-        s_of[i] = sft < k ? (int8_t)sft : (int8_t)-1;
-        c_of[i] = (int8_t)(i - sft * C);
-    }
-    const float *row = src + ((int64_t)b * C * H + y) * W;
-    for (int i = threadIdx.x; i < C * tw; i += blockDim.x) {
-        const int c = i / tw, j = i - c * tw, xx = x0 - halo + j;
-        tile[c][j] = (xx >= 0 && xx < W) ? __ldg(row + (int64_t)c * H * W + xx) : 0.f;
-    }
-    __syncthreads();
-    const int chunks = Cpad / 8;
-    T *drow = dst + (((int64_t)b * H + y) * W + x0) * ldd;
-    for (int i = threadIdx.x; i < PX * chunks; i += blockDim.x) {
-        const int px = i / chunks, ch = i - px * chunks;
-        float v[8];
+    const int chunks = Cpad / 8, ch = threadIdx.x % chunks, px0 = threadIdx.x / chunks, pstep = blockDim.x / chunks;
+    int off[8];                                   // source of channel ch*8 + j inside a tile row set: c * TW + tap, or -1 (zero padding)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int kc = ch * 8 + j, sft = s_of[kc];
-            v[j] = sft >= 0 ? tile[c_of[kc]][px + sft] : 0.f;
+    for (int j = 0; j < 8; ++j) {
+        const int kc = ch * 8 + j, sft = kc / C;
+        off[j] = sft < k ? (kc - sft * C) * TW + sft : -1;
+    }
+    auto load_row = [&](int y, int buf) {
+        const float *row = src + ((int64_t)b * C * H + y) * W;
+        for (int i = threadIdx.x; i < C * tw; i += blockDim.x) {
+            const int c = i / tw, j = i - c * tw, xx = x0 - halo + j;
+            tile[buf][c][j] = (xx >= 0 && xx < W) ? __ldg(row + (int64_t)c * H * W + xx) : 0.f;
         }
-        store8(drow + (int64_t)px * ldd + ch * 8, v);
+    };
+    load_row(y0, 0);
+    for (int r = 0; r < rows; ++r) {
+        __syncthreads();                          // row r is in tile[r & 1]; everyone is done reading tile[(r + 1) & 1]
+        if (r + 1 < rows) load_row(y0 + r + 1, (r + 1) & 1);
+        const float *tl = &tile[r & 1][0][0];
+        T *drow = dst + (((int64_t)b * H + y0 + r) * W + x0) * ldd + ch * 8;
+        for (int px = px0; px < PX; px += pstep) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = off[j] >= 0 ? tl[off[j] + px] : 0.f;
+            store8(drow + (int64_t)px * ldd, v);
+        }
     }
 }
 
@@ -1341,8 +1347,11 @@ extern "C" int hoig_hunfold_nchw(const float *src, int B, int C, int H, int W, i
     if (n == 0) return HOIG_OK;
     return dispatch(dtype, [&](auto *tag) {
         using T = std::remove_pointer_t<decltype(tag)>;
-        if (W % 128 == 0 && C <= 16 && k <= 7 && Cpad <= 256)
-            hunfold_row_kernel<T><<<(unsigned)(n / 128), 256, 0, as_stream(stream)>>>(src, C, H, W, k, (T *)dst, ldd, Cpad);
+        const int chunks = Cpad / 8;
+        if (W % 128 == 0 && C <= 16 && k <= 7 && Cpad <= 256 && 256 % chunks == 0) {
+            const int rows = H % 8 == 0 ? 8 : (H % 4 == 0 ? 4 : 1);
+            hunfold_row_kernel<T><<<(unsigned)(n / 128 / rows), 256, 0, as_stream(stream)>>>(src, C, H, W, k, (T *)dst, ldd, Cpad, rows);
+        }
         else
             hunfold_kernel<T><<<ceil_div(n, TPB), TPB, 0, as_stream(stream)>>>(src, B, C, H, W, k, (T *)dst, ldd, Cpad);
         return check_launch("hunfold_kernel");

@@ -214,6 +214,8 @@ class GeneratorB200(nn.Module):
         self._seen_epoch = -1
         self._graphs: Dict[tuple, object] = {}         # captured forwards, see forward()
         self.auto_graph = os.environ.get("HOIG_AUTO_GRAPH", "1") != "0"
+        # bg_model / obj_model run twice with the same weights (source and target side): one pass over a batch of 2B instead
+        self.batch_shared_passes = os.environ.get("HOIG_BATCH2", "1") != "0"
         self.auto_graph_after, self.auto_graph_max = 2, 2   # eager calls before capture; captured shapes kept
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.refresh_weights())
         self.reset_parameters()
@@ -705,7 +707,7 @@ class GeneratorB200(nn.Module):
             src_bg.append(src_armask)
         if tsf_armask is not None:
             tsf_bg.append(tsf_armask)
-        if len(src_bg) == len(tsf_bg):
+        if len(src_bg) == len(tsf_bg) and self.batch_shared_passes:
             # the two bg_model passes share their weights: one pass over a batch of 2B (InstanceNorm statistics are per sample)
             both = self._bg([torch.cat([a, b], 0) for a, b in zip(src_bg, tsf_bg)])
             nb = bg_inputs.shape[0]
@@ -757,7 +759,7 @@ class GeneratorB200(nn.Module):
         s_xy, t_xy = xy[:n], xy[n:]
         # obj_model runs on the source and the target object with the same weights: one pass over a batch of 2B
         obj_conds = None if src_obj_conds is None or tsf_obj_conds is None else torch.cat([src_obj_conds, tsf_obj_conds], 0)
-        if (src_obj_conds is None) == (tsf_obj_conds is None):
+        if (src_obj_conds is None) == (tsf_obj_conds is None) and self.batch_shared_passes:
             self._unet_features("obj_model", torch.cat([src_obj_inputs, tsf_obj_inputs], 0), obj_conds, {}, xy[..., c0:])
         else:
             self._unet_features("obj_model", src_obj_inputs, src_obj_conds, {}, s_xy[..., c0:])
