@@ -43,8 +43,7 @@ print(json.dumps({"meshes": N, "faces": F, "ms": ms, "meshes_per_s": N / ms * 1e
                   "achieved_GBs": gbs, "hbm_peak_GBs": peak, "frac": gbs / peak, "covered_frac": (fim >= 0).float().mean().item()}))
 
 try:
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from test_gpu_rasterizer import _load_ref, _ref_rasterize
+    from oracle.ref_kernels import load_ref as _load_ref, ref_rasterize as _ref_rasterize
     mod = _load_ref("ref_rasterize_cuda")
     if mod is not None:
         sub = faces[:64].contiguous()

@@ -15,7 +15,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 dtype = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}[sys.argv[2] if len(sys.argv) > 2 else "f16"]
 g = create("generator_spade_attn", dtype=dtype, **CFG).cuda().eval()
 inp = {k: v.cuda() for k, v in synth.generator_inputs(B, seed=1, size=256).items()}
-for _ in range(2):
+for _ in range(0 if os.environ.get("HOIG_PROFILE_SINGLE") else 2):      # HOIG_PROFILE_SINGLE=1: exactly one forward (ncu captures)
     g(**inp)
 torch.cuda.synchronize()
 _lib.recorder.reset(timing=True)
