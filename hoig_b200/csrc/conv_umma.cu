@@ -898,6 +898,7 @@ int g_umma_debug = 0;
 int g_contig_mode = 1;      // HOIG_UMMA_CONTIG
 int g_mma_stats = 1;        // HOIG_UMMA_MMA_STATS
 int g_halo_mode = 1;        // HOIG_UMMA_HALO: row-halo activation reuse for full-row tiles
+int g_small_split_mode = 1; // HOIG_UMMA_SMALL_SPLIT: narrower n-tiles when a launch has fewer work units than half the SMs (small batches)
 int g_tap_skip_mode = 1;    // HOIG_UMMA_TAP_SKIP: transposed convs skip (n-tile, tap) k-blocks whose weight blocks are structurally zero
 int g_early_release = 0;    // HOIG_UMMA_EARLY_RELEASE
 int g_relaxed_release = 1;  // HOIG_UMMA_RELAXED_RELEASE
@@ -936,8 +937,15 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     const ConvParams &p = P.c;
     HOIG_REQUIRE(p.Npad <= 4096, "conv2d: Cout too large");
     P.BN = p.Npad <= 256 ? p.Npad : 256;
-    P.n_tiles = ceil_div(p.Npad, P.BN);
     P.m_tiles = p.N * p.tiles_per_image;
+    // Small batches (the eval.py case, batch 1): a 32x32 layer has only 8 pixel tiles, so wide n-tiles leave most SMs idle.
+    // Narrower n-tiles multiply the number of work units (each re-reads the L2-resident activations): 512 -> 512 at batch 1 runs on
+    // 64 SMs instead of 16.  Never taken at batch >= 8 (the unit count is already above half the SM count).
+    if (g_small_split_mode)
+        while (P.BN > 64 && (P.BN / 2) % 16 == 0 && p.Npad % (P.BN / 2) == 0 &&
+               (int64_t)P.m_tiles * ceil_div(p.Npad, P.BN) < device_sm_count() / 2)
+            P.BN /= 2;
+    P.n_tiles = ceil_div(p.Npad, P.BN);
     P.k_blocks = p.Kpad / BK;
     P.cpt_shift = -1;
     if (p.Cin < 64) {
@@ -1072,6 +1080,8 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
         if (ms) g_mma_stats = atoi(ms);
         const char *hm = getenv("HOIG_UMMA_HALO");
         if (hm) g_halo_mode = atoi(hm);
+        const char *ss = getenv("HOIG_UMMA_SMALL_SPLIT");
+        if (ss) g_small_split_mode = atoi(ss);
         const char *ts = getenv("HOIG_UMMA_TAP_SKIP");
         if (ts) g_tap_skip_mode = atoi(ts);
         const char *er = getenv("HOIG_UMMA_EARLY_RELEASE");

@@ -302,8 +302,8 @@ def conv2d(x0: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, *, kh: int
         d.act_table = None
     L = _lib.lib()
     if _lib.recorder.timing:
-        _lib.recorder.tag = (f"{('conv', 'convT', 'attn')[mode]} k{kh} s{stride} Cin{d.C0 + d.C1} Cout{d.Cout} "
-                             f"{H}x{W}->{OH}x{OW} N{N}")
+        _lib.recorder.tag = (f"{('conv', 'convT', 'attn')[mode]} k{kh}x{kw} s{stride} Cin{d.C0 + d.C1} Cout{d.Cout} "
+                             f"{H}x{W}->{OH}x{OW} N{N}" + (" spade" if spade_x is not None else ""))
     fn = L.hoig_conv2d_simt if simt else L.hoig_conv2d
     _lib.check(fn(ctypes.byref(d), _stream()), "conv2d")
     return out

@@ -37,10 +37,11 @@ for (name, tag), (n, ms) in rows[:60]:
         extra = f" {by * n / ms / 1e6:8.1f} GB/s"
     elif tag:
         import re
-        m = re.match(r"(\w+) k(\d+) s(\d+) Cin(\d+) Cout(\d+) (\d+)x(\d+)->(\d+)x(\d+) N(\d+)", tag)
-        mode, k, s, cin, cout, h, w, oh, ow, nn = m.group(1), *map(int, m.groups()[1:])
-        px = (h * w) if mode == "convT" else (oh * ow)
-        fl = 2.0 * nn * px * cout * cin * k * k
-        extra = f" {fl * n / ms / 1e9:8.1f} TFLOP/s(padded)"
+        m = re.match(r"(\w+) k(\d+)x(\d+) s(\d+) Cin(\d+) Cout(\d+) (\d+)x(\d+)->(\d+)x(\d+) N(\d+)", tag)
+        mode, kh, kw, s, cin, cout, h, w, oh, ow, nn = m.group(1), *map(int, m.groups()[1:])
+        # FLOPs of the GEMM as the layer defines it (2 * MACs over the operand shapes the kernel sees: input channels padded to 8 / the
+        # 7-tap unfold padded to 64; a transposed conv counts its 9 live taps per input pixel, not the 16 blocks of the packed matrix)
+        fl = 2.0 * nn * (h * w if mode == "convT" else oh * ow) * cout * cin * kh * kw
+        extra = f" {fl * n / ms / 1e9:8.1f} TFLOP/s"
     print(f"{ms:9.3f} ms {100 * ms / total:5.1f}% n={n:3d} {name.replace('hoig_', ''):16s} {tag or ''}{extra}")
 print(f"listed {acc:.1f} ms of {total:.1f}")

@@ -112,3 +112,33 @@ def test_stepwise_kernels_vs_reference(fx, inp):
         assert torch.equal(ops.erode(not_hand, 3).cpu(), torch.from_numpy(fx[key]).float())
     T = ops.bc_transform(_c(fx["faces_src"]), _c(fx["fim_ref"]), _wim(fx, "ref"))
     assert (T.cpu() - torch.from_numpy(fx["bc_T"])).abs().max().item() <= 1e-6
+
+
+def test_hand_recovery_flow_module_end_to_end_vs_reference(fx, inp):
+    """Row N1: ``HandRecoveryFlowB200`` from MESHES (own projection + rasterization + texture warp + conditions) against the outputs of
+    the unmodified ``HandRecoveryFlow.forward``.  The projection differs from torch's in the last ulp (<= 2e-6), which moves a handful
+    of silhouette-edge pixels; everything else must agree."""
+    d, _ = inp
+    sc = d["scene"]
+    flow = renderer.HandRecoveryFlowB200(sc.faces_idx, d["map_fn"], d["sem_full"], d["fim_uv"], d["wim_uv"], d["coord"], d["obj_tex"]).cuda()
+    kw, masks = flow(d["src_img"].cuda(), sc.verts_src.cuda(), sc.verts_ref.cuda(), sc.cam.cuda())
+    torch.cuda.synchronize()
+    assert set(kw) == {"bg_inputs", "src_obj_inputs", "src_obj_conds", "src_hand_inputs", "src_hand_conds", "tsf_obj_inputs",
+                       "tsf_obj_conds", "tsf_hand_inputs", "tsf_hand_conds", "T"}
+
+    def frac_diff(t, key):
+        ref = torch.from_numpy(fx[key]).to(t.dtype)
+        return (t.cpu() != ref).float().mean().item()
+
+    assert frac_diff(masks["src_mask_bg"], "out_src_crop_mask_bg") <= 2e-4
+    assert frac_diff(masks["ref_mask_hand"], "out_ref_crop_mask_hand") <= 2e-4
+    assert frac_diff(kw["bg_inputs"][:, 3:], "out_input_G_src_bg_mask") <= 2e-4
+    assert frac_diff(kw["src_obj_conds"][:, 3:], "out_input_G_src_obj_seg") <= 2e-4
+    Tref = torch.from_numpy(fx["out_T_hand"])
+    both = (kw["T"].cpu()[..., 0] > -1.5) & (Tref[..., 0] > -1.5)
+    assert both.float().mean().item() > 0.01
+    assert (kw["T"].cpu() - Tref)[both].abs().max().item() <= 5e-3           # sub-pixel agreement where both are on the hand
+    assert ((kw["T"].cpu()[..., 0] > -1.5) != (Tref[..., 0] > -1.5)).float().mean().item() <= 2e-4
+    s = gi.STRIDE
+    a, b = kw["src_hand_inputs"][..., ::s, ::s].cpu(), torch.from_numpy(fx["out_input_G_src_hand_rgb_s"])
+    assert ((a - b).abs() > 1e-5).float().mean().item() <= 1e-3
