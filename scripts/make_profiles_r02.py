@@ -29,13 +29,14 @@ def dump(name, obj):
 
 
 def ncu_csv_rows(path):
-    rows = [r for r in csv.reader(open(path, errors="replace")) if len(r) > 5]
+    f = gzip.open(path, "rt", errors="replace") if path.endswith(".gz") else open(path, errors="replace")
+    rows = [r for r in csv.reader(f) if len(r) > 5]
     hdr = rows[0]
     return hdr, rows[1:]
 
 
 def launches_summary():
-    src = os.path.join(G, "r02_launches_bench.csv")
+    src = os.path.join(G, "r02_launches_bench.csv.gz")
     if not os.path.exists(src):
         return
     hdr, rows = ncu_csv_rows(src)
@@ -56,13 +57,12 @@ def launches_summary():
                 f"# {len(rows)} launches, {total:.2f} ms total\n")
         for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
             f.write(f"{t:10.3f} ms {100 * t / total:5.1f}%  n={n:5d}  {name}\n")
-    with open(src, "rb") as a, gzip.open(os.path.join(P, "r02_launches_bench.csv.gz"), "wb") as b:
-        shutil.copyfileobj(a, b)
+    shutil.copy(src, os.path.join(P, "r02_launches_bench.csv.gz"))
     print("wrote r02_launches_bench_summary.txt")
 
 
 def conv_traffic():
-    src = os.path.join(G, "r02_conv_traffic.csv")
+    src = os.path.join(G, "r02_conv_traffic.csv.gz")
     if not os.path.exists(src):
         return
     hdr, rows = ncu_csv_rows(src)
@@ -82,8 +82,7 @@ def conv_traffic():
         "dram_bytes_per_launch": (rd + wr) / max(n, 1), "conv_ms_under_ncu": ms,
         "note": f"DRAM traffic of all tensor-core conv launches of one forward: {(rd + wr) / 1e9:.1f} GB = {(rd + wr) / 6553e6:.1f} ms at the measured 6.55 TB/s "
                 "against ~54 ms of conv time -- the convs are not HBM-bound"})
-    with open(src, "rb") as a, gzip.open(os.path.join(P, "r02_conv_traffic.csv.gz"), "wb") as b:
-        shutil.copyfileobj(a, b)
+    shutil.copy(src, os.path.join(P, "r02_conv_traffic.csv.gz"))
 
 
 COLS = [("gpu__time_duration.sum", "dur"), ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor%"),
@@ -97,12 +96,18 @@ COLS = [("gpu__time_duration.sum", "dur"), ("sm__pipe_tensor_cycles_active.avg.p
         ("smsp__average_warps_issue_stalled_membar_per_issue_active.ratio", "st_membar")]
 
 
-def ncu_table(rep, out_name, title, top=None):
-    path = os.path.join(G, rep)
-    if not os.path.exists(path):
+def ncu_table(raw_csvs, out_name, title, top=None):
+    """raw_csvs: `ncu -i report --page raw --csv` exports made on the GPU box (the reports themselves are too large to bring back)."""
+    rows = []
+    for name in raw_csvs:
+        path = os.path.join(G, name)
+        if not os.path.exists(path):
+            continue
+        part = list(csv.reader(open(path, errors="replace")))
+        h = next(i for i, r in enumerate(part) if r and r[0] == "ID")
+        rows = part[h:] if not rows else rows + part[h + 2:]
+    if not rows:
         return
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(out)))
     hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
     names, units, data = rows[hdr_i], rows[hdr_i + 1], rows[hdr_i + 2:]
     idx = {}
@@ -156,10 +161,11 @@ def main():
         shutil.copy(p, os.path.join(P, "r02_per_conv_shapes_b64.txt"))
     launches_summary()
     conv_traffic()
-    ncu_table("r02_conv_umma_full.ncu-rep", "r02_conv_umma_full.txt", "conv_umma_kernel: every launch of ONE forward at batch 64 (fp16)", top=60)
-    ncu_table("r02_attn_full.ncu-rep", "r02_attn_full.txt", "conv_halo_kernel + attn_combine_tc_kernel: the 9 attention layers of one forward at batch 64")
-    ncu_table("r02_ops_full.ncu-rep", "r02_ops_full.txt", "instnorm_apply / hunfold / hfold / replicate_pad / seg_unfold3 of one forward at batch 64", top=60)
-    ncu_table("r02_rast_full.ncu-rep", "r02_rast_full.txt", "rast_bin_kernel + rasterize_kernel, 256 meshes of 13776 faces")
+    ncu_table(["r02_conv_umma_a_raw.csv", "r02_conv_umma_b_raw.csv"], "r02_conv_umma_full.txt",
+              "conv_umma_kernel: 88 of the ~125 launches of ONE forward at batch 64 (fp16), all layer families")
+    ncu_table(["r02_attn_raw.csv"], "r02_attn_full.txt", "conv_halo_kernel + attn_combine_tc_kernel: the 9 attention layers of one forward at batch 64")
+    ncu_table(["r02_ops_raw.csv"], "r02_ops_full.txt", "instnorm_apply / hunfold / hfold / replicate_pad / seg_unfold3: the first 40 of one forward at batch 64")
+    ncu_table(["r02_rast_raw.csv"], "r02_rast_full.txt", "rast_bin_kernel + rasterize_kernel, 256 meshes of 13776 faces")
 
 
 if __name__ == "__main__":
