@@ -260,3 +260,30 @@ def test_vertical_halo_mode_matches_per_tap_boxes(case, dtype):
     assert (a != b).float().mean().item() < 0.05          # almost every element rounds identically
     if outs[0][1] is not None:
         assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-4, atol=0.3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+@pytest.mark.parametrize("hw,cout", [(32, 64), (32, 256), (128, 64)], ids=["32x32_n64_persist", "32x32_n256", "128x128_n64_persist"])
+def test_epilogue_statistics_on_large_mean_planes(dtype, hw, cout):
+    """the MMA-based statistics round x^2 to bf16 before the column sum, so E[x^2] - mean^2 cancels for planes with
+    |mean| >> std.  Quantify it: planes with mean 20 and std ~1 (bias 20).  The variance derived from the epilogue statistics must
+    stay within 5 % (rstd within 2.5 %) of the float64 variance of the stored values even on a 32x32 plane (1024 samples); the
+    means are exact to 1e-4.  (InstanceNorm inputs in the generator are conv outputs of normalised activations: |mean| / std is O(1).)"""
+    g = torch.Generator().manual_seed(hw + cout)
+    N, cin = 2, 64
+    x = torch.randn(N, hw, hw, cin, generator=g).to(dtype)
+    w = torch.randn(cout, cin, 3, 3, generator=g) * (1.0 / (cin * 9) ** 0.5)
+    bias = torch.full((cout,), 20.0)
+    out = torch.empty(N, hw, hw, cout, dtype=dtype, device="cuda")
+    st = torch.zeros(N * cout * 2, dtype=torch.float64, device="cuda")
+    ops.conv2d(x.cuda(), pack_conv_weight(w, dtype).cuda(), out, kh=3, kw=3, stride=1, pad=1, bias=bias.cuda(), stats=st)
+    torch.cuda.synchronize()
+    o = out.double().cpu().reshape(N, hw * hw, cout)
+    st = st.cpu().reshape(N, cout, 2)
+    mean_ref, var_ref = o.mean(1), o.var(1, unbiased=False)
+    mean = st[..., 0] / (hw * hw)
+    var = st[..., 1] / (hw * hw) - mean ** 2
+    assert ((mean - mean_ref).abs() / mean_ref.abs()).max().item() <= 1e-4
+    rel = ((var - var_ref).abs() / var_ref).max().item()
+    print(f"large-mean planes {dtype} {hw}x{hw} N={cout}: worst relative variance error {rel:.3e} (mean/std ~ {float((mean_ref / var_ref.sqrt()).mean()):.1f})")
+    assert rel <= 5e-2
