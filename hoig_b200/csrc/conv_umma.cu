@@ -988,7 +988,6 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     // (scripts/probes/mma_probe.cu: ~65-100 cycles of issue overhead vs 48-64 cycles of execution), so two warps
     // issue, each driving its own pipeline (half of the ring, two of four accumulator stages, alternate tiles).
     P.contig = g_contig_mode;
-    P.mma_stats = g_mma_stats;
     P.dual = (g_dual_mode && P.tma_a && P.BN <= 128 && P.stages >= 4) ? 1 : 0;
     if (P.dual) P.stages &= ~1;
     HOIG_REQUIRE(P.stages >= (P.tma_a ? 2 : LOOKAHEAD + 1), "conv2d: not enough shared memory stages");
@@ -1048,7 +1047,12 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     const size_t smem = (size_t)STG_BYTES + (size_t)P.stages * stage_bytes + (P.bres ? w_bytes : 0) + 1024;
     // persistent register statistics: at most two 16-column chunks per epilogue warp, one n-tile, MMA column sums enabled
     const int ngrp = P.tma_a ? 4 : 3;
-    const bool persist = p.stats && P.mma_stats && P.n_tiles == 1 && P.BN / 16 <= 2 * ngrp && !p.spade_x;
+    const bool persist = p.stats && g_mma_stats && P.n_tiles == 1 && P.BN / 16 <= 2 * ngrp && !p.spade_x;
+    // Statistics method (HOIG_UMMA_MMA_STATS: 0 = shuffle transpose-reduce everywhere, 1 = auto, 2 = warp-level MMAs everywhere).
+    // Auto: the warp-level MMA column sums only where they keep accumulating in registers (persist).  Elsewhere -- the wide / long-K
+    // convs -- legacy HMMA shares the tensor pipe with the UMMAs that bound those convs, while their issue slots are idle: the shuffle
+    // version measured 2 % (512->512) to 18 % (256->128 @128^2) faster there.
+    P.mma_stats = g_mma_stats == 2 ? 1 : (g_mma_stats == 1 ? (persist ? 1 : 0) : 0);
     auto go = [&](auto tag, auto nc, auto ps) {
         using T = std::remove_pointer_t<decltype(tag)>;
         return launch_kernel<T, decltype(nc)::value, decltype(ps)::value>(P, map_w, map_a, grid, smem, stream);
