@@ -75,6 +75,7 @@ struct UmmaParams {
     uint8_t tap_live[16]; // transposed conv: per n-tile, bit t set = tap t of the 2x2 input neighbourhood feeds some parity block of the tile;
                          //    dead (n-tile, tap) k-blocks are skipped by the producers and the MMA issuer (their weight blocks are zero)
     int tap_skip;        // 1: tap_live is in use (TMA-fed transposed conv)
+    int prefetch;        // epilogue: SPADE activation / residual loads issued one chunk ahead (HOIG_UMMA_PREFETCH)
     int early_release;   // epilogue: hand the accumulator stage back right after the last tcgen05.ld (HOIG_UMMA_EARLY_RELEASE)
     int relaxed_release; // epilogue: relaxed (signal-only) arrival on the accumulator barrier (HOIG_UMMA_RELAXED_RELEASE)
     int debug;           // timing knock-outs (HOIG_UMMA_DEBUG, results are garbage): 1 = epilogue only drains TMEM, 2 = A tile loaded once per tile, 4 = no statistics, 8 = no output stores
@@ -697,7 +698,26 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)BN;
             uint32_t ra[16], rb[16];
-            auto finalize = [&](const uint32_t (&r)[16], int ch, auto slot_tag) {
+            // The SPADE epilogue's activation tile and the residual are read once per (row, chunk) at pixel stride: their loads are
+            // issued one chunk AHEAD (right after that chunk's tcgen05.ld), so the L2 latency overlaps the TMEM wait and the
+            // previous chunk's arithmetic instead of stalling every chunk (long-scoreboard was the top stall of these epilogues).
+            const bool res_vec = res && vec_ok;
+            auto prefetch = [&](int ch, uint4 (&pf)[2]) {
+                if (PERSIST) return;      // the register-persistent statistics kernels have no registers to spare (and no SPADE epilogue)
+                if (!P.prefetch) return;
+                const int n0 = nt * BN + ch * 16;
+                if (!valid || n0 >= p.Cout) return;
+                if (spade) pf[0] = *reinterpret_cast<const uint4 *>(static_cast<const T *>(p.spade_x) + m * p.ld_spade_x + (n0 >> 4) * 8);
+                else if (res_vec && n0 + 16 <= p.Cout) {
+                    const T *rr = res + m * p.ldr + n0;
+                    pf[0] = *reinterpret_cast<const uint4 *>(rr); pf[1] = *reinterpret_cast<const uint4 *>(rr + 8);
+                }
+            };
+            auto unpack8 = [](const uint4 &q, float (&u)[8]) {
+                unpack2<T>(q.x, u[0], u[1]); unpack2<T>(q.y, u[2], u[3]); unpack2<T>(q.z, u[4], u[5]); unpack2<T>(q.w, u[6], u[7]);
+            };
+            uint4 pfa[2], pfb[2];
+            auto finalize = [&](const uint32_t (&r)[16], int ch, auto slot_tag, const uint4 (&pf)[2]) {
                 constexpr int slot = decltype(slot_tag)::value;      // which of this warp's (up to two) persistent statistics slots
                 const int c0 = ch * 16;
                     const int n0 = nt * BN + c0;
@@ -726,7 +746,8 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                         const int cb = (n0 >> 4) * 8;
                         if (valid) {
                             float xv[8];
-                            load8(static_cast<const T *>(p.spade_x) + m * p.ld_spade_x + cb, xv);
+                            if (PERSIST || !P.prefetch) load8(static_cast<const T *>(p.spade_x) + m * p.ld_spade_x + cb, xv);
+                            else unpack8(pf[0], xv);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float xn = (xv[j] - s_mod[cb + j]) * s_mod[1024 + cb + j];
@@ -740,10 +761,12 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                     if (res && valid) {
                         if (full && vec_ok) {
                             float u[8];
-                            load8(rrow + c0, u);
+                            if (PERSIST || !P.prefetch) load8(rrow + c0, u);
+                            else unpack8(pf[0], u);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] += u[j];
-                            load8(rrow + c0 + 8, u);
+                            if (PERSIST || !P.prefetch) load8(rrow + c0 + 8, u);
+                            else unpack8(pf[1], u);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[8 + j] += u[j];
                         } else {
@@ -848,20 +871,20 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                 else mbar_arrive_relaxed(tempty0 + 8u * acc);
             };
             const bool early = P.early_release != 0;
-            if (half < n_chunks) tmem_ld16(t_row + (uint32_t)(half * 16), ra);
+            if (half < n_chunks) { tmem_ld16(t_row + (uint32_t)(half * 16), ra); prefetch(half, pfa); }
             else if (early) release();
             for (int ch = half; ch < n_chunks; ch += 2 * ngrp) {
                 tmem_ld_wait(ra);
                 const bool more1 = ch + ngrp < n_chunks;
-                if (more1) tmem_ld16(t_row + (uint32_t)((ch + ngrp) * 16), rb);
+                if (more1) { tmem_ld16(t_row + (uint32_t)((ch + ngrp) * 16), rb); prefetch(ch + ngrp, pfb); }
                 else if (early) release();
-                finalize(ra, ch, std::integral_constant<int, 0>());
+                finalize(ra, ch, std::integral_constant<int, 0>(), pfa);
                 if (more1) {
                     tmem_ld_wait(rb);
                     const bool more2 = ch + 2 * ngrp < n_chunks;
-                    if (more2) tmem_ld16(t_row + (uint32_t)((ch + 2 * ngrp) * 16), ra);
+                    if (more2) { tmem_ld16(t_row + (uint32_t)((ch + 2 * ngrp) * 16), ra); prefetch(ch + 2 * ngrp, pfa); }
                     else if (early) release();
-                    finalize(rb, ch + ngrp, std::integral_constant<int, 1>());
+                    finalize(rb, ch + ngrp, std::integral_constant<int, 1>(), pfb);
                 }
             }
             if (!early) {
@@ -900,6 +923,7 @@ int g_mma_stats = 1;        // HOIG_UMMA_MMA_STATS
 int g_halo_mode = 1;        // HOIG_UMMA_HALO: row-halo activation reuse for full-row tiles
 int g_small_split_mode = 1; // HOIG_UMMA_SMALL_SPLIT: narrower n-tiles when a launch has fewer work units than half the SMs (small batches)
 int g_tap_skip_mode = 1;    // HOIG_UMMA_TAP_SKIP: transposed convs skip (n-tile, tap) k-blocks whose weight blocks are structurally zero
+int g_prefetch = 1;         // HOIG_UMMA_PREFETCH: 0 = never, 1 = SPADE epilogue only (default), 2 = SPADE and residual
 int g_early_release = 0;    // HOIG_UMMA_EARLY_RELEASE
 int g_relaxed_release = 1;  // HOIG_UMMA_RELAXED_RELEASE
 int g_vhalo_mode = 1;       // HOIG_UMMA_VHALO: vertical-halo activation reuse for kh x 1 convs
@@ -1013,6 +1037,7 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     }
     P.debug = g_umma_debug;
     P.early_release = g_early_release;
+    P.prefetch = g_prefetch == 2 ? 1 : (g_prefetch == 1 && p.spade_x ? 1 : 0);   // measured: SPADE epilogue -2.6 %, residual epilogue +1.8 % (off there)
     P.relaxed_release = g_relaxed_release;
     P.tpi_shift = -1;
     if ((p.tiles_per_image & (p.tiles_per_image - 1)) == 0) { P.tpi_shift = 0; while ((1 << P.tpi_shift) < p.tiles_per_image) ++P.tpi_shift; }
@@ -1088,6 +1113,8 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
         if (ss) g_small_split_mode = atoi(ss);
         const char *ts = getenv("HOIG_UMMA_TAP_SKIP");
         if (ts) g_tap_skip_mode = atoi(ts);
+        const char *pf = getenv("HOIG_UMMA_PREFETCH");
+        if (pf) g_prefetch = atoi(pf);
         const char *er = getenv("HOIG_UMMA_EARLY_RELEASE");
         if (er) g_early_release = atoi(er);
         const char *rr = getenv("HOIG_UMMA_RELAXED_RELEASE");

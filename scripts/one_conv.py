@@ -40,6 +40,15 @@ elif which == "s2_64":
     x = rnd(B, 256, 256, 64); w = torch.randn(128, 64, 3, 3, device="cuda") * 0.05
     out = torch.empty(B, 128, 128, 128, dtype=dt, device="cuda")
     kw = dict(kh=3, kw=3, stride=2, pad=1); tr = False; cout = 128
+elif which == "res512":
+    x = rnd(B, 32, 32, 512); w = torch.randn(512, 512, 3, 3, device="cuda") * 0.02
+    out = torch.empty(B, 32, 32, 512, dtype=dt, device="cuda")
+    kw = dict(kh=3, kw=3, stride=1, pad=1, residual=rnd(B, 32, 32, 512)); tr = False; cout = 512
+elif which == "spade":
+    x = rnd(B, 32, 32, 128); w = torch.randn(1024, 128, 3, 3, device="cuda") * 0.05
+    out = torch.empty(B, 32, 32, 512, dtype=dt, device="cuda")
+    sx = rnd(B, 32, 32, 512); sst = torch.zeros(B * 512 * 2, dtype=torch.float64, device="cuda"); ops.plane_stats(sx, sst)
+    kw = dict(kh=3, kw=3, stride=1, pad=1, cout=1024, spade_x=sx, spade_stats=sst, act=ops.ACT_RELU, bias=torch.zeros(1024, device="cuda")); tr = False; cout = None
 else:
     raise SystemExit("unknown shape")
 wp = pack_conv_weight(w, dt, transposed=tr)
