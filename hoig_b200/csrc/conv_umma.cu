@@ -75,6 +75,7 @@ struct UmmaParams {
     uint8_t tap_live[16]; // transposed conv: per n-tile, bit t set = tap t of the 2x2 input neighbourhood feeds some parity block of the tile;
                          //    dead (n-tile, tap) k-blocks are skipped by the producers and the MMA issuer (their weight blocks are zero)
     int tap_skip;        // 1: tap_live is in use (TMA-fed transposed conv)
+    int backoff_ns;      // epilogue: maximum nanosleep between polls of the accumulator-full barrier (HOIG_UMMA_BACKOFF_NS, 0 = spin)
     int prefetch;        // epilogue: SPADE activation / residual loads issued one chunk ahead (HOIG_UMMA_PREFETCH)
     int early_release;   // epilogue: hand the accumulator stage back right after the last tcgen05.ld (HOIG_UMMA_EARLY_RELEASE)
     int relaxed_release; // epilogue: relaxed (signal-only) arrival on the accumulator barrier (HOIG_UMMA_RELAXED_RELEASE)
@@ -694,7 +695,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                 cur_img = n_img; cur_nt = nt;
                 epi_bar(epi_threads);
             }
-            mbar_wait(smem_u32(&tfull_bar[acc]), use & 1);
+            mbar_wait_backoff(smem_u32(&tfull_bar[acc]), use & 1, (uint32_t)P.backoff_ns);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)BN;
             uint32_t ra[16], rb[16];
@@ -923,6 +924,7 @@ int g_mma_stats = 1;        // HOIG_UMMA_MMA_STATS
 int g_halo_mode = 1;        // HOIG_UMMA_HALO: row-halo activation reuse for full-row tiles
 int g_small_split_mode = 1; // HOIG_UMMA_SMALL_SPLIT: narrower n-tiles when a launch has fewer work units than half the SMs (small batches)
 int g_tap_skip_mode = 1;    // HOIG_UMMA_TAP_SKIP: transposed convs skip (n-tile, tap) k-blocks whose weight blocks are structurally zero
+int g_backoff_ns = 0;       // HOIG_UMMA_BACKOFF_NS
 int g_prefetch = 1;         // HOIG_UMMA_PREFETCH: 0 = never, 1 = SPADE epilogue only (default), 2 = SPADE and residual
 int g_early_release = 0;    // HOIG_UMMA_EARLY_RELEASE
 int g_relaxed_release = 1;  // HOIG_UMMA_RELAXED_RELEASE
@@ -1037,6 +1039,7 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     }
     P.debug = g_umma_debug;
     P.early_release = g_early_release;
+    P.backoff_ns = P.k_blocks >= 16 ? g_backoff_ns : 0;      // only where a tile's main loop is long
     P.prefetch = g_prefetch == 2 ? 1 : (g_prefetch == 1 && p.spade_x ? 1 : 0);   // measured: SPADE epilogue -2.6 %, residual epilogue +1.8 % (off there)
     P.relaxed_release = g_relaxed_release;
     P.tpi_shift = -1;
@@ -1113,6 +1116,8 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
         if (ss) g_small_split_mode = atoi(ss);
         const char *ts = getenv("HOIG_UMMA_TAP_SKIP");
         if (ts) g_tap_skip_mode = atoi(ts);
+        const char *bo = getenv("HOIG_UMMA_BACKOFF_NS");
+        if (bo) g_backoff_ns = atoi(bo);
         const char *pf = getenv("HOIG_UMMA_PREFETCH");
         if (pf) g_prefetch = atoi(pf);
         const char *er = getenv("HOIG_UMMA_EARLY_RELEASE");

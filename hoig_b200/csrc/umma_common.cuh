@@ -42,6 +42,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         }
     }
 }
+// Same wait with exponential back-off (nanosleep) between polls: for warps whose wait is long and not latency-critical (the epilogue
+// warps waiting for a whole tile's MMAs).  Twenty spinning warps per SM cost issue slots and, on a power-capped part, clock.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t max_ns)
+{
+    uint32_t done = 0, ns = 32;
+    long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        if (max_ns) {
+            __nanosleep(ns);
+            if (ns < max_ns) ns <<= 1;
+        }
+        if ((spin & 0x3ff) == 0x3ff) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 6000000000ll) __trap();
+        }
+    }
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
 {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
