@@ -788,7 +788,7 @@ __global__ void __launch_bounds__(256, 2)
 attn_combine_tc_kernel(const T *__restrict__ gt, int64_t ldgt, const T *__restrict__ gs, int64_t ldgs, const float *__restrict__ b1,
                        const float *__restrict__ w2, const float *__restrict__ b2, const T *__restrict__ src, int64_t lds,
                        const float *__restrict__ flow, const T *__restrict__ tgt, int64_t ldt, T *__restrict__ dst, int64_t ldd,
-                       int N, int h, int C, int debug)
+                       int N, int h, int C, int debug, int g_phase1_tc)
 {
     constexpr int K = 5, KK = 25, HID = 128, PK = K + 1, R = K / 2;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -844,7 +844,105 @@ attn_combine_tc_kernel(const T *__restrict__ gt, int64_t ldgt, const T *__restri
                 *reinterpret_cast<uint4 *>(sA + (i / per_row) * ATC_AP + (i % per_row) * 8) = make_uint4(0u, 0u, 0u, 0u);
         }
         __syncthreads();
-        // ---- phase 1: per pixel (8 lanes each): hidden, logits, softmax, the 36 patch coefficients
+        // ---- phase 1 (staged path): hidden -> shared memory, logits as a 64 x 32 x 128 warp-level GEMM, softmax + coefficients 4 threads/pixel
+        if (fits && g_phase1_tc && !(debug & 2)) {
+            T *sH = reinterpret_cast<T *>(sS);                                   // [64 px][136]
+            T *sW = reinterpret_cast<T *>(sS + 17408);                           // [32 logits][136] (rows >= KK are zero)
+            float *sL = reinterpret_cast<float *>(sS + 26112);                   // [64 px][32]
+            float *s_fr = reinterpret_cast<float *>(sS + 34304);                 // [64 px][2]: bilinear fractions wx1, wy1
+            constexpr int HP = 136;
+            for (int i = threadIdx.x; i < 32 * (HID / 8); i += blockDim.x) {     // W2 -> 16-bit, once per tile (the S region is reused by phase 2)
+                const int r = i / (HID / 8), c8 = (i % (HID / 8)) * 8;
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = r < KK ? s_w2[r * HID + c8 + j] : 0.f;
+                store8(sW + r * HP + c8, v);
+            }
+            if (threadIdx.x < ATC_PX) {
+                const int x = tx * ATC_TILE + (threadIdx.x & 7), y = ty * ATC_TILE + (threadIdx.x >> 3);
+                const int64_t pix = ((int64_t)n * h + y) * h + x;
+                const float dx = __fadd_rn(__fadd_rn(flow[pix * 2], 0.f), (float)x), dy = __fadd_rn(__fadd_rn(flow[pix * 2 + 1], 0.f), (float)y);
+                s_fr[2 * threadIdx.x] = __fsub_rn(dx, floorf(dx));
+                s_fr[2 * threadIdx.x + 1] = __fsub_rn(dy, floorf(dy));
+            }
+            __syncthreads();
+            // (a) hidden[px][128] = LeakyReLU(Gt + bilinear(Gs) + b1): one (pixel, 8-channel chunk) item per thread and step
+            for (int i = threadIdx.x; i < ATC_PX * (HID / 8); i += blockDim.x) {
+                const int pi = i / (HID / 8), c8 = (i % (HID / 8)) * 8;
+                const int x = tx * ATC_TILE + (pi & 7), y = ty * ATC_TILE + (pi >> 3);
+                const int x0 = s_xy[2 * pi], y0 = s_xy[2 * pi + 1];
+                const float wx1 = s_fr[2 * pi], wy1 = s_fr[2 * pi + 1], wx0 = __fsub_rn(1.f, wx1), wy0 = __fsub_rn(1.f, wy1);
+                float hv[8], u[8];
+                load8(gt + (((int64_t)n * hpt + y + R) * hpt + x + R) * ldgt + c8, hv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) hv[j] += s_b1[c8 + j];
+#pragma unroll
+                for (int qy = 0; qy < 2; ++qy)
+#pragma unroll
+                    for (int qx = 0; qx < 2; ++qx) {
+                        const int cy = max(min(y0 + qy, h - 1 + R), -R) + 2 * R, cx = max(min(x0 + qx, h - 1 + R), -R) + 2 * R;
+                        const float w = __fmul_rn(qx ? wx1 : wx0, qy ? wy1 : wy0);
+                        load8(gs + (((int64_t)n * hps + cy) * hps + cx) * ldgs + c8, u);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) hv[j] = fmaf(w, u[j], hv[j]);
+                    }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) hv[j] = hv[j] > 0.f ? hv[j] : 0.01f * hv[j];
+                store8(sH + pi * HP + c8, hv);
+            }
+            __syncthreads();
+            // (b) logits[64][32] = hidden[64][128] * W2^T: warp = (row tile, half of the 32 logit columns), 8 k-steps
+            {
+                const int mt = warp & 3, nh = warp >> 2, g = lane >> 2, tq = lane & 3;
+                const uint32_t sH_u = (uint32_t)__cvta_generic_to_shared(sH), sW_u = (uint32_t)__cvta_generic_to_shared(sW);
+                const uint32_t a_ad = sH_u + (uint32_t)(((mt * 16 + (lane & 15)) * HP + (lane >> 4) * 8) * 2);
+                const int mi = lane >> 3;
+                const uint32_t b_ad = sW_u + (uint32_t)(((nh * 16 + (mi >> 1) * 8 + (lane & 7)) * HP + (mi & 1) * 8) * 2);
+                float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+                for (int ks = 0; ks < HID / 16; ++ks) {
+                    uint32_t af[4], bf[4];
+                    ldmatrix_x4(af, a_ad + (uint32_t)(ks * 32));
+                    ldmatrix_x4(bf, b_ad + (uint32_t)(ks * 32));
+                    mma_16816<T>(acc[0], af, bf[0], bf[1]);
+                    mma_16816<T>(acc[1], af, bf[2], bf[3]);
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int col = (nh * 2 + j) * 8 + 2 * tq;
+                    *reinterpret_cast<float2 *>(sL + (mt * 16 + g) * 32 + col) = make_float2(acc[j][0], acc[j][1]);
+                    *reinterpret_cast<float2 *>(sL + (mt * 16 + g + 8) * 32 + col) = make_float2(acc[j][2], acc[j][3]);
+                }
+            }
+            __syncthreads();
+            // (c) softmax and the 36 patch coefficients, four threads per pixel (nine coefficients each), scattered into A
+            {
+                const int pi = threadIdx.x >> 2, part = threadIdx.x & 3;
+                float a[KK];
+                float mx = -3.0e38f;
+#pragma unroll
+                for (int t = 0; t < KK; ++t) { a[t] = sL[pi * 32 + t] + s_b2[t]; mx = fmaxf(mx, a[t]); }
+                float den = 0.f;
+#pragma unroll
+                for (int t = 0; t < KK; ++t) { a[t] = expf(a[t] - mx); den += a[t]; }
+                const float inv = 1.0f / (den * (float)KK);
+                const float wx1 = s_fr[2 * pi], wy1 = s_fr[2 * pi + 1], wx0 = __fsub_rn(1.f, wx1), wy0 = __fsub_rn(1.f, wy1);
+                T *arow = sA + pi * ATC_AP + (s_xy[2 * pi + 1] - R - by0) * WW + (s_xy[2 * pi] - R - bx0);
+#pragma unroll
+                for (int uy = 0; uy < PK; ++uy)
+#pragma unroll
+                    for (int ux = 0; ux < PK; ++ux) {
+                        if ((uy * PK + ux) / 9 != part) continue;
+                        float c = 0.f;
+                        if (uy < K && ux < K) c = fmaf(a[uy * K + ux], wy0 * wx0, c);
+                        if (uy < K && ux > 0) c = fmaf(a[uy * K + ux - 1], wy0 * wx1, c);
+                        if (uy > 0 && ux < K) c = fmaf(a[(uy - 1) * K + ux], wy1 * wx0, c);
+                        if (uy > 0 && ux > 0) c = fmaf(a[(uy - 1) * K + ux - 1], wy1 * wx1, c);
+                        DT<T>::st(arow + uy * WW + ux, c * inv);
+                    }
+            }
+        } else
+        // ---- phase 1 (gather path, or staged path with HOIG_ATTN_PHASE1_TC=0): per pixel (8 lanes each): hidden, logits, softmax, coefficients
 #pragma unroll 1
         for (int pass = 0; pass < ((debug & 2) ? 0 : 2); ++pass) {
             const int pi = pass * 32 + warp * 4 + grp;          // pixel of the tile
@@ -1406,6 +1504,7 @@ extern "C" int hoig_replicate_pad(const void *src, int64_t lds, void *dst, int64
 }
 
 static int g_attn_debug = 0;
+static int g_attn_phase1_tc = 1;      // HOIG_ATTN_PHASE1_TC: logits of the staged path as a warp-level GEMM (1) or per-pixel FMAs (0)
 static int g_attn_tc = 1;      // HOIG_ATTN_TC / hoig_set_attn_tc_mode: 1 = tensor-core attn_combine with staged source windows, 0 = per-pixel gathers
 extern "C" void hoig_set_attn_tc_mode(int on) { g_attn_tc = on ? 1 : 0; }
 
@@ -1430,6 +1529,8 @@ extern "C" int hoig_attn_combine(const void *gt, int64_t ldgt, const void *gs, i
         if (e) g_attn_tc = atoi(e) ? 1 : 0;
         const char *dbg = getenv("HOIG_ATTN_DEBUG");       // timing knock-outs (garbage results): 1 = no patch-sum GEMM, 2 = no per-pixel phase
         if (dbg) g_attn_debug = atoi(dbg);
+        const char *p1 = getenv("HOIG_ATTN_PHASE1_TC");
+        if (p1) g_attn_phase1_tc = atoi(p1) ? 1 : 0;
     }
     if (g_attn_tc && (dtype == HOIG_BF16 || dtype == HOIG_F16) && k == 5 && h % ATC_TILE == 0 && C % 64 == 0) {
         // tensor-core formulation with shared-memory staging of the source window (attn_combine_tc_kernel)
@@ -1440,14 +1541,14 @@ extern "C" int hoig_attn_combine(const void *gt, int64_t ldgt, const void *gs, i
                 cudaFuncSetAttribute(attn_combine_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM) != cudaSuccess)
                 return check_launch("attn_combine_tc smem attribute");
             attn_combine_tc_kernel<__half><<<tgrid, 256, ATC_SMEM, as_stream(stream)>>>(
-                (const __half *)gt, ldgt, (const __half *)gs, ldgs, b1, w2, b2, (const __half *)src, lds, flow, (const __half *)tgt, ldt, (__half *)dst, ldd, N, h, C, g_attn_debug);
+                (const __half *)gt, ldgt, (const __half *)gs, ldgs, b1, w2, b2, (const __half *)src, lds, flow, (const __half *)tgt, ldt, (__half *)dst, ldd, N, h, C, g_attn_debug, g_attn_phase1_tc);
         } else {
             if (first_use_on_device(SLOT_ATTN_TC_BF16) &&
                 cudaFuncSetAttribute(attn_combine_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM) != cudaSuccess)
                 return check_launch("attn_combine_tc smem attribute");
             attn_combine_tc_kernel<__nv_bfloat16><<<tgrid, 256, ATC_SMEM, as_stream(stream)>>>(
                 (const __nv_bfloat16 *)gt, ldgt, (const __nv_bfloat16 *)gs, ldgs, b1, w2, b2, (const __nv_bfloat16 *)src, lds, flow, (const __nv_bfloat16 *)tgt, ldt,
-                (__nv_bfloat16 *)dst, ldd, N, h, C, g_attn_debug);
+                (__nv_bfloat16 *)dst, ldd, N, h, C, g_attn_debug, g_attn_phase1_tc);
         }
         return check_launch("attn_combine_tc_kernel");
     }

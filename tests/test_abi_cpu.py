@@ -37,14 +37,16 @@ def test_sass_contains_blackwell_instructions():
         pytest.skip("cuobjdump unavailable")
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "LDGSTS"):
         assert mnemonic in out, mnemonic
-    # No kernel uses the legacy warp-level MMA as its GEMM path: HMMA may only appear inside the tcgen05 conv kernel, where
-    # it reduces the epilogue's per-plane statistics (umma_common.cuh colsum16), a handful of instructions per kernel.
+    # The convolutions run on tcgen05 only.  Legacy warp-level HMMA may appear in exactly two places: inside the tcgen05 conv kernel, where
+    # it reduces the epilogue's per-plane statistics (umma_common.cuh colsum16), and in attn_combine_tc_kernel, whose per-tile window GEMMs
+    # (64 x <=256 x 64 per slab, A built on the fly in shared memory) are warp-level by design.
     for fn in out.split("Function :")[1:]:
         body = fn.replace("UTCHMMA", "")
         n_legacy = body.count("HMMA.")
         if n_legacy:
-            assert "UTCHMMA" in fn and "conv_umma_kernel" in fn.split("\n", 1)[0], fn.split("\n", 1)[0]
-            assert n_legacy <= 64, (fn.split("\n", 1)[0], n_legacy)
+            head = fn.split("\n", 1)[0]
+            assert ("UTCHMMA" in fn and "conv_umma_kernel" in head) or "attn_combine_tc_kernel" in head, head
+            assert n_legacy <= 64, (head, n_legacy)
 
 
 def test_argument_validation_without_gpu(lib):

@@ -291,6 +291,8 @@ def test_epilogue_statistics_on_large_mean_planes(dtype, hw, cout, bias_value):
           f"(mean/std ~ {float((mean_ref / var_ref.sqrt()).mean()):.1f})")
     wide = cout > 128
     if bias_value <= 2.0 or wide:
-        assert rel <= (1e-2 if (dtype == torch.bfloat16 and not wide) else 3e-3)
+        # (the wide path takes statistics of the fp32 values BEFORE the 16-bit store: against the variance of the stored values that
+        #  differs by the storage rounding noise, 0.036^2 for bf16 values near 20)
+        assert rel <= (1e-2 if dtype == torch.bfloat16 else 3e-3)
     else:
         assert rel <= (0.3 if dtype == torch.bfloat16 else 0.15)        # documented limitation of the bf16-squared persistent path
