@@ -87,7 +87,7 @@ def conv_traffic():
 
 COLS = [("gpu__time_duration.sum", "dur"), ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor%"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"), ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2%"),
-        ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "DRAM%"), ("dram__bytes_read.sum", "DRAMrd"), ("dram__bytes_write.sum", "DRAMwr"),
+        ("dram__bytes.sum.per_second", "DRAM/s"), ("dram__bytes_read.sum", "DRAMrd"), ("dram__bytes_write.sum", "DRAMwr"),
         ("launch__grid_size", "grid"), ("launch__cluster_dim_x", "cl"), ("launch__registers_per_thread", "regs"),
         ("launch__shared_mem_per_block_dynamic", "dsmem"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ%"),
         ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "st_lsb"),
@@ -112,7 +112,7 @@ def ncu_table(raw_csvs, out_name, title, top=None):
     names, units, data = rows[hdr_i], rows[hdr_i + 1], rows[hdr_i + 2:]
     idx = {}
     for key, label in COLS:
-        hits = [i for i, n in enumerate(names) if n.endswith(key)]
+        hits = [i for i, n in enumerate(names) if n == key] or [i for i, n in enumerate(names) if n.endswith(key)]
         if hits:
             idx[label] = hits[0]
     i_kn = names.index("Kernel Name")
@@ -127,7 +127,7 @@ def ncu_table(raw_csvs, out_name, title, top=None):
     with open(os.path.join(P, out_name), "w") as f:
         f.write(f"# {title}\n# ncu --set full --clock-control none (cold cache, serialised replays): one row per kernel instance, sorted by duration"
                 + (f" (top {top} of {len(data)})" if top else "") + "\n"
-                "# tensor% = sm__pipe_tensor_cycles_active (of active cycles); issue% = issue slots busy; st_* = average warps stalled per issue-active cycle\n")
+                "# tensor% = sm__pipe_tensor_cycles_active (of active cycles); issue% = issue slots busy; L2% = lts__throughput; DRAM/s = dram__bytes per second (unit in the cell);\n# st_* = average warps stalled per issue-active cycle\n")
         f.write(f"{'kernel':46s} {'ms':>8s} " + " ".join(f"{lab:>9s}" for lab in list(idx)[1:]) + "\n")
         tot = 0.0
         for i in order:
@@ -139,7 +139,7 @@ def ncu_table(raw_csvs, out_name, title, top=None):
                 u = units[idx[lab]]
                 try:
                     x = float(v.replace(",", ""))
-                    vals.append(f"{x:7.1f}{u[:2] if 'byte' in u else '':2s}"[:9].rjust(9))
+                    vals.append(f"{x:7.1f}{u[:2] if 'byte' in u else '':2s}"[:9].rjust(9) if "/s" not in u else f"{x:5.2f}{u[:2]}/s".rjust(9))
                 except ValueError:
                     vals.append(v[:9].rjust(9))
             f.write(f"{kn:46s} {dur_ms(r):8.4f} " + " ".join(vals) + "\n")
