@@ -1,5 +1,5 @@
-"""Config 4: condition rasterizer alone, N meshes (F = 13776) -> 256x256 fim/wim.  CUDA-event timing, HBM roofline,
-and the reference's own kernel (oracle/_ref, same GPU) timed on a subset for context."""
+"""Config 4: condition rasterizer alone, N meshes (F = 13776) -> 256x256 fim/wim.  CUDA-event timing and HBM roofline.
+(bench.py's `rasterizer` extra also checks it bit-for-bit against, and times, the reference's own kernel.)"""
 import json
 import os
 import sys
@@ -41,19 +41,3 @@ peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if 
 gbs = N * bytes_per_mesh / ms / 1e6
 print(json.dumps({"meshes": N, "faces": F, "ms": ms, "meshes_per_s": N / ms * 1e3, "algorithmic_bytes_per_mesh": bytes_per_mesh,
                   "achieved_GBs": gbs, "hbm_peak_GBs": peak, "frac": gbs / peak, "covered_frac": (fim >= 0).float().mean().item()}))
-
-try:
-    from oracle.ref_kernels import load_ref as _load_ref, ref_rasterize as _ref_rasterize
-    mod = _load_ref("ref_rasterize_cuda")
-    if mod is not None:
-        sub = faces[:64].contiguous()
-        _ref_rasterize(mod, sub, 256)
-        e0.record()
-        _ref_rasterize(mod, sub, 256)
-        e1.record()
-        torch.cuda.synchronize()
-        ms_ref = e0.elapsed_time(e1)
-        print(json.dumps({"reference_kernel_meshes": 64, "ms": ms_ref, "meshes_per_s": 64 / ms_ref * 1e3,
-                          "speedup_vs_reference_kernel": (N / ms) / (64 / ms_ref)}))
-except Exception as ex:  # noqa: BLE001
-    print("reference kernel timing skipped:", ex)
