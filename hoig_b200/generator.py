@@ -217,6 +217,11 @@ class GeneratorB200(nn.Module):
         # bg_model / obj_model run twice with the same weights (source and target side): one pass over a batch of 2B instead
         self.batch_shared_passes = os.environ.get("HOIG_BATCH2", "1") != "0"
         self.auto_graph_after, self.auto_graph_max = 2, 2   # eager calls before capture; captured shapes kept
+        # captured graphs only: bg_model, obj_model and the two halves of the src/tsf chain (between the feature warps that
+        # couple them) are independent, so they are captured as parallel branches of the graph (fork/join on events):
+        # -15% at batch 1, where one kernel leaves most SMs idle; -0.7% at batch 64 (kernel tails overlap).  "0" = one chain
+        self.branch_streams = os.environ.get("HOIG_BRANCH_STREAMS", "1")
+        self._side_streams: dict = {}
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.refresh_weights())
         self.reset_parameters()
 
@@ -700,6 +705,63 @@ class GeneratorB200(nn.Module):
                       src_armask=None, tsf_armask=None):
         self._dev = bg_inputs.device
         self._arena = _StatsArena(self._dev)
+        self._fork = self._branch_fork()
+        try:
+            return self._forward_body(bg_inputs, src_obj_inputs, tsf_obj_inputs, src_hand_inputs, tsf_hand_inputs, T, src_obj_conds,
+                                      src_hand_conds, tsf_obj_conds, tsf_hand_conds, src_armask, tsf_armask)
+        finally:
+            self._join()
+            self._arena = self._fork = None
+
+    # ---- graph branches: fork/join of side streams inside a capture (see ``branch_streams``)
+    N_BRANCH = 3            # 0: bg_model, 1: obj_model, 2: the tsf_model half of the src/tsf chain
+
+    def _branch_fork(self):
+        if self.branch_streams == "0" or self._dev.type != "cuda" or not torch.cuda.is_current_stream_capturing():
+            return None
+        dev = self._dev.index
+        if dev not in self._side_streams:
+            self._side_streams[dev] = [torch.cuda.Stream(device=self._dev) for _ in range(self.N_BRANCH)]
+        return {"streams": self._side_streams[dev], "joins": [[] for _ in range(self.N_BRANCH)],
+                "arenas": [_StatsArena(self._dev) for _ in range(self.N_BRANCH)], "keep": [[] for _ in range(self.N_BRANCH)]}
+
+    def _run_branch(self, idx, fn, keep=()):
+        """Runs ``fn`` on side stream ``idx``, ordered after everything issued so far on the main stream; ``_join(idx)``
+        makes the main stream wait for it.  ``keep``: tensors allocated on the main stream that ``fn`` reads -- they are
+        held until the join so that the allocator cannot hand their memory to later main-stream work while the branch is
+        still reading.  Each branch carves its own statistics arena (an arena zero-fills on the stream it is taken on).
+        Without a fork (eager, or ``branch_streams='0'``) it is a plain call."""
+        if self._fork is None:
+            return fn()
+        f = self._fork
+        main, side = torch.cuda.current_stream(self._dev), f["streams"][idx]
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        arena, self._arena = self._arena, f["arenas"][idx]
+        try:
+            with torch.cuda.stream(side):
+                r = fn()
+                done = torch.cuda.Event()
+                done.record(side)
+        finally:
+            self._arena = arena
+        f["joins"][idx].append(done)
+        f["keep"][idx].extend(keep)
+        return r
+
+    def _join(self, idx=None):
+        if self._fork is None:
+            return
+        main = torch.cuda.current_stream(self._dev)
+        for i in (range(self.N_BRANCH) if idx is None else (idx,)):
+            for ev in self._fork["joins"][i]:
+                main.wait_event(ev)
+            self._fork["joins"][i].clear()
+            self._fork["keep"][i].clear()
+
+    def _forward_body(self, bg_inputs, src_obj_inputs, tsf_obj_inputs, src_hand_inputs, tsf_hand_inputs, T,
+                      src_obj_conds, src_hand_conds, tsf_obj_conds, tsf_hand_conds, src_armask, tsf_armask):
         # generator.py:351-365 background input assembly
         src_bg = [bg_inputs, src_obj_inputs[:, 3:] if (src_obj_conds is None or src_hand_conds is None) else src_hand_conds]
         tsf_bg = [bg_inputs, tsf_hand_inputs[:, 3:] if (tsf_obj_conds is None or tsf_hand_conds is None) else tsf_hand_conds]
@@ -707,17 +769,17 @@ class GeneratorB200(nn.Module):
             src_bg.append(src_armask)
         if tsf_armask is not None:
             tsf_bg.append(tsf_armask)
-        if len(src_bg) == len(tsf_bg) and self.batch_shared_passes:
-            # the two bg_model passes share their weights: one pass over a batch of 2B (InstanceNorm statistics are per sample)
-            both = self._bg([torch.cat([a, b], 0) for a, b in zip(src_bg, tsf_bg)])
-            nb = bg_inputs.shape[0]
-            src_img_bg, tsf_img_bg = both[:nb], both[nb:]
-        else:
-            src_img_bg = self._bg(src_bg)
-            tsf_img_bg = self._bg(tsf_bg)
+        def bg_branch():
+            if len(src_bg) == len(tsf_bg) and self.batch_shared_passes:
+                # the two bg_model passes share their weights: one pass over a batch of 2B (InstanceNorm statistics are per sample)
+                both = self._bg([torch.cat([a, b], 0) for a, b in zip(src_bg, tsf_bg)])
+                nb = bg_inputs.shape[0]
+                return both[:nb], both[nb:]
+            return self._bg(src_bg), self._bg(tsf_bg)
+
+        src_img_bg, tsf_img_bg = self._run_branch(0, bg_branch)
         outs = self._infer_front(src_obj_inputs, tsf_obj_inputs, src_hand_inputs, tsf_hand_inputs, T.float().contiguous(),
                                  src_obj_conds, src_hand_conds, tsf_obj_conds, tsf_hand_conds)
-        self._arena = None
         return (src_img_bg, tsf_img_bg) + outs
 
     def _infer_front(self, src_obj_inputs, tsf_obj_inputs, src_hand_inputs, tsf_hand_inputs, T,
@@ -733,9 +795,26 @@ class GeneratorB200(nn.Module):
         def cat_buf(level):
             return self._new(n, H >> level, W >> level, 2 * c0 * 2 ** level)
 
+        # decoders (:449-461): hand and object decoder outputs share one 2c-wide buffer per side so
+        # attetion_reg_bg's cat[x, y] input is a plain view
+        xy = self._new(2 * n, H, W, 2 * c0)
+        s_xy, t_xy = xy[:n], xy[n:]
+
+        def obj_branch():
+            # obj_model runs on the source and the target object with the same weights: one pass over a batch of 2B
+            if (src_obj_conds is None) == (tsf_obj_conds is None) and self.batch_shared_passes:
+                obj_conds = None if src_obj_conds is None else torch.cat([src_obj_conds, tsf_obj_conds], 0)
+                self._unet_features("obj_model", torch.cat([src_obj_inputs, tsf_obj_inputs], 0), obj_conds, {}, xy[..., c0:])
+            else:
+                self._unet_features("obj_model", src_obj_inputs, src_obj_conds, {}, s_xy[..., c0:])
+                self._unet_features("obj_model", tsf_obj_inputs, tsf_obj_conds, {}, t_xy[..., c0:])
+
+        self._run_branch(1, obj_branch)
+        # the tsf_model half runs as branch 2 between the warps (:407, :427, :446), which need both halves
         s_cats, t_cats = [cat_buf(0)], [cat_buf(0)]
+        tx = self._run_branch(2, lambda: self._stem("tsf_model.encoders.0.0.weight", "tsf_model.encoders.0.1.", [tsf_hand_inputs],
+                                                    out=t_cats[0][..., :c0]))
         sx = self._stem("src_model.encoders.0.0.weight", "src_model.encoders.0.1.", [src_hand_inputs], out=s_cats[0][..., :c0])
-        tx = self._stem("tsf_model.encoders.0.0.weight", "tsf_model.encoders.0.1.", [tsf_hand_inputs], out=t_cats[0][..., :c0])
         c = c0
         for i in range(1, nd + 1):
             c *= 2
@@ -744,31 +823,29 @@ class GeneratorB200(nn.Module):
                 so, to = s_cats[i][..., :c], t_cats[i][..., :c]
             else:
                 so = to = None
+            tx = self._run_branch(2, lambda: self._encoder("tsf_model", i, tx, tsf_hand_conds, seg_t, to), keep=(tx,))
             sx = self._encoder("src_model", i, sx, src_hand_conds, seg_s, so)
-            tx = self._encoder("tsf_model", i, tx, tsf_hand_conds, seg_t, to)
+            self._join(2)
             tx = self._warp(i, sx, tx, T, flows)            # tsf_x = tsf_x + warp   (:407)
         s_st = None
         for i in range(self.repeat_num):
             nxt = i + 1 < self.repeat_num and self._is_spade_res(i + 1)
+            tx, _ = self._run_branch(2, lambda: self._resnet("tsf_model", i, tx, None, tsf_hand_conds, seg_t, want_stats=False), keep=(tx,))
             sx, s_st = self._resnet("src_model", i, sx, s_st, src_hand_conds, seg_s, want_stats=nxt)
-            tx, _ = self._resnet("tsf_model", i, tx, None, tsf_hand_conds, seg_t, want_stats=False)
+            self._join(2)
             tx = self._warp(i + nd + 1, sx, tx, T, flows)    # (:427, :446)
-        # decoders (:449-461): hand and object decoder outputs share one 2c-wide buffer per side so
-        # attetion_reg_bg's cat[x, y] input is a plain view
-        xy = self._new(2 * n, H, W, 2 * c0)
-        s_xy, t_xy = xy[:n], xy[n:]
-        # obj_model runs on the source and the target object with the same weights: one pass over a batch of 2B
-        obj_conds = None if src_obj_conds is None or tsf_obj_conds is None else torch.cat([src_obj_conds, tsf_obj_conds], 0)
-        if (src_obj_conds is None) == (tsf_obj_conds is None) and self.batch_shared_passes:
-            self._unet_features("obj_model", torch.cat([src_obj_inputs, tsf_obj_inputs], 0), obj_conds, {}, xy[..., c0:])
-        else:
-            self._unet_features("obj_model", src_obj_inputs, src_obj_conds, {}, s_xy[..., c0:])
-            self._unet_features("obj_model", tsf_obj_inputs, tsf_obj_conds, {}, t_xy[..., c0:])
-        self._decode("src_model", sx, s_cats, src_hand_conds, seg_s, s_xy[..., :c0])
-        self._decode("tsf_model", tx, t_cats, tsf_hand_conds, seg_t, t_xy[..., :c0])
+        self._join(1)                                        # the heads read obj_model's half of xy
+
+        def tail(net, x, cats, conds, seg, buf):
+            self._decode(net, x, cats, conds, seg, buf[..., :c0])
+            return self._heads(net, buf)
+
         res = {}
-        for tag, net, xy in (("src", "src_model", s_xy), ("tsf", "tsf_model", t_xy)):
-            res[tag + "_hand"], res[tag + "_mask_hand"], res[tag + "_mask_bg"], res[tag + "_obj"] = self._heads(net, xy)
+        t_out = self._run_branch(2, lambda: tail("tsf_model", tx, t_cats, tsf_hand_conds, seg_t, t_xy), keep=(tx,))
+        s_out = tail("src_model", sx, s_cats, src_hand_conds, seg_s, s_xy)
+        self._join(2)
+        for tag, out in (("src", s_out), ("tsf", t_out)):
+            res[tag + "_hand"], res[tag + "_mask_hand"], res[tag + "_mask_bg"], res[tag + "_obj"] = out
         return (res["src_obj"], res["src_hand"], res["src_mask_bg"], res["src_mask_hand"],
                 res["tsf_obj"], res["tsf_hand"], res["tsf_mask_bg"], res["tsf_mask_hand"])
 

@@ -200,6 +200,35 @@ def test_dexycb_dims_vs_oracle(dtype):
         assert rel <= REL_L2_GATE
 
 
+@pytest.mark.parametrize("batch,size", [(1, 256), (3, 128)])
+def test_graph_branch_streams_match_one_chain(batch, size):
+    """Captured graphs run bg_model, obj_model and the src/tsf chain as three parallel branches (fork/join on events);
+    the result must equal the single-chain graph and the eager schedule on every replay."""
+    variant = "generator_spade_attn"
+    sd = gr.init_state_dict(seed=0, jitter=0.05, **SMALL, **TABLE[variant])
+    g = create(variant, **SMALL)
+    g.load_state_dict(sd)
+    g = g.cuda().eval()
+    g.auto_graph = False
+    inputs = [{k: v.cuda() for k, v in synth.generator_inputs(batch, seed=s, size=size).items()} for s in (1, 2, 3)]
+    eager = [[o.clone() for o in g(**inp)] for inp in inputs]
+    runs = {}
+    for mode in ("0", "1"):
+        g.branch_streams = mode
+        runs[mode] = g.graphed(inputs[0], with_composite=True)
+    assert len(g._side_streams) == 1
+    for rep in range(3):
+        for inp, want in zip(inputs, eager):
+            got = {}
+            for mode, run in runs.items():
+                outs, img = run(**inp)
+                got[mode] = [o.clone() for o in outs] + [img.clone()]
+            for x, y, z in zip(got["0"], got["1"], want + [None]):
+                assert (x - y).abs().max().item() <= 2e-3
+                if z is not None:
+                    assert (y - z).abs().max().item() <= 2e-3
+
+
 def test_auto_graph_matches_eager_and_tracks_weight_updates():
     """Repeated same-shape inference calls are served by a captured CUDA graph from the third call on; results must equal the
     eager schedule, survive in-place weight updates (parameter version counters) and ``load_state_dict``."""
