@@ -8,6 +8,8 @@ timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench.log 2>&
 timeout 900 python bench.py --steps 10 --warmup 3 --dtype bf16 --no-extras --no-cpu-baseline > gpurun_out/r02_bench_bf16.log 2>&1; echo "bench bf16 rc=$?"
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_ref.log 2>&1; echo "bench ref rc=$?"
 timeout 900 python bench.py --mode train --steps 3 --warmup 1 > gpurun_out/r02_bench_train.log 2>&1; echo "bench train rc=$?"
+timeout 300 python bench.py --mode train --batch 16 --steps 2 --warmup 1 > gpurun_out/r02_bench_train_b16.log 2>&1; echo "bench train b16 rc=$?"
+timeout 200 python scripts/branch_ab.py 1 4 64 > gpurun_out/r02_branch_ab.log 2>&1
 timeout 600 python scripts/profile_convs.py 64 f16 > gpurun_out/r02_prof_convs_b64.log 2>&1
 timeout 600 python scripts/bench_conditions.py 64 > gpurun_out/r02_conditions.log 2>&1
 tail -n 1 gpurun_out/r02_bench.log | cut -c1-600; tail -n 1 gpurun_out/r02_bench_ref.log | cut -c1-300; tail -n 1 gpurun_out/r02_bench_train.log | cut -c1-300
