@@ -26,7 +26,9 @@ int check_launch(const char *what);  // cudaGetLastError -> status
 // process is keyed by the current device.
 constexpr int kMaxDevices = 64;
 enum DeviceSlot { SLOT_CONV_UMMA_BF16_1, SLOT_CONV_UMMA_BF16_1P, SLOT_CONV_UMMA_BF16_2, SLOT_CONV_UMMA_BF16_2P, SLOT_CONV_UMMA_F16_1,
-                  SLOT_CONV_UMMA_F16_1P, SLOT_CONV_UMMA_F16_2, SLOT_CONV_UMMA_F16_2P, SLOT_CONV_HALO, SLOT_RASTERIZE, SLOT_ATTN_TC_F16, SLOT_ATTN_TC_BF16,
+                  SLOT_CONV_UMMA_F16_1P, SLOT_CONV_UMMA_F16_2, SLOT_CONV_UMMA_F16_2P,
+                  SLOT_CONV_UMMA_FAST_FIRST, SLOT_CONV_UMMA_FAST_LAST = SLOT_CONV_UMMA_FAST_FIRST + 7,   // the same eight with the streamlined epilogue
+                  SLOT_CONV_HALO, SLOT_RASTERIZE, SLOT_ATTN_TC_F16, SLOT_ATTN_TC_BF16,
                   SLOT_COUNT };
 int device_sm_count();               // SM count of the CURRENT device
 bool first_use_on_device(int slot);  // true exactly once per (current device, slot): set the kernel's function attributes then

@@ -58,6 +58,7 @@ struct UmmaParams {
     int cpt_shift;   // log2(Cin / 8) when Cin < 64 (chunk -> tap by shift), -1: generic division
     int tpi_shift;       // log2(tiles_per_image) when it is a power of two, else -1
     int contig;          // 1: contiguous tile range per CTA, 0: tiles strided by the grid size
+    int fast_epi;        // 2: streamlined epilogue over 32-column chunks (plain bias / ReLU / statistics convs, see launch_one)
     int halo;            // 1: regular kh x kw stride-1 conv whose tiles are 128 consecutive pixels of ONE image row: a stage holds one
                          //    activation box of 128 + kw - 1 pixels per (kernel row, 64 channels) and the kw taps read it through
                          //    descriptors shifted by one pixel row (128 B) each -- L2->SM activation traffic / kw (see conv_halo.cu)
@@ -88,7 +89,7 @@ struct UmmaParams {
 // pixels of A and HALF of the weight tile (BN/2 rows), the leader (cluster rank 0) issues 256 x BN x 16 MMAs that read both
 // CTAs' shared memory, and each CTA drains its own 128 TMEM lanes.  Weight traffic (L2->SM and smem writes) per CTA halves,
 // which is what bounds the wide-N convs: TMA writes and UMMA operand reads share the 128 B/clk shared-memory port.
-template <typename T, int NCTA, bool PERSIST>
+template <typename T, int NCTA, bool PERSIST, bool FAST>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
@@ -625,7 +626,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
         auto dump_stats = [&]() {      // registers -> this warp's private s_stats columns, then clear
 #pragma unroll
             for (int sl = 0; sl < NSLOT; ++sl) {
-                const int ch = half + sl * ngrp;
+                const int ch = (FAST && P.fast_epi == 2) ? 2 * half + sl : half + sl * ngrp;      // the 16-column chunk slot sl accumulated
                 float s_lo = st_sum[sl][0] + st_sum[sl][1], s_hi = st_sum[sl][2] + st_sum[sl][3];
                 float q_lo = st_sq[sl][0] + st_sq[sl][1], q_hi = st_sq[sl][2] + st_sq[sl][3];
                 s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1); s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1);
@@ -859,6 +860,122 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                         }
                     }
             };
+            if constexpr (FAST) {
+                // Streamlined epilogue (launch_one: no residual / SPADE / per-channel activations, 16-byte aligned rows, whole 16- or
+                // 32-column chunks).  Its own kernel instantiation, so neither the general epilogue's code nor its registers are carried.
+                // P.fast_epi = 2: 32-column chunks -- the lane writes 64 contiguous bytes (two full sectors, no lane-pair exchange) and the
+                // per-chunk address / bounds code runs once per 32 columns; 1: 16-column chunks with the lane-pair store of the general path.
+                T *const drow0 = dst + m * p.ldd;
+                const bool relu = p.act == HOIG_ACT_RELU;
+                auto fast_chunk = [&](auto wtag, int ch, auto slot_tag) {
+                    constexpr int W = decltype(wtag)::value;
+                    uint32_t r[W];
+                    if constexpr (W == 32) { tmem_ld32(t_row + (uint32_t)(ch * W), r); tmem_ld_wait32(r); }
+                    else { tmem_ld16(t_row + (uint32_t)(ch * W), r); tmem_ld_wait(r); }
+                    const int c0 = ch * W, n0 = nt * BN + c0;
+                    if (n0 >= p.Cout) return;         // warp-uniform: padded output channels
+                    T *drow = drow0 + n0;
+                    if (pc) {       // transposed conv: parity block ph of pc channels, blocks ordered (0,0),(0,1),(1,1),(1,0)
+                        const int ph = n0 / pc;
+                        drow = dst + (m + (int64_t)(ph >> 1) * p.OWf + ((ph & 1) ^ (ph >> 1))) * p.ldd + (n0 - ph * pc);
+                    }
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < W; j += 4) {
+                            const float4 bv = *reinterpret_cast<const float4 *>(&s_bias[c0 + j]);
+                            r[j] = __float_as_uint(__uint_as_float(r[j]) + bv.x);
+                            r[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + bv.y);
+                            r[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + bv.z);
+                            r[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + bv.w);
+                        }
+                    }
+                    if (relu) {
+#pragma unroll
+                        for (int j = 0; j < W; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]), 0.f));
+                    }
+#pragma unroll
+                    for (int hh = 0; hh < W / 16; ++hh) {       // 16-column pieces: pack, store, statistics
+                        constexpr int slot0 = decltype(slot_tag)::value;
+                        const int slot = W == 32 ? hh : slot0;   // PERSIST: a 32-column chunk is the warp's only one (slots 0, 1)
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) pk[j] = pack2<T>(__uint_as_float(r[hh * 16 + 2 * j]), __uint_as_float(r[hh * 16 + 2 * j + 1]));
+                        if (P.debug & 8) {
+                        } else if (W == 32 || !all_valid) {
+                            if (valid) {
+                                *reinterpret_cast<uint4 *>(drow + hh * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                                *reinterpret_cast<uint4 *>(drow + hh * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                            }
+                        } else {
+                            // lane pairs swap one 16-byte piece: each store instruction writes 16 full 32-byte sectors (see the general path)
+                            const bool odd = lane & 1;
+                            uint32_t keep[4], got[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint32_t send = odd ? pk[j] : pk[4 + j];
+                                keep[j] = odd ? pk[4 + j] : pk[j];
+                                got[j] = __shfl_xor_sync(0xffffffffu, send, 1);
+                            }
+                            T *own = drow + (odd ? 8 : 0);
+                            const uint64_t oth_bits = __shfl_xor_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(drow), 1);
+                            T *oth = reinterpret_cast<T *>((uintptr_t)oth_bits) + (odd ? 8 : 0);
+                            *reinterpret_cast<uint4 *>(odd ? oth : own) = odd ? make_uint4(got[0], got[1], got[2], got[3]) : make_uint4(keep[0], keep[1], keep[2], keep[3]);
+                            *reinterpret_cast<uint4 *>(odd ? own : oth) = odd ? make_uint4(keep[0], keep[1], keep[2], keep[3]) : make_uint4(got[0], got[1], got[2], got[3]);
+                        }
+                        if (p.stats && !(P.debug & 4)) {
+                            const int cc = c0 + hh * 16;
+                            if (P.mma_stats) {
+                                constexpr bool kF16 = std::is_same<T, __half>::value;
+                                uint32_t sq[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    float a = __uint_as_float(r[hh * 16 + 2 * j]), b = __uint_as_float(r[hh * 16 + 2 * j + 1]);
+                                    if (!all_valid && !valid) { pk[j] = 0u; a = 0.f; b = 0.f; }
+                                    sq[j] = pack2<__nv_bfloat16>(a * a, b * b);
+                                }
+                                if (persist) {
+                                    colsum16_acc<kF16>(pk, e_sel, st_sum[slot < NSLOT ? slot : 0]);
+                                    colsum16_acc<false>(sq, e_sel_bf, st_sq[slot < NSLOT ? slot : 0]);
+                                } else {
+                                    float s_lo, s_hi, q_lo, q_hi;
+                                    colsum16<kF16>(pk, e_sel, s_lo, s_hi);
+                                    colsum16<false>(sq, e_sel_bf, q_lo, q_hi);
+                                    if ((lane & 3) == 0) {
+                                        const int col = cc + (lane >> 2);
+                                        s_stats[quad][0][col] += s_lo; s_stats[quad][0][col + 8] += s_hi;
+                                        s_stats[quad][1][col] += q_lo; s_stats[quad][1][col + 8] += q_hi;
+                                    }
+                                }
+                            } else {
+                                float v[16], q[16];
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    v[j] = (all_valid || valid) ? __uint_as_float(r[hh * 16 + j]) : 0.f;
+                                    q[j] = v[j] * v[j];
+                                }
+                                const float cs = transpose_reduce16(v, lane);
+                                const float cq = transpose_reduce16(q, lane);
+                                if ((lane & 1) == 0) {
+                                    const int col = cc + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                                    s_stats[quad][0][col] += cs;
+                                    s_stats[quad][1][col] += cq;
+                                }
+                            }
+                        }
+                    }
+                };
+                if (P.fast_epi == 2) {
+                    for (int ch = half; ch < BN / 32; ch += ngrp) fast_chunk(std::integral_constant<int, 32>(), ch, std::integral_constant<int, 0>());
+                } else {
+                    for (int ch = half; ch < n_chunks; ch += 2 * ngrp) {
+                        fast_chunk(std::integral_constant<int, 16>(), ch, std::integral_constant<int, 0>());
+                        if (ch + ngrp < n_chunks) fast_chunk(std::integral_constant<int, 16>(), ch + ngrp, std::integral_constant<int, 1>());
+                    }
+                }
+                tc_fence_before();
+                if (NCTA == 2) mbar_arrive_cluster_relaxed(tempty0 + 8u * acc);
+                else mbar_arrive_relaxed(tempty0 + 8u * acc);
+            } else {
             if (P.debug & 1) {
                 for (int ch = half; ch < n_chunks; ch += ngrp) { tmem_ld16(t_row + (uint32_t)(ch * 16), ra); tmem_ld_wait(ra); }
                 if (ra[0] == 0x7fc12345u && valid) dst[m * p.ldd] = T(0);
@@ -899,6 +1016,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
             tc_fence_before();
             if (NCTA == 2) mbar_arrive_cluster(tempty0 + 8u * acc);
             else mbar_arrive(tempty0 + 8u * acc);
+            }   // !FAST
         }
         if (p.stats && cur_img >= 0) {   // the last plane this CTA touched
             if (persist) dump_stats();
@@ -920,6 +1038,7 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
 int g_umma_debug = 0;
 
 int g_contig_mode = 1;      // HOIG_UMMA_CONTIG
+int g_fast_epi = 1;         // HOIG_UMMA_FAST_EPI: streamlined 32-column epilogue for plain convs
 int g_mma_stats = 1;        // HOIG_UMMA_MMA_STATS
 int g_halo_mode = 1;        // HOIG_UMMA_HALO: row-halo activation reuse for full-row tiles
 int g_small_split_mode = 1; // HOIG_UMMA_SMALL_SPLIT: narrower n-tiles when a launch has fewer work units than half the SMs (small batches)
@@ -933,12 +1052,13 @@ int g_bres_mode = 1;        // HOIG_UMMA_BRES: resident weights for small weight
 int g_dual_mode = 1;        // 1: narrow-N TMA convs run two MMA issue pipelines per CTA (HOIG_UMMA_DUAL=0 disables)
 int g_pair_mode = 1;        // 0: one CTA per tile; 1: CTA pairs (cta_group::2) where they pay off; 2: pairs wherever legal (tests)
 
-template <typename T, int NCTA, bool PERSIST>
+template <typename T, int NCTA, bool PERSIST, bool FAST>
 int launch_kernel(const UmmaParams &P, const CUtensorMap &map_w, const CUtensorMap *map_a, int grid, size_t smem, cudaStream_t stream)
 {
-    constexpr int slot = (std::is_same<T, __half>::value ? SLOT_CONV_UMMA_F16_1 : SLOT_CONV_UMMA_BF16_1) + 2 * (NCTA - 1) + (PERSIST ? 1 : 0);
+    constexpr int slot = (std::is_same<T, __half>::value ? SLOT_CONV_UMMA_F16_1 : SLOT_CONV_UMMA_BF16_1) + 2 * (NCTA - 1) + (PERSIST ? 1 : 0) +
+                         (FAST ? (int)SLOT_CONV_UMMA_FAST_FIRST - (int)SLOT_CONV_UMMA_BF16_1 : 0);
     if (first_use_on_device(slot) &&
-        cudaFuncSetAttribute(conv_umma_kernel<T, NCTA, PERSIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess)
+        cudaFuncSetAttribute(conv_umma_kernel<T, NCTA, PERSIST, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess)
         return check_launch("conv_umma smem attribute");
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -951,7 +1071,7 @@ int launch_kernel(const UmmaParams &P, const CUtensorMap &map_w, const CUtensorM
     attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = NCTA > 1 ? 1 : 0;
-    if (cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, NCTA, PERSIST>, P, map_w, map_a[0], map_a[1], map_a[2], map_a[3]) != cudaSuccess)
+    if (cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, NCTA, PERSIST, FAST>, P, map_w, map_a[0], map_a[1], map_a[2], map_a[3]) != cudaSuccess)
         return check_launch("conv_umma_kernel launch");
     return check_launch("conv_umma_kernel");
 }
@@ -1081,9 +1201,22 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     // convs -- legacy HMMA shares the tensor pipe with the UMMAs that bound those convs, while their issue slots are idle: the shuffle
     // version measured 2 % (512->512) to 18 % (256->128 @128^2) faster there.
     P.mma_stats = g_mma_stats == 2 ? 1 : (g_mma_stats == 1 ? (persist ? 1 : 0) : 0);
+    // Streamlined epilogue (HOIG_UMMA_FAST_EPI; kernels instantiated with FAST): plain TMA-fed convs -- optional bias, no / ReLU activation,
+    // optional statistics -- with whole 16-column chunks.  32-column chunks where every epilogue warp gets at least one (exactly one in
+    // PERSIST kernels).  Measured (batch 64, fp16): stem -10 %, 128->64 @256^2 -6 %, ConvT 128->64 -13 %, mlp_shared GEMMs -18..-27 %;
+    // the gather-mode stride-2 convs were 6 % slower with it and keep the general epilogue.
+    P.fast_epi = 0;
+    if (g_fast_epi && P.tma_a && !p.residual && !p.spade_x && !p.act_table && (p.act == HOIG_ACT_NONE || p.act == HOIG_ACT_RELU) && p.ldd % 8 == 0 &&
+        reinterpret_cast<uintptr_t>(p.dst) % 16 == 0 && p.Cout % 16 == 0 && (p.phase_cout == 0 || p.phase_cout % 16 == 0)) {
+        const bool wide = P.BN % 32 == 0 && P.BN / 32 >= ngrp && p.Cout % 32 == 0 && (p.phase_cout == 0 || p.phase_cout % 32 == 0) &&
+                          (!persist || P.BN / 32 == ngrp);
+        P.fast_epi = wide ? 2 : 1;
+        if (g_fast_epi == 2 && !wide) P.fast_epi = 0;       // HOIG_UMMA_FAST_EPI=2: only the 32-column form (A/B runs)
+    }
     auto go = [&](auto tag, auto nc, auto ps) {
         using T = std::remove_pointer_t<decltype(tag)>;
-        return launch_kernel<T, decltype(nc)::value, decltype(ps)::value>(P, map_w, map_a, grid, smem, stream);
+        return P.fast_epi ? launch_kernel<T, decltype(nc)::value, decltype(ps)::value, true>(P, map_w, map_a, grid, smem, stream)
+                          : launch_kernel<T, decltype(nc)::value, decltype(ps)::value, false>(P, map_w, map_a, grid, smem, stream);
     };
     auto pick_ps = [&](auto tag, auto nc) {
         return persist ? go(tag, nc, std::true_type()) : go(tag, nc, std::false_type());
@@ -1130,6 +1263,8 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
         if (bm) g_bres_mode = atoi(bm);
         const char *cm = getenv("HOIG_UMMA_CONTIG");
         if (cm) g_contig_mode = atoi(cm);
+        const char *fe = getenv("HOIG_UMMA_FAST_EPI");
+        if (fe) g_fast_epi = atoi(fe);
         const char *dm = getenv("HOIG_UMMA_DUAL");
         if (dm) g_dual_mode = atoi(dm);
         const char *pm = getenv("HOIG_UMMA_2CTA");

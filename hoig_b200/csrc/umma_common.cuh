@@ -188,6 +188,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r)
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
+// 32 consecutive columns of this warp's 32 lanes (two x16 loads, one wait: tmem_ld_wait32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r)
+{
+    tmem_ld16(taddr, r);
+    tmem_ld16(taddr + 16u, r + 16);
+}
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t *r)
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
 // wait::ld with the destination registers as read-write operands, so the compiler cannot hoist their uses
 __device__ __forceinline__ void tmem_ld_wait(uint32_t *r)
 {

@@ -494,17 +494,19 @@ class GeneratorB200(nn.Module):
         writes NCHW f32.  ``weights`` is a callable returning the (G, C, 7, 7) fp32 weight."""
         prm, make = weights
         g = len(acts)
+        gz = ceil_to(7 * g, 16)     # Z is padded to whole 16-channel chunks (zero weight rows): the conv then takes the streamlined epilogue
 
         def build():
             wm = make()                                                   # (G, C, 7, 7)
-            wz = wm.permute(3, 0, 1, 2).reshape(7 * g, wm.shape[1], 7, 1)  # row s*G + g  <-  W[g, :, r, s]
+            wz = torch.zeros(gz, wm.shape[1], 7, 1, dtype=wm.dtype, device=wm.device)
+            wz[:7 * g] = wm.permute(3, 0, 1, 2).reshape(7 * g, wm.shape[1], 7, 1)   # row s*G + g  <-  W[g, :, r, s]
             table = torch.tensor(acts, dtype=torch.int32, device=wm.device)
             return pack_conv_weight(wz, self.compute_dtype), table
 
         wp, table = self._cached(key, prm, build)
         n, h, w_, _ = x.shape
-        z = self._new(n, h, w_, ceil_to(7 * g, 8))
-        ops.conv2d(x, wp, z, kh=7, kw=1, stride=1, pad=3, pad_w=0, cout=7 * g)
+        z = self._new(n, h, w_, gz)
+        ops.conv2d(x, wp, z, kh=7, kw=1, stride=1, pad=3, pad_w=0, cout=gz)
         return ops.hfold_nchw(z, g, 7, segments, table)
 
     def _heads(self, net, xy):

@@ -1,5 +1,5 @@
 """Runs ONE conv shape of the generator a few times (for ncu captures / quick timing).
-    python scripts/one_conv.py stem|c128_64|convT128|s2_64|heads [reps]"""
+    python scripts/one_conv.py stem|c128_64|convT128|s2_64|heads|res512|spade|mlp128|mlp896 [reps]"""
 import os
 import sys
 
@@ -49,6 +49,14 @@ elif which == "spade":
     out = torch.empty(B, 32, 32, 512, dtype=dt, device="cuda")
     sx = rnd(B, 32, 32, 512); sst = torch.zeros(B * 512 * 2, dtype=torch.float64, device="cuda"); ops.plane_stats(sx, sst)
     kw = dict(kh=3, kw=3, stride=1, pad=1, cout=1024, spade_x=sx, spade_stats=sst, act=ops.ACT_RELU, bias=torch.zeros(1024, device="cuda")); tr = False; cout = None
+elif which == "mlp128":     # merged mlp_shared GEMM over the unfolded segmentation map, 128x128
+    x = rnd(B, 128, 128, 64); w = torch.randn(128, 64, 1, 1, device="cuda") * 0.05
+    out = torch.empty(B, 128, 128, 128, dtype=dt, device="cuda")
+    kw = dict(kh=1, kw=1, stride=1, pad=0, act=ops.ACT_RELU, bias=torch.zeros(128, device="cuda")); tr = False; cout = None
+elif which == "mlp896":     # the same at 32x32: 7 SPADE layers in one GEMM
+    x = rnd(B, 32, 32, 64); w = torch.randn(896, 64, 1, 1, device="cuda") * 0.05
+    out = torch.empty(B, 32, 32, 896, dtype=dt, device="cuda")
+    kw = dict(kh=1, kw=1, stride=1, pad=0, act=ops.ACT_RELU, bias=torch.zeros(896, device="cuda")); tr = False; cout = None
 else:
     raise SystemExit("unknown shape")
 wp = pack_conv_weight(w, dt, transposed=tr)
