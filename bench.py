@@ -422,18 +422,30 @@ def run_ours(args):
     per_kernel = _lib.recorder.summary()
     _lib.recorder.reset(timing=False)
 
+    # The clocks sampler (nvidia-smi polling every 100 ms) covers the `value` and roofline regions.  It is stopped before the end-to-end
+    # region unless HOIG_BENCH_SAMPLE_E2E=1: each poll takes driver locks that the ~100 launches and the allocations of a stage-R step
+    # queue behind (graph replays do not), which cost one e2e run in three 10-20 % (profiles/r02_e2e_repeatability.txt).
+    sample_e2e = os.environ.get("HOIG_BENCH_SAMPLE_E2E", "0") == "1"
+    clocks = None
+    if rank == 0 and not sample_e2e:
+        clocks = sampler.stop()
+
     # ---- timed region 2: end to end from host buffers (meshes, cameras, source image, arm masks -> composite on the host) ----
     # Every step copies ITS inputs host->device (pinned memory), runs stage R on them and reads its composite back; upload + stage R of
     # step i+1 (side streams) and the download of step i-1 overlap step i's generator kernels (double buffering through the public API).
     main = torch.cuda.current_stream()
     h2d, d2h, cond = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
 
+    prep_t = [0.0, 0.0]
+
     def prepare():
         """Upload one batch (h2d stream) and run stage R on it (cond stream): both overlap the generator of the previous batch."""
+        tp = time.perf_counter()
         with torch.cuda.stream(h2d):
             buf = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
             up = torch.cuda.Event()
             up.record(h2d)
+        prep_t[0] = time.perf_counter() - tp
         with torch.cuda.stream(cond):
             cond.wait_event(up)
             for t in buf.values():
@@ -444,36 +456,49 @@ def run_ours(args):
         return kw, ev
 
     trace = [] if os.environ.get("HOIG_BENCH_E2E_TRACE") else None
+    gc_ms = [0.0, 0.0]
+    if trace is not None:
+        import gc
 
-    def run_e2e(n_steps):
+        def _gc_cb(phase, info):
+            if phase == "start":
+                gc_ms[1] = time.perf_counter()
+            else:
+                gc_ms[0] += 1e3 * (time.perf_counter() - gc_ms[1])
+        gc.callbacks.append(_gc_cb)
+
+    def run_e2e(n_steps, depth=2):
+        """``depth``: bounded run-ahead of the host (what a service does) -- at most ``depth`` generator steps queued.  The warm-up call runs
+        with a larger depth than the timed one, so the caching allocator ends the warm-up holding MORE blocks than the timed steps ever
+        need at once: a cudaMalloc inside the timed region costs 2-160 ms while the GPU is busy (HOIG_BENCH_E2E_TRACE=1 shows them) and used
+        to cost one run in three 10-20 %."""
         nxt = prepare()
         inflight = []
         for i in range(n_steps):
             kw, ev = nxt
-            # bounded run-ahead (what a service does): at most two generator steps queued, so the allocator reaches its steady
-            # state during the warm-up steps instead of growing (cudaMalloc) inside the timed region
-            if len(inflight) >= 2:
+            if len(inflight) >= depth:
                 inflight.pop(0).synchronize()
-            t0 = time.perf_counter()
-            if i + 1 < n_steps:
-                nxt = prepare()
-            t1 = time.perf_counter()
             main.wait_event(ev)
             for t in kw.values():
                 t.record_stream(main)
+            t1 = time.perf_counter()
             img = step(kw)
             done = torch.cuda.Event(enable_timing=trace is not None)
             done.record(main)
             inflight.append(done)
+            t0 = time.perf_counter()
+            if i + 1 < n_steps:
+                nxt = prepare()              # upload + stage R of the next batch: side streams, under this step's generator kernels
+            t2 = time.perf_counter()
             if trace is not None:
-                trace.append((t0, t1, time.perf_counter(), done))
+                trace.append((t0, t2, t0 - t1 + t2, done, prep_t[0], torch.cuda.memory_stats(dev).get("num_device_alloc", 0), gc_ms[0]))
             with torch.cuda.stream(d2h):
                 d2h.wait_event(done)
                 img.record_stream(d2h)
                 out_host.copy_(img, non_blocking=True)
         main.wait_stream(d2h)
 
-    run_e2e(4)
+    run_e2e(6, depth=5)
     barrier()
     _lib.recorder.reset(timing=False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -484,11 +509,13 @@ def run_ours(args):
     ms_e2e = e0.elapsed_time(e1)
     if trace is not None and rank == 0:
         tr = trace[-args.steps:]
-        for i, (t0, t1, t2, done) in enumerate(tr):
-            print(f"[e2e trace] step {i}: host prepare {1e3 * (t1 - t0):7.2f} ms, generator call {1e3 * (t2 - t1):6.2f} ms, "
-                  f"host since first {1e3 * (t0 - tr[0][0]):8.2f} ms, gpu done at {e0.elapsed_time(done):8.2f} ms", file=sys.stderr)
+        for i, (t0, t1, t2, done, up_s, n_malloc, gcms) in enumerate(tr):
+            print(f"[e2e trace] step {i}: host prepare {1e3 * (t1 - t0):7.2f} ms (upload {1e3 * up_s:6.2f}), generator call {1e3 * (t2 - t1):6.2f} ms, "
+                  f"host since first {1e3 * (t0 - tr[0][0]):8.2f} ms, gpu done at {e0.elapsed_time(done):8.2f} ms, cudaMallocs so far {n_malloc}, "
+                  f"gc ms so far {gcms:.1f}", file=sys.stderr)
     stage_r_launches = _lib.recorder.launches          # C-ABI calls made outside the graph in the e2e region (stage R + composite)
-    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0 and sample_e2e:
+        clocks = sampler.stop()
 
     ms, ms_e2e, ms_eager = dist_utils.reduce_max([ms, ms_e2e, ms_eager], "cuda")
     if rank != 0:

@@ -46,6 +46,7 @@ struct HaloSeg {
     void *dst;
     int64_t ldd;
     int tile0;         // first tile of this segment
+    int st256;         // rows are 32-byte aligned: one 256-bit store per 16-column piece (a whole sector per lane)
 };
 struct HaloParams {
     HaloSeg seg[2];
@@ -217,8 +218,12 @@ conv_halo_kernel(const HaloParams P, const __grid_constant__ CUtensorMap map_a0,
 #pragma unroll
                 for (int j = 0; j < 8; ++j) pk[j] = pack2<T>(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
                 if (valid) {
-                    *reinterpret_cast<uint4 *>(drow + ch * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    *reinterpret_cast<uint4 *>(drow + ch * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    if (S.st256) {
+                        st_global_v8(drow + ch * 16, pk);
+                    } else {
+                        *reinterpret_cast<uint4 *>(drow + ch * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4 *>(drow + ch * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
                 }
             };
             tmem_ld16(t_row, ra);
@@ -270,6 +275,7 @@ int conv2d_halo(int dtype, int KH, int KW, int Cout, const hoigHaloConvSeg *segs
         HOIG_REQUIRE(rows + HBM < (1ll << 31), "conv2d_halo: raster too large");
         HaloSeg &S = P.seg[i];
         S.rows = rows; S.pitch = g.Wp; S.C = g.C; S.cblocks = g.C / HBK; S.dst = g.dst; S.ldd = g.ldd; S.tile0 = tiles;
+        S.st256 = (getenv("HOIG_UMMA_ST256") == nullptr || (atoi(getenv("HOIG_UMMA_ST256")) & 4) != 0) && g.ldd % 16 == 0 && ((uintptr_t)g.dst % 32) == 0;
         tiles += ceil_div(rows, HBM);
         {
             const cuuint64_t dims[2] = {(cuuint64_t)g.C, (cuuint64_t)rows};

@@ -211,6 +211,13 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t *r)
                    "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
                  :: "memory");
 }
+// 32 bytes per lane in one instruction (sm_100: STG.256): a lane then writes one whole 32-byte sector, so row-per-lane epilogue stores need no
+// lane-pair exchange to fill their sectors.  ``p`` must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8(void *p, const uint32_t (&v)[8])
+{
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]),
+                 "r"(v[6]), "r"(v[7]) : "memory");
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -272,12 +279,15 @@ EncodeTiledFn encode_fn()
     return fn;
 }
 
+// ``elem_strides`` (optional, one per dimension): traversal strides; a box of boxDim elements then delivers boxDim / stride of them
 int make_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
-             const cuuint32_t *box, const char *what, int dtype)
+             const cuuint32_t *box, const char *what, int dtype, const cuuint32_t *elem_strides = nullptr)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return HOIG_ERR_CUDA; }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (elem_strides)
+        for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
     const CUresult r = fn(map, dtype == HOIG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), dims, strides_bytes, box,
                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

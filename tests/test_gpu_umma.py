@@ -46,11 +46,12 @@ def test_umma_plain_gemm_identity_weight():
     assert torch.equal(out.cpu(), x)
 
 
+@pytest.mark.parametrize("stride", [1, 2])
 @pytest.mark.parametrize("gather_only", [False, True], ids=["tma_a", "gather"])
-def test_umma_3x3_both_operand_paths(gather_only, monkeypatch):
-    """The same stride-1 conv through the TMA-box A path and the cp.async gather A path."""
+def test_umma_3x3_both_operand_paths(gather_only, stride, monkeypatch):
+    """The same conv through the TMA-box A path (stride 2: element-strided tensor map) and the cp.async gather A path."""
     import hoig_b200._lib as L
-    case = ("3x3_s1_c128", 2, 32, 128, 256, 3, 1, "conv", dict(bias=True, stats=True))
+    case = (f"3x3_s{stride}_c128", 2, 32 * stride, 128, 256, 3, stride, "conv", dict(bias=True, stats=True))
     L.lib().hoig_set_umma_gather_only(int(gather_only))
     try:
         out, ref, st, st_ref = _run_conv(case, torch.bfloat16)
@@ -86,7 +87,7 @@ def test_umma_matches_simt_bf16_bitwise_mostly():
     assert (diff <= 2.0 ** -7 * b.float().abs() + 1e-3).all()
 
 
-F16_CASES = [c for c in CONV_CASES if c[0] in ("3x3_s1_c64", "3x3_s1_k4608", "3x3_s2", "7x7_stem_c8", "7x1_stem_c64", "convT_3x3_s2",
+F16_CASES = [c for c in CONV_CASES if c[0] in ("3x3_s1_c64", "3x3_s1_k4608", "3x3_s2", "3x3_s2_w256", "3x3_s2_c256", "7x7_stem_c8", "7x1_stem_c64", "convT_3x3_s2",
                                                 "attn_c64", "1x1_k3200_attn_gemm", "7x7_heads_merged_act_table", "3x3_s1_c128_n512_bias_res")]
 
 
@@ -103,7 +104,7 @@ def test_conv_f16_umma(case):
         assert torch.allclose(st.cpu(), st_ref, rtol=1e-3, atol=0.3)
 
 
-PAIR_CASES = [c for c in CONV_CASES if c[0] in ("3x3_s1_k4608", "3x3_s1_c128", "3x3_s2", "7x1_stem_c64", "convT_3x3_s2", "1x1_k3200_attn_gemm",
+PAIR_CASES = [c for c in CONV_CASES if c[0] in ("3x3_s1_k4608", "3x3_s1_c128", "3x3_s2", "3x3_s2_w256", "3x3_s2_c256", "7x1_stem_c64", "convT_3x3_s2", "1x1_k3200_attn_gemm",
                                                  "3x3_s1_c128_n512_bias_res", "3x3_s1_c64")]
 
 
