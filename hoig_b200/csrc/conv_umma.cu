@@ -402,10 +402,10 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
                                         mbar_arrive(bar);
                                     } else if (NCTA == 2) {
                                         if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[0]) + 8u * st, 2u * (uint32_t)A_STAGE_BYTES);
-                                        tma_load_4d_2sm(a_dst, maps[p.tap_map[tt]], bar, c, gx0[w] * p.stride + p.tap_dx[tt], gy0[w] * p.stride + p.tap_dy[tt], n_img[w]);
+                                        tma_load_4d_2sm(a_dst, maps[p.tap_map[tt]], bar, c, gx0[w] + p.tap_dx[tt], gy0[w] + p.tap_dy[tt], n_img[w]);
                                     } else {
                                         mbar_arrive_expect_tx(bar, (uint32_t)A_STAGE_BYTES);
-                                        tma_load_4d(a_dst, maps[p.tap_map[tt]], bar, c, gx0[w] * p.stride + p.tap_dx[tt], gy0[w] * p.stride + p.tap_dy[tt], n_img[w]);
+                                        tma_load_4d(a_dst, maps[p.tap_map[tt]], bar, c, gx0[w] + p.tap_dx[tt], gy0[w] + p.tap_dy[tt], n_img[w]);
                                     }
                                 }
                             } else if (elect_one()) {
@@ -1042,7 +1042,6 @@ conv_umma_kernel(const UmmaParams P, const __grid_constant__ CUtensorMap map_w,
 
 int g_umma_debug = 0;
 
-int g_tma_stride2 = 1;      // HOIG_UMMA_TMA_STRIDE2: stride-2 convs on the TMA-fed path (element-strided tensor map) instead of the gather producers
 int g_st256 = 7;            // HOIG_UMMA_ST256 (bit mask): 256-bit epilogue stores in 1 = the FAST kernels, 2 = the general epilogue, 4 = conv_halo
 int g_contig_mode = 1;      // HOIG_UMMA_CONTIG
 int g_fast_epi = 1;         // HOIG_UMMA_FAST_EPI: streamlined 32-column epilogue for plain convs
@@ -1108,9 +1107,8 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
 
     const int64_t npix = (int64_t)p.GH * p.GW;
     const bool rect = (p.GW % BM == 0) || (BM % p.GW == 0);
-    // (stride-2 convs: the tensor map walks the input with element strides 2, so a box still delivers one pixel per output pixel)
-    P.tma_a = (!force_gather && p.mode == HOIG_CONV && (p.stride == 1 || (p.stride == 2 && g_tma_stride2)) && p.C1 == 0 && p.C0 % 64 == 0 && rect &&
-               npix % BM == 0) ? 1 : 0;
+    // (stride-2 convs arrive here as stride-1 convs over four input-parity views, see conv_plan.cu)
+    P.tma_a = (!force_gather && p.mode == HOIG_CONV && p.stride == 1 && p.C1 == 0 && p.C0 % 64 == 0 && rect && npix % BM == 0) ? 1 : 0;
     if (P.tma_a)   // view strides must be 16-byte multiples for a tensor map
         for (int v = 0; v < p.nviews; ++v)
             if ((p.view[v].sx * 2) % 16 || ((uintptr_t)p.view[v].base % 16)) P.tma_a = 0;
@@ -1122,14 +1120,14 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     int ncta = (pair_ok && (g_pair_mode == 2 || (g_pair_mode == 1 && P.k_blocks >= 12))) ? 2 : 1;
     // Vertical-halo mode for the kh x 1 convs (7x7 stems / heads after re-association): single CTAs, resident weights
     const int vh_a_bytes = (VH_ROWS + p.kh - 1) * VH_COLS * 128;
-    P.vhalo = (g_vhalo_mode && g_pair_mode != 2 && P.tma_a && p.stride == 1 && p.nviews == 1 && p.kw == 1 && p.kh >= 2 && p.kh <= 8 && p.GW % VH_COLS == 0 &&
+    P.vhalo = (g_vhalo_mode && g_pair_mode != 2 && P.tma_a && p.nviews == 1 && p.kw == 1 && p.kh >= 2 && p.kh <= 8 && p.GW % VH_COLS == 0 &&
                p.GH % VH_ROWS == 0 && p.Cin % BK == 0 && P.n_tiles == 1 && p.Kpad == p.kh * p.Cin &&
                (size_t)P.k_blocks * P.BN * BK * 2 + 4 * (size_t)vh_a_bytes <= (size_t)RING_BUDGET) ? 1 : 0;
     P.tiles_x = P.vhalo ? p.GW / VH_COLS : 0;
     if (P.vhalo) ncta = 1;
     // Resident weights (single-CTA tiles, one n-tile): worth it when the whole matrix fits beside >= 4 activation stages
     // Row-halo mode: regular stride-1 kh x kw conv, tiles = 128 consecutive pixels of one image row
-    P.halo = (g_halo_mode && P.tma_a && p.stride == 1 && p.nviews == 1 && p.kw >= 2 && p.kw <= 7 && p.GW % BM == 0 && p.Cin % BK == 0) ? 1 : 0;
+    P.halo = (g_halo_mode && P.tma_a && p.nviews == 1 && p.kw >= 2 && p.kw <= 7 && p.GW % BM == 0 && p.Cin % BK == 0) ? 1 : 0;
     if (P.halo && RING_BUDGET / (A_HALO_BYTES + p.kw * (P.BN / ncta) * BK * 2) < 3) P.halo = 0;   // needs >= 3 stages of kw weight tiles
     P.k_steps = P.halo ? p.kh * (p.Cin / BK) : (P.vhalo ? p.Cin / BK : 0);
     const size_t w_bytes = (size_t)P.k_blocks * P.BN * BK * 2;
@@ -1187,14 +1185,12 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     if (P.tma_a) {
         const int bw = P.vhalo ? VH_COLS : P.halo ? BM + p.kw - 1 : (p.GW < BM ? p.GW : BM);
         const int bh = P.vhalo ? VH_ROWS + p.kh - 1 : P.halo ? 1 : BM / bw;
-        const cuuint32_t es = (cuuint32_t)p.stride;
-        const cuuint32_t box[4] = {BK, (cuuint32_t)bw * es, (cuuint32_t)bh * es, 1};
-        const cuuint32_t estr[4] = {1, es, es, 1};
+        const cuuint32_t box[4] = {BK, (cuuint32_t)bw, (cuuint32_t)bh, 1};
         for (int v = 0; v < p.nviews; ++v) {
             const InputView &vw = p.view[v];
             const cuuint64_t dims[4] = {(cuuint64_t)p.C0, (cuuint64_t)vw.W, (cuuint64_t)vw.H, (cuuint64_t)p.N};
             const cuuint64_t strides[3] = {(cuuint64_t)vw.sx * 2, (cuuint64_t)vw.sy * 2, (cuuint64_t)vw.sn * 2};
-            st = make_map(&map_a[v], vw.base, 4, dims, strides, box, "activations", dtype, estr);
+            st = make_map(&map_a[v], vw.base, 4, dims, strides, box, "activations", dtype);
             if (st != HOIG_OK) return st;
         }
     }
@@ -1214,8 +1210,8 @@ int launch_one(const ConvParams &cp, cudaStream_t stream, int force_gather, int 
     P.mma_stats = g_mma_stats == 2 ? 1 : (g_mma_stats == 1 ? (persist ? 1 : 0) : 0);
     // Streamlined epilogue (HOIG_UMMA_FAST_EPI; kernels instantiated with FAST): plain TMA-fed convs -- optional bias, no / ReLU activation,
     // optional statistics -- with whole 16-column chunks.  32-column chunks where every epilogue warp gets at least one (exactly one in
-    // PERSIST kernels).  Measured (batch 64, fp16): stem -10 %, 128->64 @256^2 -6 %, ConvT 128->64 -13 %, mlp_shared GEMMs -18..-27 %;
-    // the gather-mode stride-2 convs were 6 % slower with it and keep the general epilogue.
+    // PERSIST kernels).  Measured (batch 64, fp16): stem -10 %, 128->64 @256^2 -6 %, ConvT 128->64 -13 %, mlp_shared GEMMs -18..-27 %
+    // (and, with the 256-bit stores, stride-2 64->128 -12 %).
     P.fast_epi = 0;
     P.st256 = (g_st256 != 0 && !p.spade_x && p.ldd % 16 == 0 && reinterpret_cast<uintptr_t>(p.dst) % 32 == 0 &&
                (!p.residual || p.ldr % 8 == 0)) ? 1 : 0;     // also the general epilogue's full chunks
@@ -1277,8 +1273,6 @@ int conv2d_umma(const hoigConvDesc *d, cudaStream_t stream)
         if (bm) g_bres_mode = atoi(bm);
         const char *cm = getenv("HOIG_UMMA_CONTIG");
         if (cm) g_contig_mode = atoi(cm);
-        const char *t2 = getenv("HOIG_UMMA_TMA_STRIDE2");
-        if (t2) g_tma_stride2 = atoi(t2);
         const char *s2 = getenv("HOIG_UMMA_ST256");
         if (s2) g_st256 = atoi(s2);
         const char *fe = getenv("HOIG_UMMA_FAST_EPI");

@@ -279,15 +279,12 @@ EncodeTiledFn encode_fn()
     return fn;
 }
 
-// ``elem_strides`` (optional, one per dimension): traversal strides; a box of boxDim elements then delivers boxDim / stride of them
 int make_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
-             const cuuint32_t *box, const char *what, int dtype, const cuuint32_t *elem_strides = nullptr)
+             const cuuint32_t *box, const char *what, int dtype)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return HOIG_ERR_CUDA; }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    if (elem_strides)
-        for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
     const CUresult r = fn(map, dtype == HOIG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), dims, strides_bytes, box,
                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -268,7 +268,7 @@ CONV_CASES = [
     ("3x3_s2", 2, 32, 64, 128, 3, 2, "conv", dict(stats=True)),
     ("3x3_s2_c32_gather_views", 2, 16, 32, 64, 3, 2, "conv", dict(stats=True, bias=True)),
     ("3x3_s2_c256", 1, 64, 256, 512, 3, 2, "conv", dict(stats=True)),
-    ("3x3_s2_w256", 1, 256, 64, 128, 3, 2, "conv", dict(stats=True)),        # element-strided TMA boxes of the full 256 elements
+    ("3x3_s2_w256", 1, 256, 64, 128, 3, 2, "conv", dict(stats=True)),        # the 256 -> 128 stride-2 level: full-row tiles over the four parity views
     ("7x7_heads_merged_act_table", 1, 32, 128, 8, 7, 1, "conv", dict(act_table=[3, 3, 3, 4, 4, 3, 3, 3])),
     ("convT_3x3_s2_c512", 1, 32, 512, 256, 3, 2, "convT", dict(stats=True)),
     ("7x7_stem_c8", 2, 32, 8, 64, 7, 1, "conv", dict(stats=True)),
